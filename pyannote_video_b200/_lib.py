@@ -1,0 +1,112 @@
+"""ctypes binding of libpvb200.so (the sm_100a kernels behind this package).
+
+There is deliberately no CPU fallback: if the shared library is missing or a launch fails,
+the caller gets an exception (`PvError`).  The ABI is declared in include/pv_b200.h.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpvb200.so")
+
+PV_SR_MAX_TAPS = 9
+PV_SR_MAX_STAGES = 192
+
+
+class PvError(RuntimeError):
+    pass
+
+
+class PvSrStage(C.Structure):
+    _fields_ = [
+        ("a_row_off", C.c_int32),
+        ("b_row", C.c_int32),
+        ("a_col", C.c_int16),
+        ("cls", C.c_int16),
+        ("n_taps", C.c_int16),
+        ("use_tail", C.c_int16),
+        ("tap_rel", C.c_int16 * (PV_SR_MAX_TAPS + 1)),
+    ]
+
+
+class PvRowMap(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("cols", C.c_int32),
+        ("w", C.c_int32),
+        ("py", C.c_int32),
+        ("px", C.c_int32),
+        ("img", C.c_int64),
+        ("plane_rows", C.c_int64),
+    ]
+
+
+class PvSrgemmDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("x_rows", C.c_int64),
+        ("x_cols", C.c_int32),
+        ("n_out", C.c_int32),
+        ("n_classes", C.c_int32),
+        ("class_width", C.c_int32 * 2),
+        ("w_packed", C.c_void_p * 2),
+        ("w_rows", C.c_int64 * 2),
+        ("tail_rows", C.c_int32),
+        ("n_stages", C.c_int32),
+        ("stages", C.POINTER(PvSrStage)),
+        ("scale", C.c_void_p),
+        ("shift", C.c_void_p),
+        ("hq", C.c_int32),
+        ("wq", C.c_int32),
+        ("oh", C.c_int32),
+        ("ow", C.c_int32),
+        ("relu", C.c_int32),
+        ("out_mode", C.c_int32),
+        ("out", C.c_void_p),
+        ("dst", PvRowMap),
+        ("resid", C.c_void_p),
+        ("res", PvRowMap),
+        ("desc_mode", C.c_int32),
+        ("max_ctas", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load libpvb200.so (once).  Raises PvError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PvError(
+            "libpvb200.so not found at %s — run `python -c 'import __graft_entry__ as g; g.build()'`"
+            % LIB_PATH)
+    l = C.CDLL(LIB_PATH)
+    l.pv_last_error.restype = C.c_char_p
+    l.pv_launch_count.restype = C.c_int64
+    _lib = l
+    return l
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().pv_last_error().decode("utf-8", "replace")
+        raise PvError("%s failed (rc=%d): %s" % (what or "pv call", rc, msg))
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)"""
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return int(lib().pv_launch_count())

@@ -1,0 +1,463 @@
+// srgemm.cu — shifted-row GEMM on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the convolution arithmetic inside dlib's CNN face detector and
+// face_recognition_model_v1 that the reference reaches through
+// pyannote/video/face/face.py:66 and :74-75.  See include/pv_b200.h for the
+// contract and DESIGN.md §"srgemm" for the data layout.
+//
+// One persistent CTA per SM, 6 warps:
+//   warp 0  (1 lane)  TMA producer: A slabs (activation rows) + B tiles (weights) -> smem ring
+//   warp 1  (1 lane)  tcgen05.mma issuer, accumulators in TMEM (2 buffers of N columns)
+//   warps 2-5         epilogue: tcgen05.ld -> affine (+residual) (+ReLU) -> bf16 -> global
+#include <cuda.h>
+#include <atomic>
+#include <vector>
+#include "../../include/pv_b200.h"
+#include "pv_common.cuh"
+
+extern std::atomic<long long> g_pv_launches;
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxRing = 8;
+constexpr int kTileM = 128;
+
+struct SrParams {
+  CUtensorMap a_main[2];
+  CUtensorMap a_tail[2];
+  CUtensorMap b[2];
+  const PvSrStage* stages;
+  const float* scale;
+  const float* shift;
+  void* out;
+  const __nv_bfloat16* resid;
+  PvRowMap dst;
+  PvRowMap res;
+  long long q_rows;
+  int num_tiles;
+  int n_out, n_stages, n_ring, stage_bytes, a_bytes, tail_rows;
+  int cls_width[2];
+  int hq, wq, oh, ow, relu, out_mode, has_resid, desc_mode;
+  uint32_t tmem_cols;
+  int* err;
+};
+
+__device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint32_t y, uint32_t x) {
+  const uint32_t Y = y + m.py, X = x + m.px;
+  if (m.kind == 0) return (long long)n * m.img + (long long)Y * m.w + X;
+  const uint32_t plane = ((Y & 1u) << 1) | (X & 1u);
+  return (long long)plane * m.plane_rows + (long long)n * m.img + (long long)(Y >> 1) * m.w + (X >> 1);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_constant__ SrParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint8_t* ring = smem;
+  PvSrStage* s_stage = reinterpret_cast<PvSrStage*>(ring + (size_t)p.n_ring * p.stage_bytes);
+  float* s_scale = reinterpret_cast<float*>(s_stage + PV_SR_MAX_STAGES);
+  float* s_shift = s_scale + 256;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_shift + 256);
+  uint64_t* bar_empty = bar_full + kMaxRing;
+  uint64_t* bar_tfull = bar_empty + kMaxRing;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int N = p.n_out;
+
+  // ---- one-time setup -------------------------------------------------------
+  for (int i = threadIdx.x; i < p.n_stages * (int)(sizeof(PvSrStage) / 4); i += kThreads)
+    reinterpret_cast<uint32_t*>(s_stage)[i] = reinterpret_cast<const uint32_t*>(p.stages)[i];
+  for (int i = threadIdx.x; i < N; i += kThreads) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
+  if (warp == 0 && lane == 0) {
+    pv_tma_prefetch_desc(&p.a_main[0]);
+    pv_tma_prefetch_desc(&p.b[0]);
+    for (int i = 0; i < p.n_ring; ++i) {
+      pv_mbar_init(&bar_full[i], 1);
+      pv_mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      pv_mbar_init(&bar_tfull[i], 1);
+      pv_mbar_init(&bar_tempty[i], 4);
+    }
+    pv_fence_mbar_init();
+  }
+  if (warp == 1) pv_tmem_alloc(s_tmem, p.tmem_cols);
+  pv_tc_fence_before();
+  __syncthreads();
+  pv_tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const long long q0 = (long long)tile * kTileM;
+        for (int s = 0; s < p.n_stages; ++s) {
+          const PvSrStage& st = s_stage[s];
+          const int cls = st.cls;
+          const int rowb = p.cls_width[cls] * 2;
+          pv_mbar_wait(&bar_empty[slot], phase ^ 1u, p.err, 1);
+          uint8_t* a_dst = ring + (size_t)slot * p.stage_bytes;
+          uint8_t* b_dst = a_dst + p.a_bytes;
+          const int slab_rows = kTileM + (st.use_tail ? p.tail_rows : 0);
+          const uint32_t bytes = (uint32_t)(slab_rows * rowb + st.n_taps * N * rowb);
+          pv_mbar_arrive_expect_tx(&bar_full[slot], bytes);
+          const int32_t r0 = (int32_t)(q0 + st.a_row_off);
+          pv_tma_load_2d(a_dst, &p.a_main[cls], &bar_full[slot], st.a_col, r0);
+          if (st.use_tail)
+            pv_tma_load_2d(a_dst + kTileM * rowb, &p.a_tail[cls], &bar_full[slot], st.a_col, r0 + kTileM);
+          for (int t = 0; t < st.n_taps; ++t)
+            pv_tma_load_2d(b_dst + (size_t)t * N * rowb, &p.b[cls], &bar_full[slot], 0, st.b_row + t * N);
+          if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, M=128, N
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+                             ((uint32_t)(kTileM >> 4) << 24);
+      int slot = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        pv_mbar_wait(&bar_tempty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u, p.err, 2);
+        pv_tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * N);
+        uint32_t accum = 0;
+        for (int s = 0; s < p.n_stages; ++s) {
+          const PvSrStage& st = s_stage[s];
+          const int width = p.cls_width[st.cls];
+          const int rowb = width * 2;
+          const uint32_t ltype = (width == 64) ? 2u : (width == 32 ? 4u : 6u);
+          const uint32_t sbo = 8u * rowb;
+          pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
+          pv_tc_fence_after();
+          const uint32_t a_base = pv_smem_u32(ring + (size_t)slot * p.stage_bytes);
+          const uint32_t b_base = a_base + p.a_bytes;
+          const int ksteps = width >> 4;
+          for (int t = 0; t < st.n_taps; ++t) {
+            const uint32_t a_tap = a_base + (uint32_t)st.tap_rel[t] * rowb;
+            const uint32_t b_tap = b_base + (uint32_t)(t * N) * rowb;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t aa = a_tap + k * 32, bb = b_tap + k * 32;
+              const uint32_t boa = p.desc_mode ? ((aa >> 7) & 7u) : 0u;
+              const uint32_t bob = p.desc_mode ? ((bb >> 7) & 7u) : 0u;
+              pv_umma_bf16(tmem_d, pv_umma_desc(aa, sbo, ltype, boa), pv_umma_desc(bb, sbo, ltype, bob),
+                           idesc, accum);
+              accum = 1;
+            }
+          }
+          pv_umma_commit(&bar_empty[slot]);  // frees the smem slot once these MMAs retire
+          if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
+        }
+        pv_umma_commit(&bar_tfull[buf]);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32)
+    const int m = quarter * 32 + lane;
+    const uint32_t img = (uint32_t)p.hq * (uint32_t)p.wq;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const long long q = (long long)tile * kTileM + m;
+      bool valid = q < p.q_rows;
+      const uint32_t n = (uint32_t)(q / img);
+      const uint32_t rem = (uint32_t)(q - (long long)n * img);
+      const uint32_t y = rem / (uint32_t)p.wq;
+      const uint32_t x = rem - y * (uint32_t)p.wq;
+      valid = valid && (y < (uint32_t)p.oh) && (x < (uint32_t)p.ow);
+      const long long drow = row_of(p.dst, n, y, x);
+      const long long rrow = p.has_resid ? row_of(p.res, n, y, x) : 0;
+
+      pv_mbar_wait(&bar_tfull[buf], ((uint32_t)it >> 1) & 1u, p.err, 4);
+      pv_tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N);
+
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        pv_tmem_ld16(taddr + c0, v);
+        pv_tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[c0 + j], s_shift[c0 + j]);
+          if (p.has_resid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + rrow * p.res.cols + c0);
+            uint4 r0 = rp[0], r1 = rp[1];
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+              f[2 * j] += __bfloat162float(h.x);
+              f[2 * j + 1] += __bfloat162float(h.y);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.out_mode == 0) {
+            uint4 o0, o1;
+            o0.x = pv_pack_bf16x2(f[0], f[1]);
+            o0.y = pv_pack_bf16x2(f[2], f[3]);
+            o0.z = pv_pack_bf16x2(f[4], f[5]);
+            o0.w = pv_pack_bf16x2(f[6], f[7]);
+            o1.x = pv_pack_bf16x2(f[8], f[9]);
+            o1.y = pv_pack_bf16x2(f[10], f[11]);
+            o1.z = pv_pack_bf16x2(f[12], f[13]);
+            o1.w = pv_pack_bf16x2(f[14], f[15]);
+            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + drow * p.dst.cols + c0);
+            dp[0] = o0;
+            dp[1] = o1;
+          } else if (c0 == 0) {
+            reinterpret_cast<float*>(p.out)[drow] = f[0];
+          }
+        }
+      }
+      pv_tc_fence_before();
+      __syncwarp();
+      if (lane == 0) pv_mbar_arrive(&bar_tempty[buf]);
+    }
+  }
+
+  // ---- teardown ----------------------------------------------------------------
+  pv_tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    pv_tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+              uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    pv_set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return PV_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = box_cols == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                           : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    pv_set_error("cuTensorMapEncodeTiled failed: CUresult %d (cols=%llu rows=%llu box=%ux%u)", (int)r,
+                 (unsigned long long)cols, (unsigned long long)rows, box_cols, box_rows);
+    return PV_ERR_CUDA;
+  }
+  return PV_OK;
+}
+
+struct SrPlan {
+  SrParams p;
+  PvSrStage* d_stages = nullptr;
+  int* d_err = nullptr;
+  size_t smem_bytes = 0;
+  long long q_cap = 0;
+  int num_sms = 0;
+  int max_ctas = 0;
+};
+
+}  // namespace
+
+extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
+  PV_REQUIRE(d && out_handle, "pv_srgemm_create: null argument");
+  PV_REQUIRE(d->n_out >= 16 && d->n_out <= 256 && d->n_out % 16 == 0, "srgemm: n_out=%d must be a multiple of 16 in [16,256]", d->n_out);
+  PV_REQUIRE(d->n_classes == 1 || d->n_classes == 2, "srgemm: n_classes=%d", d->n_classes);
+  PV_REQUIRE(d->n_stages >= 1 && d->n_stages <= PV_SR_MAX_STAGES, "srgemm: n_stages=%d out of range", d->n_stages);
+  PV_REQUIRE(d->tail_rows >= 0 && d->tail_rows <= 128 && d->tail_rows % 8 == 0, "srgemm: tail_rows=%d", d->tail_rows);
+  PV_REQUIRE(d->x_cols % 8 == 0 && d->x_cols >= 16, "srgemm: x_cols=%d must be a multiple of 8", d->x_cols);
+  PV_REQUIRE(d->x_rows > 0 && d->x_rows < (1ll << 31), "srgemm: x_rows=%lld out of range", (long long)d->x_rows);
+  PV_REQUIRE(d->hq > 0 && d->wq > 0 && d->oh > 0 && d->ow > 0, "srgemm: bad grid");
+  PV_REQUIRE(d->out_mode == 0 || d->out_mode == 2, "srgemm: out_mode=%d", d->out_mode);
+  PV_REQUIRE(d->x && d->out && d->scale && d->shift && d->stages, "srgemm: null operand");
+  int maxw = 0;
+  for (int c = 0; c < d->n_classes; ++c) {
+    const int w = d->class_width[c];
+    PV_REQUIRE(w == 16 || w == 32 || w == 64, "srgemm: class_width[%d]=%d", c, w);
+    PV_REQUIRE(d->w_packed[c] && d->w_rows[c] > 0, "srgemm: missing weights for class %d", c);
+    if (w > maxw) maxw = w;
+  }
+  if (d->out_mode == 0) {
+    PV_REQUIRE(d->dst.cols % 8 == 0 && d->dst.cols >= d->n_out, "srgemm: dst.cols=%d < n_out=%d", d->dst.cols, d->n_out);
+  }
+  if (d->resid) PV_REQUIRE(d->res.cols % 8 == 0 && d->res.cols >= d->n_out, "srgemm: res.cols=%d", d->res.cols);
+
+  int b_bytes = 0;
+  for (int s = 0; s < d->n_stages; ++s) {
+    const PvSrStage& st = d->stages[s];
+    PV_REQUIRE(st.cls >= 0 && st.cls < d->n_classes, "srgemm: stage %d class %d", s, st.cls);
+    PV_REQUIRE(st.n_taps >= 1 && st.n_taps <= PV_SR_MAX_TAPS, "srgemm: stage %d n_taps %d", s, st.n_taps);
+    const int w = d->class_width[st.cls];
+    PV_REQUIRE(st.a_col >= 0 && st.a_col + w <= d->x_cols, "srgemm: stage %d column segment out of range", s);
+    for (int t = 0; t < st.n_taps; ++t) {
+      const int rel = st.tap_rel[t];
+      PV_REQUIRE(rel >= 0 && rel <= (st.use_tail ? d->tail_rows : 0), "srgemm: stage %d tap %d rel %d outside slab", s, t, rel);
+    }
+    PV_REQUIRE(st.b_row >= 0 && (long long)st.b_row + (long long)st.n_taps * d->n_out <= d->w_rows[st.cls], "srgemm: stage %d weights out of range", s);
+    const int bb = st.n_taps * d->n_out * w * 2;
+    if (bb > b_bytes) b_bytes = bb;
+  }
+  const int a_bytes = (((kTileM + d->tail_rows) * maxw * 2) + 1023) & ~1023;
+  b_bytes = (b_bytes + 1023) & ~1023;
+  const int stage_bytes = a_bytes + b_bytes;
+  const size_t fixed = sizeof(PvSrStage) * PV_SR_MAX_STAGES + 2 * 256 * sizeof(float) + (2 * kMaxRing + 4) * sizeof(uint64_t) + 16;
+  const size_t budget = 227 * 1024 - 1024 - fixed;
+  int n_ring = (int)(budget / stage_bytes);
+  if (n_ring > kMaxRing) n_ring = kMaxRing;
+  PV_REQUIRE(n_ring >= 2, "srgemm: stage of %d bytes does not fit a 2-deep ring", stage_bytes);
+
+  SrPlan* plan = new SrPlan();
+  memset(&plan->p, 0, sizeof(SrParams));
+  SrParams& p = plan->p;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&plan->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) {
+    pv_set_error("pv_srgemm_create: no CUDA device: %s", cudaGetErrorString(e));
+    delete plan;
+    return PV_ERR_CUDA;
+  }
+  plan->max_ctas = d->max_ctas > 0 ? d->max_ctas : plan->num_sms;
+
+  int rc = PV_OK;
+  for (int c = 0; c < d->n_classes && rc == PV_OK; ++c) {
+    const int w = d->class_width[c];
+    rc = encode_2d(&p.a_main[c], d->x, d->x_cols, d->x_rows, w, kTileM);
+    if (rc == PV_OK && d->tail_rows > 0) rc = encode_2d(&p.a_tail[c], d->x, d->x_cols, d->x_rows, w, d->tail_rows);
+    if (rc == PV_OK) rc = encode_2d(&p.b[c], d->w_packed[c], w, d->w_rows[c], w, d->n_out);
+  }
+  if (rc != PV_OK) {
+    delete plan;
+    return rc;
+  }
+  if (cudaMalloc(&plan->d_stages, sizeof(PvSrStage) * d->n_stages) != cudaSuccess ||
+      cudaMalloc(&plan->d_err, sizeof(int)) != cudaSuccess) {
+    pv_set_error("pv_srgemm_create: cudaMalloc failed");
+    delete plan;
+    return PV_ERR_CUDA;
+  }
+  cudaMemcpy(plan->d_stages, d->stages, sizeof(PvSrStage) * d->n_stages, cudaMemcpyHostToDevice);
+  cudaMemset(plan->d_err, 0, sizeof(int));
+
+  p.stages = plan->d_stages;
+  p.scale = d->scale;
+  p.shift = d->shift;
+  p.out = d->out;
+  p.resid = reinterpret_cast<const __nv_bfloat16*>(d->resid);
+  p.dst = d->dst;
+  p.res = d->res;
+  p.n_out = d->n_out;
+  p.n_stages = d->n_stages;
+  p.n_ring = n_ring;
+  p.stage_bytes = stage_bytes;
+  p.a_bytes = a_bytes;
+  p.tail_rows = d->tail_rows;
+  p.cls_width[0] = d->class_width[0];
+  p.cls_width[1] = d->n_classes > 1 ? d->class_width[1] : d->class_width[0];
+  p.hq = d->hq;
+  p.wq = d->wq;
+  p.oh = d->oh;
+  p.ow = d->ow;
+  p.relu = d->relu;
+  p.out_mode = d->out_mode;
+  p.has_resid = d->resid != nullptr;
+  p.desc_mode = d->desc_mode;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * d->n_out)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.err = plan->d_err;
+  plan->smem_bytes = (size_t)n_ring * stage_bytes + fixed + 1024;
+  plan->q_cap = d->x_rows;
+
+  e = cudaFuncSetAttribute(srgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+  if (e != cudaSuccess) {
+    pv_set_error("pv_srgemm_create: cudaFuncSetAttribute(%zu B smem): %s", plan->smem_bytes, cudaGetErrorString(e));
+    cudaFree(plan->d_stages);
+    cudaFree(plan->d_err);
+    delete plan;
+    return PV_ERR_CUDA;
+  }
+  *out_handle = plan;
+  return PV_OK;
+}
+
+extern "C" int pv_srgemm_run(void* handle, int64_t q_rows, void* stream) {
+  PV_REQUIRE(handle, "pv_srgemm_run: null handle");
+  SrPlan* plan = static_cast<SrPlan*>(handle);
+  PV_REQUIRE(q_rows > 0 && q_rows < (1ll << 31), "pv_srgemm_run: q_rows=%lld", (long long)q_rows);
+  SrParams p = plan->p;
+  p.q_rows = q_rows;
+  p.num_tiles = (int)((q_rows + kTileM - 1) / kTileM);
+  int grid = p.num_tiles < plan->max_ctas ? p.num_tiles : plan->max_ctas;
+  srgemm_kernel<<<grid, kThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_srgemm_check(void* handle, void* stream) {
+  PV_REQUIRE(handle, "pv_srgemm_check: null handle");
+  SrPlan* plan = static_cast<SrPlan*>(handle);
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  int flag = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&flag, plan->d_err, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    pv_set_error("pv_srgemm_check: %s", cudaGetErrorString(e));
+    return PV_ERR_CUDA;
+  }
+  if (flag != 0) {
+    pv_set_error("srgemm: device-side pipeline timeout (role code %d)", flag);
+    cudaMemset(plan->d_err, 0, sizeof(int));
+    return PV_ERR_DEVICE_TIMEOUT;
+  }
+  return PV_OK;
+}
+
+extern "C" int pv_srgemm_destroy(void* handle) {
+  if (!handle) return PV_OK;
+  SrPlan* plan = static_cast<SrPlan*>(handle);
+  cudaFree(plan->d_stages);
+  cudaFree(plan->d_err);
+  delete plan;
+  return PV_OK;
+}

@@ -1,0 +1,92 @@
+"""CPU: conv -> srgemm tap tables reproduce torch conv2d through the kernel emulator."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from pyannote_video_b200.plan import ConvPlan, RowLayout
+from srgemm_emu import emulate
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("group", ["tap", "row", "all"])
+@pytest.mark.parametrize("cin,cout,k,pad", [(32, 32, 3, 1), (48, 45, 5, 2), (16, 32, 3, 1), (64, 64, 3, 1), (48, 1, 9, 4)])
+def test_stride1_padded(group, cin, cout, k, pad):
+    torch.manual_seed(0)
+    B, H, W = 2, 11, 13
+    x = _bf(torch.randn(B, H, W, cin))
+    w = _bf(torch.randn(cout, cin, k, k) * 0.1)
+    lin = RowLayout("padded", B, H, W, cin, pad=pad)
+    cp = ConvPlan(lin, w, 1, pad, group=group)
+    lout = RowLayout("padded", B, cp.OH, cp.OW, cp.N, pad=1)
+    out = torch.zeros(lout.rows, lout.cols, dtype=torch.bfloat16)
+    scale = torch.rand(cout) + 0.5
+    shift = torch.randn(cout)
+    emulate(cp, lin.to_rows(x), out, lout, scale, shift, relu=True)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, padding=pad) * scale[None, :, None, None] + shift[None, :, None, None]
+    ref = torch.relu(ref).permute(0, 2, 3, 1)
+    got = lout.from_rows(out, C=cout)
+    assert torch.allclose(got, ref, atol=2e-2, rtol=2e-2)
+    # border stays zero
+    full = out.float().reshape(B, lout.Hq, lout.Wq, -1)
+    assert full[:, 0].abs().max() == 0 and full[:, :, 0].abs().max() == 0
+
+
+@pytest.mark.parametrize("group", ["tap", "row"])
+@pytest.mark.parametrize("cin,cout,k,H,W", [(16, 32, 5, 21, 18), (32, 64, 3, 17, 17), (128, 256, 3, 8, 8), (256, 256, 3, 4, 4)])
+def test_stride2_parity(group, cin, cout, k, H, W):
+    torch.manual_seed(1)
+    B = 2
+    x = _bf(torch.randn(B, H, W, cin))
+    w = _bf(torch.randn(cout, cin, k, k) * 0.1)
+    lin = RowLayout("parity", B, H, W, cin, pad=0)
+    cp = ConvPlan(lin, w, 2, 0, group=group)
+    lout = RowLayout("parity", B, cp.OH, cp.OW, cp.N, pad=0)
+    out = torch.zeros(lout.rows, lout.cols, dtype=torch.bfloat16)
+    scale = torch.ones(cout)
+    shift = torch.zeros(cout)
+    emulate(cp, lin.to_rows(x), out, lout, scale, shift, relu=False)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, stride=2).permute(0, 2, 3, 1)
+    got = lout.from_rows(out, C=cout)
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, atol=3e-2, rtol=3e-2)
+
+
+@pytest.mark.parametrize("k,cout,H,W", [(5, 16, 23, 30), (7, 32, 150, 150)])
+def test_stride2_gathered_first_layer(k, cout, H, W):
+    torch.manual_seed(2)
+    B = 2
+    x = _bf(torch.randn(B, H, W, 3))
+    w = _bf(torch.randn(cout, 3, k, k) * 0.1)
+    lin = RowLayout("gathered", B, H, W, 3, kw=k)
+    cp = ConvPlan(lin, w, 2, 0, group="tap")
+    lout = RowLayout("padded", B, cp.OH, cp.OW, cp.N, pad=0)
+    out = torch.zeros(lout.rows, lout.cols, dtype=torch.bfloat16)
+    emulate(cp, lin.to_rows(x), out, lout, torch.ones(cout), torch.zeros(cout), relu=False)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, stride=2).permute(0, 2, 3, 1)
+    got = lout.from_rows(out, C=cout)
+    assert torch.allclose(got, ref, atol=3e-2, rtol=3e-2)
+
+
+def test_residual_and_f32_out():
+    torch.manual_seed(3)
+    B, H, W, C = 1, 6, 7, 32
+    x = _bf(torch.randn(B, H, W, C))
+    w = _bf(torch.randn(C, C, 3, 3) * 0.1)
+    lin = RowLayout("padded", B, H, W, C, pad=1)
+    cp = ConvPlan(lin, w, 1, 1, group="row")
+    lout = RowLayout("parity", B, H, W, C, pad=0)
+    out = torch.zeros(lout.rows, lout.cols, dtype=torch.bfloat16)
+    xr = lin.to_rows(x)
+    emulate(cp, xr, out, lout, torch.ones(C), torch.zeros(C), relu=True, resid=xr, lres=lin)
+    ref = torch.relu(F.conv2d(x.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1) + x)
+    assert torch.allclose(lout.from_rows(out), ref, atol=3e-2, rtol=3e-2)
+    # f32 single-channel output
+    w1 = _bf(torch.randn(1, C, 3, 3) * 0.1)
+    cp1 = ConvPlan(lin, w1, 1, 1, group="tap")
+    o = torch.zeros(B, cp1.OH, cp1.OW)
+    emulate(cp1, xr, o, None, torch.ones(1), torch.zeros(1), relu=False, out_f32=True)
+    ref1 = F.conv2d(x.permute(0, 3, 1, 2), w1, padding=1)[:, 0]
+    assert torch.allclose(o, ref1, atol=1e-3, rtol=1e-3)
