@@ -1,0 +1,279 @@
+// detect.cu — input and output stages of the CNN (MMOD) face detector around the conv stack:
+//   resize_bilinear  dlib pyramid_up / pyramid_down<6> (resize_image + interpolate_bilinear) into the
+//                    tiled pyramid plane (RGBA u8, A = 255 inside tiles)
+//   det_candidates   score map -> compacted list of cells above adjust_threshold
+//   det_nms          loss_mmod::to_label: cells -> boxes in image space, sort by score, greedy NMS
+// Reference call site: face_detector_(rgb, 1), pyannote/video/face/face.py:66.
+// All float arithmetic uses explicitly rounded, unfused operations in the same order as
+// oracle/pyramid.py so results are bit-identical.
+#include <atomic>
+#include "../../include/pv_b200.h"
+#include "pv_common.cuh"
+
+extern std::atomic<long long> g_pv_launches;
+
+namespace {
+
+template <int SRC_CH>
+__global__ void resize_bilinear_kernel(const uint8_t* __restrict__ src, long long src_img_stride, int src_pitch_px,
+                                       int sx0, int sy0, int sw, int sh, uchar4* __restrict__ dst,
+                                       long long dst_img_stride, int dst_pitch_px, int dx0, int dy0, int dw, int dh,
+                                       float xs, float ys, int B, int copy_only) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * dw * dh;
+  if (idx >= total) return;
+  const int c = (int)(idx % dw);
+  long long r_ = idx / dw;
+  const int r = (int)(r_ % dh);
+  const int n = (int)(r_ / dh);
+  const uint8_t* s = src + (long long)n * src_img_stride;
+  uchar4 o;
+  o.w = 255;
+  if (copy_only) {
+    const uint8_t* p = s + ((long long)(sy0 + r) * src_pitch_px + sx0 + c) * SRC_CH;
+    o.x = p[0];
+    o.y = p[1];
+    o.z = p[2];
+  } else {
+    const float y = __fmul_rn((float)r, ys);
+    const float x = __fmul_rn((float)c, xs);
+    int top = (int)floorf(y), left = (int)floorf(x);
+    top = min(top, sh - 1);
+    left = min(left, sw - 1);
+    const int bot = min(top + 1, sh - 1), right = min(left + 1, sw - 1);
+    const float tb = __fsub_rn(y, (float)top), lr = __fsub_rn(x, (float)left);
+    const float omlr = __fsub_rn(1.0f, lr), omtb = __fsub_rn(1.0f, tb);
+    const uint8_t* ptl = s + ((long long)(sy0 + top) * src_pitch_px + sx0 + left) * SRC_CH;
+    const uint8_t* ptr_ = s + ((long long)(sy0 + top) * src_pitch_px + sx0 + right) * SRC_CH;
+    const uint8_t* pbl = s + ((long long)(sy0 + bot) * src_pitch_px + sx0 + left) * SRC_CH;
+    const uint8_t* pbr = s + ((long long)(sy0 + bot) * src_pitch_px + sx0 + right) * SRC_CH;
+    uint8_t res[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float a = __fadd_rn(__fmul_rn(omlr, (float)ptl[ch]), __fmul_rn(lr, (float)ptr_[ch]));
+      const float b = __fadd_rn(__fmul_rn(omlr, (float)pbl[ch]), __fmul_rn(lr, (float)pbr[ch]));
+      float v = __fadd_rn(__fmul_rn(omtb, a), __fmul_rn(tb, b));
+      v = floorf(__fadd_rn(v, 0.5f));
+      v = fminf(fmaxf(v, 0.f), 255.f);
+      res[ch] = (uint8_t)v;
+    }
+    o.x = res[0];
+    o.y = res[1];
+    o.z = res[2];
+  }
+  dst[(long long)n * dst_img_stride + (long long)(dy0 + r) * dst_pitch_px + dx0 + c] = o;
+}
+
+// ---- candidates -----------------------------------------------------------------------------
+__global__ void det_candidates_kernel(const float* __restrict__ scores, int B, int cells, float thr,
+                                      int* __restrict__ counts, float* __restrict__ cand_score,
+                                      int* __restrict__ cand_cell, int cap) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * cells) return;
+  const float s = scores[idx];
+  if (s > thr) {
+    const int n = (int)(idx / cells);
+    const int cell = (int)(idx - (long long)n * cells);
+    const int slot = atomicAdd(&counts[n], 1);
+    if (slot < cap) {
+      cand_score[(long long)n * cap + slot] = s;
+      cand_cell[(long long)n * cap + slot] = cell;
+    }
+  }
+}
+
+struct DetGeom {
+  int n_levels;
+  int window;
+  int ow;         // score-map width
+  int cell_mul;   // plane = cell * cell_mul + cell_add
+  int cell_add;
+  double iou_thresh, covered_thresh;
+};
+
+__device__ __forceinline__ long long rect_area(int l, int t, int r, int b) {
+  if (r < l || b < t) return 0;
+  return (long long)(r - l + 1) * (long long)(b - t + 1);
+}
+
+__device__ __forceinline__ bool boxes_overlap(const int4 a, const int4 b, double iou, double cov) {
+  const long long inner = rect_area(max(a.x, b.x), max(a.y, b.y), min(a.z, b.z), min(a.w, b.w));
+  if (inner == 0) return false;
+  const long long aa = rect_area(a.x, a.y, a.z, a.w), ab = rect_area(b.x, b.y, b.z, b.w);
+  const long long outer = aa + ab - inner;
+  if ((double)inner / (double)outer > iou) return true;
+  if ((double)inner / (double)aa > cov || (double)inner / (double)ab > cov) return true;
+  return false;
+}
+
+constexpr int kNmsCap = 4096;
+
+// one CTA per frame.  key = (score desc, cell asc) — the same total order as the oracle.
+__global__ void __launch_bounds__(1024) det_nms_kernel(const int* __restrict__ counts, const float* __restrict__ cand_score,
+                                                       const int* __restrict__ cand_cell, int cap,
+                                                       const int* __restrict__ rects,   // [L,4] x0,y0,w,h
+                                                       const float* __restrict__ fxy,   // [L,2]
+                                                       DetGeom g, int max_det, int* __restrict__ out_boxes,
+                                                       float* __restrict__ out_scores, int* __restrict__ out_counts) {
+  extern __shared__ uint8_t sm[];
+  float* s_score = reinterpret_cast<float*>(sm);
+  int* s_cell = reinterpret_cast<int*>(s_score + kNmsCap);
+  int4* s_box = reinterpret_cast<int4*>(s_cell + kNmsCap);
+  uint8_t* s_dead = reinterpret_cast<uint8_t*>(s_box + kNmsCap);
+  __shared__ int s_nkept;
+  const int n = blockIdx.x;
+  int cnt = counts[n];
+  if (cnt > cap || cnt > kNmsCap) {  // overflow: report, do not guess
+    if (threadIdx.x == 0) out_counts[n] = -cnt;
+    return;
+  }
+  int npow = 1;
+  while (npow < cnt) npow <<= 1;
+  for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+    if (i < cnt) {
+      s_score[i] = cand_score[(long long)n * cap + i];
+      s_cell[i] = cand_cell[(long long)n * cap + i];
+    } else {
+      s_score[i] = -INFINITY;
+      s_cell[i] = 0x7fffffff;
+    }
+  }
+  __syncthreads();
+  // bitonic sort: "a before b" iff score_a > score_b or (== and cell_a < cell_b)
+  for (int k = 2; k <= npow; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float sa = s_score[i], sb = s_score[ixj];
+          const int ca = s_cell[i], cb = s_cell[ixj];
+          const bool a_first = (sa > sb) || (sa == sb && ca < cb);
+          const bool up = ((i & k) == 0);
+          if (up ? !a_first : a_first) {
+            s_score[i] = sb; s_score[ixj] = sa;
+            s_cell[i] = cb; s_cell[ixj] = ca;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // boxes
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int cell = s_cell[i];
+    const int r = cell / g.ow, c = cell - r * g.ow;
+    const int px = c * g.cell_mul + g.cell_add, py = r * g.cell_mul + g.cell_add;
+    int lv = -1;
+    for (int L = 0; L < g.n_levels; ++L) {
+      const int x0 = rects[4 * L], y0 = rects[4 * L + 1], w = rects[4 * L + 2], h = rects[4 * L + 3];
+      if (px >= x0 && px < x0 + w && py >= y0 && py < y0 + h) { lv = L; break; }
+    }
+    if (lv < 0) {
+      s_dead[i] = 2;  // centre in padding: no box
+      s_box[i] = make_int4(0, 0, -1, -1);
+    } else {
+      const int l = px - g.window / 2 - rects[4 * lv], t = py - g.window / 2 - rects[4 * lv + 1];
+      const int rr = l + g.window - 1, bb = t + g.window - 1;
+      const float fx = fxy[2 * lv], fy = fxy[2 * lv + 1];
+      int4 b;
+      b.x = (int)floorf(__fadd_rn(__fmul_rn((float)l, fx), 0.5f));
+      b.y = (int)floorf(__fadd_rn(__fmul_rn((float)t, fy), 0.5f));
+      b.z = (int)floorf(__fadd_rn(__fmul_rn((float)rr, fx), 0.5f));
+      b.w = (int)floorf(__fadd_rn(__fmul_rn((float)bb, fy), 0.5f));
+      s_box[i] = b;
+      s_dead[i] = 0;
+    }
+  }
+  if (threadIdx.x == 0) s_nkept = 0;
+  __syncthreads();
+  // greedy NMS in sorted order
+  for (int i = 0; i < cnt; ++i) {
+    if (s_dead[i] == 0) {  // uniform across the CTA (read after the barrier below)
+      const int4 bi = s_box[i];
+      if (threadIdx.x == 0) {
+        const int k = s_nkept;
+        if (k < max_det) {
+          int* ob = out_boxes + ((long long)n * max_det + k) * 4;
+          ob[0] = bi.x; ob[1] = bi.y; ob[2] = bi.z; ob[3] = bi.w;
+          out_scores[(long long)n * max_det + k] = s_score[i];
+        }
+        s_nkept = k + 1;
+      }
+      for (int j = i + 1 + threadIdx.x; j < cnt; j += blockDim.x)
+        if (s_dead[j] == 0 && boxes_overlap(s_box[j], bi, g.iou_thresh, g.covered_thresh)) s_dead[j] = 1;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out_counts[n] = s_nkept;
+}
+
+}  // namespace
+
+extern "C" int pv_resize_bilinear(const void* src, int src_channels, int64_t src_img_stride, int src_pitch_px, int sx0,
+                                  int sy0, int sw, int sh, void* dst_rgba, int64_t dst_img_stride_px, int dst_pitch_px,
+                                  int dx0, int dy0, int dw, int dh, float xs, float ys, int B, int copy_only,
+                                  void* stream) {
+  PV_REQUIRE(src && dst_rgba, "pv_resize_bilinear: null argument");
+  PV_REQUIRE(src_channels == 3 || src_channels == 4, "pv_resize_bilinear: src_channels=%d", src_channels);
+  PV_REQUIRE(sw > 0 && sh > 0 && dw > 0 && dh > 0 && B > 0, "pv_resize_bilinear: empty rect");
+  const long long total = (long long)B * dw * dh;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (src_channels == 3)
+    resize_bilinear_kernel<3><<<blocks, threads, 0, s>>>(static_cast<const uint8_t*>(src), src_img_stride, src_pitch_px,
+                                                         sx0, sy0, sw, sh, static_cast<uchar4*>(dst_rgba),
+                                                         dst_img_stride_px, dst_pitch_px, dx0, dy0, dw, dh, xs, ys, B,
+                                                         copy_only);
+  else
+    resize_bilinear_kernel<4><<<blocks, threads, 0, s>>>(static_cast<const uint8_t*>(src), src_img_stride, src_pitch_px,
+                                                         sx0, sy0, sw, sh, static_cast<uchar4*>(dst_rgba),
+                                                         dst_img_stride_px, dst_pitch_px, dx0, dy0, dw, dh, xs, ys, B,
+                                                         copy_only);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_det_candidates(const float* scores, int B, int cells, float thr, int* counts, float* cand_score,
+                                 int* cand_cell, int cap, void* stream) {
+  PV_REQUIRE(scores && counts && cand_score && cand_cell, "pv_det_candidates: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PV_CUDA_CHECK(cudaMemsetAsync(counts, 0, sizeof(int) * B, s));
+  const long long total = (long long)B * cells;
+  const int threads = 256;
+  det_candidates_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(scores, B, cells, thr, counts,
+                                                                                       cand_score, cand_cell, cap);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_det_nms(const int* counts, const float* cand_score, const int* cand_cell, int cap, int B,
+                          const int* level_rects, const float* level_fxy, int n_levels, int window, int ow,
+                          int cell_mul, int cell_add, double iou_thresh, double covered_thresh, int max_det,
+                          int* out_boxes, float* out_scores, int* out_counts, void* stream) {
+  PV_REQUIRE(counts && cand_score && cand_cell && level_rects && level_fxy && out_boxes && out_scores && out_counts,
+             "pv_det_nms: null argument");
+  PV_REQUIRE(cap <= kNmsCap, "pv_det_nms: cap=%d exceeds %d", cap, kNmsCap);
+  DetGeom g;
+  g.n_levels = n_levels;
+  g.window = window;
+  g.ow = ow;
+  g.cell_mul = cell_mul;
+  g.cell_add = cell_add;
+  g.iou_thresh = iou_thresh;
+  g.covered_thresh = covered_thresh;
+  const size_t smem = kNmsCap * (sizeof(float) + sizeof(int) + sizeof(int4) + 1);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PV_CUDA_CHECK(cudaFuncSetAttribute(det_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  det_nms_kernel<<<B, 1024, smem, static_cast<cudaStream_t>(stream)>>>(counts, cand_score, cand_cell, cap, level_rects,
+                                                                      level_fxy, g, max_det, out_boxes, out_scores,
+                                                                      out_counts);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}

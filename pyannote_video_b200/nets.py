@@ -1,0 +1,267 @@
+"""Device-resident execution plans for the two CNNs on the path (host orchestration only).
+
+  DetectorNet  dlib CNN/MMOD face detector: tiled image pyramid -> 7 convs -> decode + NMS
+               (replaces face_detector_(rgb, 1), pyannote/video/face/face.py:66)
+  EmbedNet     dlib face_recognition_resnet_model_v1: 150x150 chip -> 29 convs -> 128-d
+               (replaces compute_face_descriptor, pyannote/video/face/face.py:74-75)
+
+Every convolution is one launch of the tcgen05 srgemm kernel with the dlib `affine` (frozen BN),
+bias, residual add and ReLU fused into its epilogue; the remaining layers are the small kernels of
+csrc/layers.cu and csrc/detect.cu.  All buffers are allocated once; nothing here touches the CPU
+oracle.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, config
+from . import weights as W
+from .plan import ConvPlan, RowLayout, Srgemm
+from .pyrgeom import pyramid_geometry, det_cell_to_plane
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _affine(c, affine=True):
+    g, b, be = _t(c["gamma"]).float(), _t(c["b"]).float(), _t(c["beta"]).float()
+    if affine:
+        return g, g * b + be
+    return torch.ones_like(b), b
+
+
+def _mean3():
+    return (C.c_float * 3)(*W.PIXEL_MEAN)
+
+
+class EmbedNet:
+    def __init__(self, model, max_batch, device, group=None, desc_mode=None):
+        if model.get("kind") != "resnet_v1_embedder":
+            raise RuntimeError("EmbedNet: not an embedder model")
+        group = config.SRGEMM_GROUP if group is None else group
+        desc_mode = config.SRGEMM_DESC_MODE if desc_mode is None else desc_mode
+        self.B = B = int(max_batch)
+        self.dev = device
+        S = W.EMB_CHIP
+        self.chips = torch.zeros(B, S, S, 4, dtype=torch.uint8, device=device)
+        self.ops = []          # (kind, payload)
+        self.flops_per_face = 0
+        # conv1 7x7 s2 on the gathered layout
+        lg = RowLayout("gathered", B, S, S, 3, kw=7)
+        self.lg, self.xg = lg, lg.alloc(device)
+        w1 = _t(model["conv1"]["w"])
+        cp = ConvPlan(lg, w1, 2, 0, group=group)
+        l1 = RowLayout("padded", B, cp.OH, cp.OW, 32, pad=0)
+        b1 = l1.alloc(device)
+        sc, sh = _affine(model["conv1"])
+        self._add_conv(cp, self.xg, b1, l1, sc, sh, True, None, None, desc_mode)
+        # max_pool 3x3 s2
+        H = (cp.OH - 3) // 2 + 1
+        blocks = model["blocks"]
+        lcur = RowLayout("parity" if blocks[0]["type"] == "ares_down" else "padded", B, H, H, 32,
+                         pad=0 if blocks[0]["type"] == "ares_down" else 1)
+        cur = lcur.alloc(device)
+        self.ops.append(("maxpool", (b1, cur, l1.H, l1.W, 32, lcur.rowmap())))
+        for i, blk in enumerate(blocks):
+            nxt = blocks[i + 1]["type"] if i + 1 < len(blocks) else None
+            ch = blk["a"]["w"].shape[0]
+            wa, wb = _t(blk["a"]["w"]), _t(blk["b"]["w"])
+            sca, sha = _affine(blk["a"])
+            scb, shb = _affine(blk["b"])
+
+            def out_layout(h, w):
+                if nxt is None:
+                    return RowLayout("padded", B, h, w, ch, pad=0)
+                if nxt == "ares_down":
+                    return RowLayout("parity", B, h, w, ch, pad=0)
+                return RowLayout("padded", B, h, w, ch, pad=1)
+
+            if blk["type"] == "ares":
+                assert lcur.kind == "padded" and lcur.pad == 1
+                la = RowLayout("padded", B, lcur.H, lcur.W, ch, pad=1)
+                t = la.alloc(device)
+                self._add_conv(ConvPlan(lcur, wa, 1, 1, group=group), cur, t, la, sca, sha, True, None, None, desc_mode)
+                lo = out_layout(lcur.H, lcur.W)
+                o = lo.alloc(device)
+                self._add_conv(ConvPlan(la, wb, 1, 1, group=group), t, o, lo, scb, shb, True, cur, lcur, desc_mode)
+            else:
+                assert lcur.kind == "parity" and lcur.pad == 0
+                cpa = ConvPlan(lcur, wa, 2, 0, group=group)
+                la = RowLayout("padded", B, cpa.OH, cpa.OW, ch, pad=1)
+                t = la.alloc(device)
+                self._add_conv(cpa, cur, t, la, sca, sha, True, None, None, desc_mode)
+                ph, pw = (lcur.H - 2) // 2 + 1, (lcur.W - 2) // 2 + 1
+                ho, wo = max(ph, cpa.OH), max(pw, cpa.OW)
+                assert (ho, wo) == (ph, pw)
+                lo = out_layout(ho, wo)
+                o = lo.alloc(device)
+                skip = lo.alloc(device)
+                self.ops.append(("avgpool", (cur, lcur, skip, o, ph, pw, ch, lo.rowmap())))
+                self._add_conv(ConvPlan(la, wb, 1, 1, group=group), t, o, lo, scb, shb, True, skip, lo, desc_mode)
+            cur, lcur = o, lo
+        assert lcur.kind == "padded" and lcur.pad == 0
+        self.fc = _t(model["fc"]).float().contiguous().to(device)
+        self.out = torch.zeros(B, W.EMB_DIM, dtype=torch.float32, device=device)
+        self.ops.append(("head", (cur, lcur.H * lcur.W, lcur.C)))
+        self.final_layout = lcur
+
+    def _add_conv(self, cp, x, out, lout, sc, sh, relu, resid, lres, desc_mode):
+        op = Srgemm(cp, x, out, lout, sc, sh, relu, resid=resid, lres=lres, desc_mode=desc_mode)
+        self.ops.append(("conv", (op, cp.lin.img)))
+        Cin = cp.lin.C if cp.lin.kind != "gathered" else 3
+        self.flops_per_face += 2 * cp.OH * cp.OW * cp.Cout * Cin * cp.KH * cp.KW
+
+    def forward_chips(self, M):
+        """Run the network on self.chips[:M] (RGBA u8).  Returns self.out[:M] (float32 [M,128])."""
+        assert 0 < M <= self.B
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        S = W.EMB_CHIP
+        _lib.check(L.pv_pack_gathered(_lib.ptr(self.chips), _lib.ptr(self.xg), M, S, S, 7,
+                                      C.c_int64(self.lg.plane_rows), _mean3(), st), "pv_pack_gathered")
+        for kind, a in self.ops:
+            if kind == "conv":
+                op, img = a
+                op.run(M * img)
+            elif kind == "maxpool":
+                src, dst, h, w, c, rm = a
+                _lib.check(L.pv_maxpool3x3s2(_lib.ptr(src), _lib.ptr(dst), M, h, w, c, C.byref(rm), st), "pv_maxpool3x3s2")
+            elif kind == "avgpool":
+                src, lsrc, skip, o, ph, pw, ch, rm = a
+                _lib.check(L.pv_avgpool_skip(_lib.ptr(src), lsrc.C, C.c_int64(lsrc.plane_rows), lsrc.Hq, lsrc.Wq,
+                                             _lib.ptr(skip), _lib.ptr(o), M, ph, pw, ch, C.byref(rm), st),
+                           "pv_avgpool_skip")
+            else:
+                src, hw, c = a
+                _lib.check(L.pv_embed_head(_lib.ptr(src), M, hw, c, _lib.ptr(self.fc), _lib.ptr(self.out),
+                                           W.EMB_DIM, st), "pv_embed_head")
+        return self.out[:M]
+
+    def check(self):
+        for kind, a in self.ops:
+            if kind == "conv":
+                a[0].check()
+
+
+class DetectorNet:
+    """Batched CNN detector for frames of one size."""
+
+    MAX_CAND = 4096
+    MAX_DET = 256
+
+    def __init__(self, model, H, W_, upsample, max_batch, device, group=None, desc_mode=None):
+        if model.get("kind") != "mmod_detector":
+            raise RuntimeError("DetectorNet: not a detector model")
+        group = config.SRGEMM_GROUP if group is None else group
+        desc_mode = config.SRGEMM_DESC_MODE if desc_mode is None else desc_mode
+        self.model = model
+        self.B = B = int(max_batch)
+        self.H, self.W, self.upsample, self.dev = H, W_, int(upsample), device
+        self.geo = geo = pyramid_geometry(H, W_, upsample)
+        Hp, Wp = geo.plane_h, geo.plane_w
+        self.plane = torch.zeros(B, Hp, Wp, 4, dtype=torch.uint8, device=device)
+        lg = RowLayout("gathered", B, Hp, Wp, 3, kw=5)
+        self.lg, self.xg = lg, lg.alloc(device)
+        self.convs = []
+        self.flops_per_frame = 0
+        convs = model["convs"]
+        lcur, cur = lg, self.xg
+        n = len(convs)
+        for i, c in enumerate(convs):
+            cout, cin, k, s = W.DET_CONVS[i]
+            pad = W.conv_pad(k, s)
+            cp = ConvPlan(lcur, _t(c["w"]), s, pad, group=group)
+            last = i == n - 1
+            sc, sh = _affine(c, affine=not last)
+            if last:
+                self.OH, self.OW = cp.OH, cp.OW
+                self.scores = torch.zeros(B, cp.OH, cp.OW, dtype=torch.float32, device=device)
+                op = Srgemm(cp, cur, self.scores, None, sc, sh, relu=False, out_f32=True, desc_mode=desc_mode)
+            else:
+                _, _, nk, ns = W.DET_CONVS[i + 1]
+                if ns == 2:
+                    lo = RowLayout("parity", B, cp.OH, cp.OW, cp.N, pad=0)
+                else:
+                    lo = RowLayout("padded", B, cp.OH, cp.OW, cp.N, pad=W.conv_pad(nk, ns))
+                o = lo.alloc(device)
+                op = Srgemm(cp, cur, o, lo, sc, sh, relu=True, desc_mode=desc_mode)
+            self.convs.append((op, cp.lin.img))
+            self.flops_per_frame += 2 * cp.OH * cp.OW * cout * cin * k * k
+            if not last:
+                lcur, cur = lo, o
+        rects, fxy = geo.level_table()
+        self.level_rects = _t(rects).to(device)
+        self.level_fxy = _t(fxy).to(device)
+        self.counts = torch.zeros(B, dtype=torch.int32, device=device)
+        self.cand_score = torch.zeros(B, self.MAX_CAND, dtype=torch.float32, device=device)
+        self.cand_cell = torch.zeros(B, self.MAX_CAND, dtype=torch.int32, device=device)
+        self.out_boxes = torch.zeros(B, self.MAX_DET, 4, dtype=torch.int32, device=device)
+        self.out_scores = torch.zeros(B, self.MAX_DET, dtype=torch.float32, device=device)
+        self.out_counts = torch.zeros(B, dtype=torch.int32, device=device)
+        cm, ca = det_cell_to_plane(1, 1)[0] - det_cell_to_plane(0, 0)[0], det_cell_to_plane(0, 0)[0]
+        self.cell_mul, self.cell_add = cm, ca
+
+    def build_plane(self, frames, M):
+        """frames: uint8 [M,H,W,3] device tensor -> tiled pyramid plane (RGBA u8)."""
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        geo = self.geo
+        Hp, Wp = geo.plane_h, geo.plane_w
+        f32 = np.float32
+        prev = None
+        for lv, (x0, y0, w, h) in enumerate(geo.rects):
+            if lv == 0:
+                sw, sh = self.W, self.H
+                xs = float(f32(sw - 1) / f32(max(w - 1, 1)))
+                ys = float(f32(sh - 1) / f32(max(h - 1, 1)))
+                _lib.check(L.pv_resize_bilinear(_lib.ptr(frames), 3, C.c_int64(self.H * self.W * 3), self.W, 0, 0, sw, sh,
+                                                _lib.ptr(self.plane), C.c_int64(Hp * Wp), Wp, x0, y0, w, h,
+                                                C.c_float(xs), C.c_float(ys), M, 0 if self.upsample else 1, st),
+                           "pv_resize_bilinear")
+            else:
+                px0, py0, pw, ph = prev
+                xs = float(f32(pw - 1) / f32(max(w - 1, 1)))
+                ys = float(f32(ph - 1) / f32(max(h - 1, 1)))
+                _lib.check(L.pv_resize_bilinear(_lib.ptr(self.plane), 4, C.c_int64(Hp * Wp * 4), Wp, px0, py0, pw, ph,
+                                                _lib.ptr(self.plane), C.c_int64(Hp * Wp), Wp, x0, y0, w, h,
+                                                C.c_float(xs), C.c_float(ys), M, 0, st), "pv_resize_bilinear")
+            prev = (x0, y0, w, h)
+
+    def forward_scores(self, M):
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        geo = self.geo
+        _lib.check(L.pv_pack_gathered(_lib.ptr(self.plane), _lib.ptr(self.xg), M, geo.plane_h, geo.plane_w, 5,
+                                      C.c_int64(self.lg.plane_rows), _mean3(), st), "pv_pack_gathered")
+        for op, img in self.convs:
+            op.run(M * img)
+        return self.scores[:M]
+
+    def decode(self, M):
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        m = self.model
+        _lib.check(L.pv_det_candidates(_lib.ptr(self.scores), M, self.OH * self.OW, C.c_float(float(m["adjust_threshold"])),
+                                       _lib.ptr(self.counts), _lib.ptr(self.cand_score), _lib.ptr(self.cand_cell),
+                                       self.MAX_CAND, st), "pv_det_candidates")
+        _lib.check(L.pv_det_nms(_lib.ptr(self.counts), _lib.ptr(self.cand_score), _lib.ptr(self.cand_cell), self.MAX_CAND,
+                                M, _lib.ptr(self.level_rects), _lib.ptr(self.level_fxy), self.geo.n_levels,
+                                int(m["window"]), self.OW, self.cell_mul, self.cell_add,
+                                C.c_double(float(m["iou_thresh"])), C.c_double(float(m["covered_thresh"])), self.MAX_DET,
+                                _lib.ptr(self.out_boxes), _lib.ptr(self.out_scores), _lib.ptr(self.out_counts), st),
+                   "pv_det_nms")
+        return self.out_boxes[:M], self.out_scores[:M], self.out_counts[:M]
+
+    def detect(self, frames):
+        """frames uint8 [M,H,W,3] (device).  Returns (boxes int32 [M,MAX_DET,4], scores, counts) on device."""
+        M = frames.shape[0]
+        assert M <= self.B and frames.shape[1:] == (self.H, self.W, 3) and frames.dtype == torch.uint8
+        self.build_plane(frames.contiguous(), M)
+        self.forward_scores(M)
+        return self.decode(M)
+
+    def check(self):
+        for op, _ in self.convs:
+            op.check()

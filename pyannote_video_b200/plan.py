@@ -129,7 +129,7 @@ def _segments(kc):
 class ConvPlan:
     """Tap table + packed weights for one convolution over a RowLayout."""
 
-    def __init__(self, lin, weight, stride, pad, group="tap", max_b_bytes=96 * 1024):
+    def __init__(self, lin, weight, stride, pad, group="tap", max_b_bytes=40 * 1024):
         """weight: float tensor [Cout, Cin, KH, KW] (dlib/torch order), CPU."""
         Cout, Cin, KH, KW = weight.shape
         self.lin, self.stride, self.pad, self.KH, self.KW = lin, stride, pad, KH, KW

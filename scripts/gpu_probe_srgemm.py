@@ -72,17 +72,25 @@ def run_case(idx):
     op.run()
     op.check()
     if timing:
-        for _ in range(3):
-            op.run()
-        torch.cuda.synchronize()
+        import time as _t
+        t0 = _t.time()
+        while _t.time() - t0 < 0.4:      # let clocks ramp: >= 0.4 s of back-to-back launches
+            for _ in range(20):
+                op.run()
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
+        reps = 50
         e0.record()
         for _ in range(reps):
             op.run()
         e1.record()
+        for _ in range(200):
+            op.run()
+        smi = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw", "--format=csv,noheader"],
+                             capture_output=True, text=True).stdout.strip()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
+        res["smi"] = smi
         q = lin.plane_rows
         flops = 2.0 * q * cp.N * 16 * cp.mma_per_tile
         useful = 2.0 * B * cp.OH * cp.OW * cout * cin * k * k
@@ -109,11 +117,14 @@ def main():
         run_case(int(sys.argv[2]))
         return
     quick = "--quick" in sys.argv
+    only_timing = "--timing" in sys.argv
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     outp = os.path.join(ROOT, "gpurun_out", "probe_srgemm.jsonl")
     with open(outp, "a") as f:
         for i, c in enumerate(CASES):
             if quick and c[-1]:
+                continue
+            if only_timing and not c[-1]:
                 continue
             t0 = time.time()
             try:
