@@ -116,6 +116,71 @@ int pv_srgemm_destroy(void* handle);
 /* reads (and clears) the device-side error flag of a plan; 0 = none. Synchronises the stream. */
 int pv_srgemm_check(void* handle, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * first-layer packing and the small layers of the embedder (csrc/layers.cu)
+ * ------------------------------------------------------------------------------------------ */
+/* RGBA u8 [B,H,W,4] (A==0: pyramid padding) -> "gathered" bf16 rows for a kw x kw stride-2 first conv:
+ * out[ph*layout_plane_rows + (n*ceil(H/2)+i)*ceil(W/2)+j][k*3+c] = (img[n,2i+ph,2j+k,c]-mean[c])/256.
+ * dlib input_rgb_image(_pyramid/_sized)::to_tensor. kw = 5 (16 cols) or 7 (32 cols). mean_host: 3 floats (HOST). */
+int pv_pack_gathered(const void* rgba, void* out, int B, int H, int W, int kw, int64_t layout_plane_rows,
+                     const float* mean_host, void* stream);
+/* dlib max_pool<3,3,2,2> (pad 0) on bf16 NHWC [B,H,W,C] -> rows of `dst` */
+int pv_maxpool3x3s2(const void* in, void* out, int B, int H, int W, int C, const PvRowMap* dst, void* stream);
+/* dlib avg_pool<2,2,2,2> skip path of ares_down: parity-layout input -> skip (zero-extended to Cout)
+ * and relu(skip) pre-written into the block output */
+int pv_avgpool_skip(const void* in, int Cin, int64_t in_plane_rows, int in_hq, int in_wq, void* skip, void* out, int B,
+                    int OH, int OW, int Cout, const PvRowMap* dst, void* stream);
+/* avg_pool_everything + fc_no_bias<128>: bf16 [B,HW,C] -> float [B,D] */
+int pv_embed_head(const void* in, int B, int HW, int C, const float* fc, float* out, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * detector input/output stages (csrc/detect.cu) — dlib pyramid_up / pyramid_down<6> /
+ * loss_mmod::to_label around face_detector_(rgb, 1), pyannote/video/face/face.py:66
+ * ------------------------------------------------------------------------------------------ */
+/* bilinear resize (dlib resize_image + interpolate_bilinear) of a sub-rectangle of `src`
+ * (3 or 4 u8 channels) into a sub-rectangle of the RGBA plane; copy_only=1 copies 1:1. */
+int pv_resize_bilinear(const void* src, int src_channels, int64_t src_img_stride_bytes, int src_pitch_px, int sx0,
+                       int sy0, int sw, int sh, void* dst_rgba, int64_t dst_img_stride_px, int dst_pitch_px, int dx0,
+                       int dy0, int dw, int dh, float xs, float ys, int B, int copy_only, void* stream);
+/* cells of the score map above `thr` -> per-frame candidate lists (counts are zeroed first) */
+int pv_det_candidates(const float* scores, int B, int cells, float thr, int* counts, float* cand_score, int* cand_cell,
+                      int cap, void* stream);
+/* candidates -> boxes in image space (integer, inclusive), sorted by score, greedy NMS with
+ * dlib test_box_overlap(iou_thresh, covered_thresh); out_counts[n] < 0 reports candidate overflow */
+int pv_det_nms(const int* counts, const float* cand_score, const int* cand_cell, int cap, int B, const int* level_rects,
+               const float* level_fxy, int n_levels, int window, int ow, int cell_mul, int cell_add, double iou_thresh,
+               double covered_thresh, int max_det, int* out_boxes, float* out_scores, int* out_counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * landmarks and chips (csrc/landmarks.cu)
+ * ------------------------------------------------------------------------------------------ */
+/* dlib.shape_predictor (pyannote/video/face/face.py:58,70).  All model arrays are device pointers
+ * that must outlive the handle: initial_shape f32[136], anchor_idx i32[S,P], deltas f32[S,P,2],
+ * split_idx1/2 i32[S,T,15], split_thresh f32[S,T,15], leaf_values f32[S,T,16,136]. */
+int pv_ert_create(const float* initial_shape, const int* anchor_idx, const float* deltas, const int* split_idx1,
+                  const int* split_idx2, const float* split_thresh, const float* leaf_values, int stages, int trees,
+                  int pool, void** out_handle);
+int pv_ert_destroy(void* handle);
+/* frames u8 [F,H,W,3]; rects i32 [M,4] (l,t,r,b); frame_idx i32 [M] -> out_parts i32 [M,68,2] */
+int pv_ert_forward(void* handle, const void* frames, int H, int W, const int* rects, const int* frame_idx, int M,
+                   int* out_parts, void* stream);
+/* get_face_chip_details + extract_image_chip of compute_face_descriptor (face/face.py:74-75):
+ * parts i32 [M,68,2] -> RGBA u8 chips [M,size,size,4]; from_pts f32 [68,2] chip-space targets,
+ * pt_idx i32 [n_idx] the landmarks used for the similarity fit */
+int pv_chip_extract(const void* frames, int H, int W, const int* parts, const int* frame_idx, int M,
+                    const float* from_pts, const int* pt_idx, int n_idx, int size, void* out_rgba, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * clustering (csrc/cluster.cu) — pyannote/video/face/clustering.py:92-119,138-148
+ * ------------------------------------------------------------------------------------------ */
+/* D[i][j] = ||x_i - x_j|| (metric 0, scipy pdist 'euclidean') or 1 - cos (metric 1); X f32 [n,128] */
+int pv_pdist(const float* X, int64_t n, int dim, int metric, float* D, void* stream);
+/* S' = P S P^T in two passes; CSR (offs i32 [tout+1], memb i32) lists the old clusters of each new one */
+int pv_pool_rows(const float* S, int64_t tin, const int* offs, const int* memb, float* R, int64_t tout, void* stream);
+int pv_pool_cols(const float* R, int64_t tin, const int* offs, const int* memb, float* Sout, int64_t tout, void* stream);
+/* nearest cluster of every cluster under average linkage S[A][C]/(size_A*size_C) */
+int pv_row_argmin(const float* S, int64_t t, const float* sizes, int* nn, float* nnd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

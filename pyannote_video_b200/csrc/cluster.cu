@@ -1,0 +1,207 @@
+// cluster.cu — pairwise distances + average-linkage agglomeration over face-track embeddings.
+// Replaces _Model.compute_similarity_matrix / compute_similarity (scipy pdist + per-pair np.mean
+// + pyannote.algorithms greedy HAC), pyannote/video/face/clustering.py:92-119,138-148.
+//
+// The cluster-pair quantity kept on the device is the SUM of embedding distances between two
+// clusters, S[A][C] = sum_{i in A, j in C} d(i,j); average linkage = S / (|A||C|) and a merge is
+// S[A u B][C] = S[A][C] + S[B][C] (exact Lance-Williams for UPGMA).  One agglomeration round =
+//   row_argmin (nearest cluster of every cluster)  ->  host picks reciprocal pairs under the
+//   threshold  ->  pool_rows + pool_cols contract the matrix  (S' = P S P^T).
+// Average linkage is reducible, so merging all reciprocal-nearest pairs per round yields the same
+// partition at the threshold as the reference's one-pair-at-a-time greedy loop (absent ties).
+#include <atomic>
+#include "../../include/pv_b200.h"
+#include "pv_common.cuh"
+
+extern std::atomic<long long> g_pv_launches;
+
+namespace {
+
+constexpr int kDim = 128;
+constexpr int kTile = 64;
+
+// D[i][j] = metric(x_i, x_j); 64x64 output tile per CTA (256 threads, 4x4 outputs each),
+// operands staged through shared memory in fp32.  metric 0: Euclidean, 1: cosine distance.
+__global__ void __launch_bounds__(256) pdist_kernel(const float* __restrict__ X, long long n, float* __restrict__ D,
+                                                    int metric) {
+  constexpr int kHalf = 64;
+  __shared__ float sa[kTile][kHalf + 1];
+  __shared__ float sb[kTile][kHalf + 1];
+  const long long i0 = (long long)blockIdx.y * kTile, j0 = (long long)blockIdx.x * kTile;
+  const int tid = threadIdx.x;
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[4][4], na[4], nb[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    na[a] = nb[a] = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  }
+  for (int k0 = 0; k0 < kDim; k0 += kHalf) {
+    __syncthreads();
+    for (int e = tid; e < kTile * kHalf; e += 256) {
+      const int r = e / kHalf, c = e - r * kHalf;
+      sa[r][c] = (i0 + r < n) ? X[(i0 + r) * kDim + k0 + c] : 0.f;
+      sb[r][c] = (j0 + r < n) ? X[(j0 + r) * kDim + k0 + c] : 0.f;
+    }
+    __syncthreads();
+    for (int k = 0; k < kHalf; ++k) {
+      float va[4], vb[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        va[a] = sa[ty + 16 * a][k];
+        vb[a] = sb[tx + 16 * a][k];
+      }
+      if (metric == 0) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const float d = va[a] - vb[b];
+            acc[a][b] = fmaf(d, d, acc[a][b]);
+          }
+      } else {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          na[a] = fmaf(va[a], va[a], na[a]);
+          nb[a] = fmaf(vb[a], vb[a], nb[a]);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(va[a], vb[b], acc[a][b]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const long long i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
+      if (i < n && j < n) {
+        float v;
+        if (metric == 0)
+          v = sqrtf(acc[a][b]);
+        else
+          v = 1.f - acc[a][b] / fmaxf(sqrtf(na[a]) * sqrtf(nb[b]), 1e-30f);
+        if (i == j) v = 0.f;
+        D[i * n + j] = v;
+      }
+    }
+}
+
+// R[A][c] = sum_{a in members(A)} S[a][c]        (CSR: offs[A]..offs[A+1] into memb)
+__global__ void pool_rows_kernel(const float* __restrict__ S, long long tin, const int* __restrict__ offs,
+                                 const int* __restrict__ memb, float* __restrict__ R, long long tout) {
+  const long long A = blockIdx.y;
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (A >= tout || c >= tin) return;
+  float s = 0.f;
+  for (int k = offs[A]; k < offs[A + 1]; ++k) s += S[(long long)memb[k] * tin + c];
+  R[A * tin + c] = s;
+}
+
+// S'[A][C] = sum_{c in members(C)} R[A][c]
+__global__ void pool_cols_kernel(const float* __restrict__ R, long long tin, const int* __restrict__ offs,
+                                 const int* __restrict__ memb, float* __restrict__ Sout, long long tout) {
+  const long long A = blockIdx.y;
+  const long long Cc = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (A >= tout || Cc >= tout) return;
+  const float* row = R + A * tin;
+  float s = 0.f;
+  for (int k = offs[Cc]; k < offs[Cc + 1]; ++k) s += row[memb[k]];
+  Sout[A * tout + Cc] = s;
+}
+
+// nearest cluster of every cluster under average linkage: argmin_{C != A} S[A][C] / (size_A size_C);
+// one CTA per row, ties -> smallest index.
+__global__ void __launch_bounds__(256) row_argmin_kernel(const float* __restrict__ S, long long t,
+                                                         const float* __restrict__ sizes, int* __restrict__ nn,
+                                                         float* __restrict__ nnd) {
+  const long long A = blockIdx.x;
+  const float sa = sizes[A];
+  float best = INFINITY;
+  int bi = -1;
+  for (long long c = threadIdx.x; c < t; c += blockDim.x) {
+    if (c == A) continue;
+    const float v = S[A * t + c] / (sa * sizes[c]);
+    if (v < best || (v == best && (int)c < bi)) {
+      best = v;
+      bi = (int)c;
+    }
+  }
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const float v = sv[threadIdx.x + s];
+      const int i = si[threadIdx.x + s];
+      if (i >= 0 && (si[threadIdx.x] < 0 || v < sv[threadIdx.x] || (v == sv[threadIdx.x] && i < si[threadIdx.x]))) {
+        sv[threadIdx.x] = v;
+        si[threadIdx.x] = i;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    nn[A] = si[0];
+    nnd[A] = sv[0];
+  }
+}
+
+}  // namespace
+
+extern "C" int pv_pdist(const float* X, int64_t n, int dim, int metric, float* D, void* stream) {
+  PV_REQUIRE(X && D, "pv_pdist: null argument");
+  PV_REQUIRE(dim == kDim, "pv_pdist: dim=%d (must be 128)", dim);
+  PV_REQUIRE(metric == 0 || metric == 1, "pv_pdist: metric=%d", metric);
+  if (n == 0) return PV_OK;
+  const unsigned g = (unsigned)((n + kTile - 1) / kTile);
+  pdist_kernel<<<dim3(g, g), 256, 0, static_cast<cudaStream_t>(stream)>>>(X, n, D, metric);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_pool_rows(const float* S, int64_t tin, const int* offs, const int* memb, float* R, int64_t tout,
+                            void* stream) {
+  PV_REQUIRE(S && offs && memb && R, "pv_pool_rows: null argument");
+  if (tout == 0 || tin == 0) return PV_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long maxy = 65535;
+  for (long long a0 = 0; a0 < tout; a0 += maxy) {  // gridDim.y limit
+    const long long na = (tout - a0 < maxy) ? tout - a0 : maxy;
+    pool_rows_kernel<<<dim3((unsigned)((tin + 255) / 256), (unsigned)na), 256, 0, s>>>(S, tin, offs + a0, memb,
+                                                                                      R + a0 * tin, na);
+    g_pv_launches.fetch_add(1);
+  }
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_pool_cols(const float* R, int64_t tin, const int* offs, const int* memb, float* Sout, int64_t tout,
+                            void* stream) {
+  PV_REQUIRE(R && offs && memb && Sout, "pv_pool_cols: null argument");
+  if (tout == 0 || tin == 0) return PV_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long maxy = 65535;
+  for (long long a0 = 0; a0 < tout; a0 += maxy) {
+    const long long na = (tout - a0 < maxy) ? tout - a0 : maxy;
+    // rows a0..a0+na of the output; the column CSR is the full one
+    pool_cols_kernel<<<dim3((unsigned)((tout + 255) / 256), (unsigned)na), 256, 0, s>>>(R + a0 * tin, tin, offs, memb,
+                                                                                       Sout + a0 * tout, tout);
+    g_pv_launches.fetch_add(1);
+  }
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_row_argmin(const float* S, int64_t t, const float* sizes, int* nn, float* nnd, void* stream) {
+  PV_REQUIRE(S && sizes && nn && nnd, "pv_row_argmin: null argument");
+  if (t == 0) return PV_OK;
+  row_argmin_kernel<<<(unsigned)t, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, t, sizes, nn, nnd);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}

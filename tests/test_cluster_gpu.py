@@ -1,0 +1,81 @@
+"""GPU parity: pairwise distances and threshold-stopped average-linkage clustering against scipy
+(`pdist`, exactly what the reference calls, pyannote/video/face/clustering.py:101) and the greedy
+oracle.  Partitions are compared up to label permutation."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hac as ohac
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(seed, n_ids=9, tracks_per_id=4, emb_per_track=(1, 6), sigma=0.02, scale=0.5):
+    rng = np.random.default_rng(seed)
+    cent = rng.standard_normal((n_ids, 128)) * scale / np.sqrt(128) * 8
+    X, tr = [], []
+    t = 0
+    for c in cent:
+        for _ in range(tracks_per_id):
+            k = int(rng.integers(emb_per_track[0], emb_per_track[1] + 1))
+            X.append(c + sigma * rng.standard_normal((k, 128)))
+            tr += [t] * k
+            t += 1
+    X = np.concatenate(X)
+    perm = rng.permutation(len(X))
+    return X[perm].astype(np.float32), np.asarray(tr)[perm] * 3 + 7   # non-contiguous ids, shuffled rows
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_pdist_matches_scipy(cuda, metric):
+    from scipy.spatial.distance import pdist, squareform
+    from pyannote_video_b200 import _lib
+    X, _ = _data(0)
+    Xd = torch.from_numpy(X).to(cuda)
+    n = X.shape[0]
+    D = torch.empty(n, n, dtype=torch.float32, device=cuda)
+    _lib.check(_lib.lib().pv_pdist(_lib.ptr(Xd), C.c_int64(n), 128, 0 if metric == "euclidean" else 1, _lib.ptr(D),
+                                   _lib.stream_ptr()))
+    ref = squareform(pdist(X.astype(np.float64), metric=metric))
+    assert np.allclose(D.cpu().numpy(), ref, atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("seed,metric,thr", [(1, "euclidean", 0.6), (2, "euclidean", 0.6), (3, "cosine", 0.05)])
+def test_cluster_matches_greedy_oracle(cuda, seed, metric, thr):
+    from pyannote_video_b200.clustering import cluster
+    X, tr = _data(seed)
+    tracks, labels, stats = cluster(X, tr, threshold=thr, metric=metric, device=cuda, return_stats=True)
+    ref = ohac.greedy_hac(X.astype(np.float64), tr, threshold=thr, metric=metric)
+    got = {int(t): int(l) for t, l in zip(tracks, labels)}
+    assert ohac.partition_of(got) == ohac.partition_of(ref)
+    assert got == ref                                  # labels too: smallest track id of the cluster
+    assert 1 < stats["n_clusters"] < len(tracks)
+
+
+def test_cluster_singletons_large(cuda):
+    """size-independent property at a larger size: every merge the GPU made respects the cut, and
+    the partition equals scipy's average-linkage cut (independent oracle)."""
+    from scipy.cluster.hierarchy import linkage, fcluster
+    from pyannote_video_b200.clustering import cluster
+    rng = np.random.default_rng(9)
+    cent = rng.standard_normal((40, 128)) * 0.35
+    X = np.concatenate([c + 0.02 * rng.standard_normal((25, 128)) for c in cent]).astype(np.float32)
+    tracks, labels = cluster(X, np.arange(len(X)), threshold=0.6, device=cuda)
+    Z = fcluster(linkage(X.astype(np.float64), "average"), t=0.6, criterion="distance")
+    assert ohac.partition_of(dict(zip(tracks.tolist(), labels.tolist()))) == ohac.partition_of(dict(enumerate(Z.tolist())))
+
+
+def test_face_clustering_file_roundtrip(cuda, tmp_path):
+    from pyannote_video_b200.clustering import FaceClustering
+    X, tr = _data(4, n_ids=4, tracks_per_id=3, emb_per_track=(2, 4))
+    path = tmp_path / "emb.txt"
+    with open(path, "w") as f:
+        for i, (x, t) in enumerate(zip(X, tr)):
+            f.write("%.3f %d" % (0.04 * i, t) + "".join(" %.5f" % v for v in x) + "\n")
+    clustering = FaceClustering(threshold=0.6)
+    starting_point, features = clustering.model.preprocess(str(path))
+    result = clustering(starting_point, features=features)
+    ref = ohac.greedy_hac(features["X"], features["track"], threshold=0.6)
+    assert ohac.partition_of(result) == ohac.partition_of({k: v for k, v in ref.items() if k in starting_point})
