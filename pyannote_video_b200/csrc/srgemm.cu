@@ -50,6 +50,32 @@ __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint3
   return (long long)plane * m.plane_rows + (long long)n * m.img + (long long)(Y >> 1) * m.w + (X >> 1);
 }
 
+// Issue the MMAs of one pipeline stage: n_taps taps x KSTEPS k16-steps.  KSTEPS = width/16, so the
+// operand rows are 32*KSTEPS bytes, 8-row groups are 256*KSTEPS bytes apart, and the swizzle mode
+// is 32B/64B/128B for KSTEPS = 1/2/4.  Descriptor hi word is a compile-time constant.
+template <int KSTEPS>
+__device__ __forceinline__ void issue_stage(const PvSrStage& st, int n_taps, int N, uint32_t a_lo, uint32_t b_lo,
+                                            uint32_t tmem_d, uint32_t idesc, uint32_t accum, bool leader) {
+  constexpr uint32_t kLayout = (KSTEPS == 4) ? 2u : (KSTEPS == 2 ? 4u : 6u);
+  constexpr uint32_t kSbo16 = (256u * KSTEPS) >> 4;                       // SBO in 16-byte units
+  constexpr uint32_t kHi = kSbo16 | (1u << 14) | (kLayout << 29);         // bits [32,64): SBO, version=1, layout
+  constexpr uint32_t kRow16 = 2u * KSTEPS;                                // one operand row in 16-byte units
+  const uint32_t b_tap16 = (uint32_t)N * kRow16;
+  uint32_t bb = b_lo;
+  for (int t = 0; t < n_taps; ++t) {
+    const uint32_t aa = a_lo + (uint32_t)st.tap_rel[t] * kRow16;
+    if (leader) {
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k) {
+        const uint64_t da = ((uint64_t)kHi << 32) | (uint64_t)(aa + 2u * k);
+        const uint64_t db = ((uint64_t)kHi << 32) | (uint64_t)(bb + 2u * k);
+        pv_umma_bf16(tmem_d, da, db, idesc, (accum | (uint32_t)t | (uint32_t)k) != 0u ? 1u : 0u);
+      }
+    }
+    bb += b_tap16;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_constant__ SrParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -96,16 +122,18 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const long long q0 = (long long)tile * kTileM;
-        for (int s = 0; s < p.n_stages; ++s) {
-          const PvSrStage& st = s_stage[s];
-          const int cls = st.cls;
-          const int rowb = p.cls_width[cls] * 2;
-          pv_mbar_wait(&bar_empty[slot], phase ^ 1u, p.err, 1);
+    // the whole warp runs the (uniform) loop, one elected lane issues
+    const bool leader = pv_elect_one();
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long q0 = (long long)tile * kTileM;
+      for (int s = 0; s < p.n_stages; ++s) {
+        const PvSrStage& st = s_stage[s];
+        const int cls = st.cls;
+        const int rowb = p.cls_width[cls] * 2;
+        pv_mbar_wait(&bar_empty[slot], phase ^ 1u, p.err, 1);
+        if (leader) {
           uint8_t* a_dst = ring + (size_t)slot * p.stage_bytes;
           uint8_t* b_dst = a_dst + p.a_bytes;
           const int slab_rows = kTileM + (st.use_tail ? p.tail_rows : 0);
@@ -117,53 +145,51 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
             pv_tma_load_2d(a_dst + kTileM * rowb, &p.a_tail[cls], &bar_full[slot], st.a_col, r0 + kTileM);
           for (int t = 0; t < st.n_taps; ++t)
             pv_tma_load_2d(b_dst + (size_t)t * N * rowb, &p.b[cls], &bar_full[slot], 0, st.b_row + t * N);
-          if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, M=128, N
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
-                             ((uint32_t)(kTileM >> 4) << 24);
-      int slot = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        pv_mbar_wait(&bar_tempty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u, p.err, 2);
+    // Warp-uniform loop (so descriptors live in uniform registers), one elected lane issues.
+    // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, M=128, N
+    const bool leader = pv_elect_one();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+                           ((uint32_t)(kTileM >> 4) << 24);
+    int slot = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      pv_mbar_wait(&bar_tempty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u, p.err, 2);
+      pv_tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * N);
+      uint32_t accum = 0;
+      for (int s = 0; s < p.n_stages; ++s) {
+        const PvSrStage& st = s_stage[s];
+        const int width = p.cls_width[st.cls];
+        const int n_taps = st.n_taps;
+        pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
         pv_tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * N);
-        uint32_t accum = 0;
-        for (int s = 0; s < p.n_stages; ++s) {
-          const PvSrStage& st = s_stage[s];
-          const int width = p.cls_width[st.cls];
-          const int rowb = width * 2;
-          const uint32_t ltype = (width == 64) ? 2u : (width == 32 ? 4u : 6u);
-          const uint32_t sbo = 8u * rowb;
-          pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
-          pv_tc_fence_after();
-          const uint32_t a_base = pv_smem_u32(ring + (size_t)slot * p.stage_bytes);
-          const uint32_t b_base = a_base + p.a_bytes;
-          const int ksteps = width >> 4;
-          for (int t = 0; t < st.n_taps; ++t) {
-            const uint32_t a_tap = a_base + (uint32_t)st.tap_rel[t] * rowb;
-            const uint32_t b_tap = b_base + (uint32_t)(t * N) * rowb;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t aa = a_tap + k * 32, bb = b_tap + k * 32;
-              const uint32_t boa = p.desc_mode ? ((aa >> 7) & 7u) : 0u;
-              const uint32_t bob = p.desc_mode ? ((bb >> 7) & 7u) : 0u;
-              pv_umma_bf16(tmem_d, pv_umma_desc(aa, sbo, ltype, boa), pv_umma_desc(bb, sbo, ltype, bob),
-                           idesc, accum);
-              accum = 1;
-            }
-          }
-          pv_umma_commit(&bar_empty[slot]);  // frees the smem slot once these MMAs retire
-          if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
+        const uint32_t a_base = pv_smem_u32(ring + (size_t)slot * p.stage_bytes);
+        // descriptor = hi (constant per width) : lo (start address >> 4, LBO field = 1)
+        const uint32_t a_lo = ((a_base & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t b_lo = (((a_base + (uint32_t)p.a_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+        if (width == 64) {
+          issue_stage<4>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
+        } else if (width == 32) {
+          issue_stage<2>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
+        } else {
+          issue_stage<1>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
         }
-        pv_umma_commit(&bar_tfull[buf]);  // accumulator complete
+        accum = 1;
+        if (leader) pv_umma_commit(&bar_empty[slot]);  // frees the smem slot once these MMAs retire
+        __syncwarp();
+        if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
       }
+      if (leader) pv_umma_commit(&bar_tfull[buf]);  // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue =====================
@@ -173,10 +199,10 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      const long long q = (long long)tile * kTileM + m;
-      bool valid = q < p.q_rows;
-      const uint32_t n = (uint32_t)(q / img);
-      const uint32_t rem = (uint32_t)(q - (long long)n * img);
+      const uint32_t q = (uint32_t)tile * kTileM + (uint32_t)m;   // q_rows < 2^31
+      bool valid = (long long)q < p.q_rows;
+      const uint32_t n = q / img;
+      const uint32_t rem = q - n * img;
       const uint32_t y = rem / (uint32_t)p.wq;
       const uint32_t x = rem - y * (uint32_t)p.wq;
       valid = valid && (y < (uint32_t)p.oh) && (x < (uint32_t)p.ow);
@@ -187,44 +213,51 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
       pv_tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N);
 
-      for (int c0 = 0; c0 < N; c0 += 16) {
-        uint32_t v[16];
-        pv_tmem_ld16(taddr + c0, v);
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[2][16];
+        const bool two = (c0 + 16) < N;
+        pv_tmem_ld16(taddr + c0, v[0]);
+        if (two) pv_tmem_ld16(taddr + c0 + 16, v[1]);
         pv_tmem_ld_wait();
         if (valid) {
-          float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[c0 + j], s_shift[c0 + j]);
-          if (p.has_resid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + rrow * p.res.cols + c0);
-            uint4 r0 = rp[0], r1 = rp[1];
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const int cb = c0 + 16 * h;
+            float f[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
-              f[2 * j] += __bfloat162float(h.x);
-              f[2 * j + 1] += __bfloat162float(h.y);
+            for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[h][j]), s_scale[cb + j], s_shift[cb + j]);
+            if (p.has_resid) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.resid + rrow * p.res.cols + cb);
+              uint4 r0 = rp[0], r1 = rp[1];
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+                f[2 * j] += __bfloat162float(hh.x);
+                f[2 * j + 1] += __bfloat162float(hh.y);
+              }
             }
-          }
-          if (p.relu) {
+            if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.out_mode == 0) {
-            uint4 o0, o1;
-            o0.x = pv_pack_bf16x2(f[0], f[1]);
-            o0.y = pv_pack_bf16x2(f[2], f[3]);
-            o0.z = pv_pack_bf16x2(f[4], f[5]);
-            o0.w = pv_pack_bf16x2(f[6], f[7]);
-            o1.x = pv_pack_bf16x2(f[8], f[9]);
-            o1.y = pv_pack_bf16x2(f[10], f[11]);
-            o1.z = pv_pack_bf16x2(f[12], f[13]);
-            o1.w = pv_pack_bf16x2(f[14], f[15]);
-            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + drow * p.dst.cols + c0);
-            dp[0] = o0;
-            dp[1] = o1;
-          } else if (c0 == 0) {
-            reinterpret_cast<float*>(p.out)[drow] = f[0];
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.out_mode == 0) {
+              uint4 o0, o1;
+              o0.x = pv_pack_bf16x2(f[0], f[1]);
+              o0.y = pv_pack_bf16x2(f[2], f[3]);
+              o0.z = pv_pack_bf16x2(f[4], f[5]);
+              o0.w = pv_pack_bf16x2(f[6], f[7]);
+              o1.x = pv_pack_bf16x2(f[8], f[9]);
+              o1.y = pv_pack_bf16x2(f[10], f[11]);
+              o1.z = pv_pack_bf16x2(f[12], f[13]);
+              o1.w = pv_pack_bf16x2(f[14], f[15]);
+              uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + drow * p.dst.cols + cb);
+              dp[0] = o0;
+              dp[1] = o1;
+            } else if (cb == 0) {
+              reinterpret_cast<float*>(p.out)[drow] = f[0];
+            }
           }
         }
       }
@@ -409,7 +442,7 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   plan->smem_bytes = (size_t)n_ring * stage_bytes + fixed + 1024;
   plan->q_cap = d->x_rows;
 
-  e = cudaFuncSetAttribute(srgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+  e = cudaFuncSetAttribute(srgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  // one function-wide attribute: always the maximum
   if (e != cudaSuccess) {
     pv_set_error("pv_srgemm_create: cudaFuncSetAttribute(%zu B smem): %s", plan->smem_bytes, cudaGetErrorString(e));
     cudaFree(plan->d_stages);
