@@ -181,6 +181,22 @@ int pv_pool_cols(const float* R, int64_t tin, const int* offs, const int* memb, 
 /* nearest cluster of every cluster under average linkage S[A][C]/(size_A*size_C) */
 int pv_row_argmin(const float* S, int64_t t, const float* sizes, int* nn, float* nnd, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * correlation-tracker bank (csrc/tracker.cu) — dlib.correlation_tracker start_track / update /
+ * get_position, pyannote/video/tracking.py:203,231,250-251; one CTA per live track
+ * ------------------------------------------------------------------------------------------ */
+/* tables are HOST float arrays: cosine window [64], FHOG orientation cos/sin [9], FFT twiddles [32] */
+int pv_tracker_create(int capacity, const float* hann64_host, const float* uu9_host, const float* vv9_host,
+                      const float* tw_re32_host, const float* tw_im32_host, float padding, float lambda, float nu,
+                      void** out_handle);
+int pv_tracker_destroy(void* handle);
+/* frame u8 [H,W,3]; ids i32 [n] bank slots; rects f32 [n,4] (l,t,r,b) */
+int pv_tracker_start(void* handle, const void* frame, int H, int W, const int* ids, const float* rects, int n,
+                     void* stream);
+int pv_tracker_update(void* handle, const void* frame, int H, int W, const int* ids, int n, void* stream);
+/* device pointers owned by the bank: positions f32 [capacity,4] and PSR f32 [capacity] */
+int pv_tracker_state(void* handle, float** pos, float** psr);
+
 #ifdef __cplusplus
 }
 #endif

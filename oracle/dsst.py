@@ -1,0 +1,166 @@
+"""ORACLE (test infrastructure — never imported by the product path).
+
+CPU restatement of dlib.correlation_tracker (DSST, Danelljan et al. BMVC'14) as the reference uses
+it: `start_track(frame, drectangle)`, `update(frame) -> PSR`, `get_position()`
+(pyannote/video/tracking.py:203,231,250-251), following dlib 19.12's correlation_tracker.h as
+recalled in SURVEY.md App. A.5 (dlib absent: parity unpinned).
+
+Restated: translation filter over the 31-channel FHOG (cell size 1) of a 64x64 chip cut from the
+position rectangle grown by 1.4, cosine window, per-channel numerators A_i = conj(G) F_i and shared
+denominator B = sum |F_i|^2, response = ifft2(sum F_i conj(A_i) / (B + 0.001)), sub-pixel peak, PSR
+over everything outside the 8x8 peak window, running update with nu = 0.025.
+NOT restated (stated gap): the 1-D scale filter of `update` (32 scales, 23x23 windows)
+— `update` here is dlib's `update_noscale`; the rectangle keeps its size.
+Chip sampling and FHOG are float32/unfused like the CUDA path; the FFTs are numpy float64.
+"""
+import numpy as np
+
+f32 = np.float32
+
+FS = 64
+PADDING = 1.4
+LAMBDA = 0.001
+NU = 0.025
+EPS = f32(0.0001)
+
+
+def extract_chip(rgb, rect):
+    """bilinear 64x64 RGB chip (uint8) of rect*PADDING; chip pixel (cx,cy) <-> image point
+    R.l + cx*(R.r-R.l)/63 (corners map to corners); outside the image -> 0."""
+    H, W, _ = rgb.shape
+    l, t, r, b = [f32(v) for v in rect]
+    cx, cy = (l + r) * f32(0.5), (t + b) * f32(0.5)
+    hw, hh = (r - l) * f32(0.5) * f32(PADDING), (b - t) * f32(0.5) * f32(PADDING)
+    rl, rt = cx - hw, cy - hh
+    sx, sy = (f32(2.0) * hw) / f32(FS - 1), (f32(2.0) * hh) / f32(FS - 1)
+    xs = (rl + np.arange(FS, dtype=f32) * sx).astype(f32)
+    ys = (rt + np.arange(FS, dtype=f32) * sy).astype(f32)
+    left = np.floor(xs).astype(np.int64)
+    top = np.floor(ys).astype(np.int64)
+    lr = (xs - left.astype(f32)).astype(f32)[None, :, None]
+    tb = (ys - top.astype(f32)).astype(f32)[:, None, None]
+    ok = ((left >= 0) & (left + 1 < W))[None, :] & ((top >= 0) & (top + 1 < H))[:, None]
+    lc, tc = np.clip(left, 0, W - 2), np.clip(top, 0, H - 2)
+    s = rgb.astype(f32)
+    tl = s[tc][:, lc]
+    tr = s[tc][:, lc + 1]
+    bl = s[tc + 1][:, lc]
+    br = s[tc + 1][:, lc + 1]
+    one = f32(1)
+    a = ((one - lr) * tl) + (lr * tr)
+    bb = ((one - lr) * bl) + (lr * br)
+    v = ((one - tb) * a) + (tb * bb)
+    v = np.clip(np.floor(v + f32(0.5)), 0, 255)
+    v = np.where(ok[..., None], v, 0)
+    return v.astype(np.uint8), (rl, rt, sx, sy)
+
+
+_UU = np.cos(np.arange(9) * np.pi / 9).astype(f32)
+_VV = np.sin(np.arange(9) * np.pi / 9).astype(f32)
+
+
+def fhog_cell1(chip):
+    """31-channel FHOG with cell size 1 of a uint8 [64,64,3] chip -> float32 [31,64,64]; the
+    outermost ring of cells is zero (dlib pads the (n-2)^2 valid cells back to n^2)."""
+    n = chip.shape[0]
+    c = chip.astype(f32)
+    dx = np.zeros((n, n, 3), f32)
+    dy = np.zeros((n, n, 3), f32)
+    dx[1:-1, 1:-1] = c[1:-1, 2:] - c[1:-1, :-2]
+    dy[1:-1, 1:-1] = c[2:, 1:-1] - c[:-2, 1:-1]
+    m2 = (dx * dx) + (dy * dy)
+    ch = np.argmax(m2, axis=2)                       # first max: channel order r,g,b
+    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    gx, gy, v2 = dx[ii, jj, ch], dy[ii, jj, ch], m2[ii, jj, ch]
+    mag = np.sqrt(v2).astype(f32)
+    best_dot = np.zeros((n, n), f32)
+    best_o = np.zeros((n, n), np.int64)
+    for o in range(9):
+        dot = (_UU[o] * gx) + (_VV[o] * gy)
+        pos = dot > best_dot
+        best_o = np.where(pos, o, best_o)
+        best_dot = np.where(pos, dot, best_dot)
+        neg = (~pos) & (-dot > best_dot)
+        best_o = np.where(neg, o + 9, best_o)
+        best_dot = np.where(neg, -dot, best_dot)
+    interior = np.zeros((n, n), bool)
+    interior[1:-1, 1:-1] = True
+    mag = np.where(interior, mag, 0).astype(f32)
+    nrm = (mag * mag).astype(f32)
+    P = np.pad(nrm, 1)
+
+    def blk(dy_, dx_):
+        # sum of the 2x2 block whose top-left cell is (y+dy_, x+dx_)
+        y0, x0 = 1 + dy_, 1 + dx_
+        return (((P[y0:y0 + n, x0:x0 + n] + P[y0:y0 + n, x0 + 1:x0 + n + 1]) + P[y0 + 1:y0 + n + 1, x0:x0 + n])
+                + P[y0 + 1:y0 + n + 1, x0 + 1:x0 + n + 1]).astype(f32)
+
+    ns = [f32(1) / np.sqrt(blk(-1, -1) + EPS), f32(1) / np.sqrt(blk(-1, 0) + EPS),
+          f32(1) / np.sqrt(blk(0, -1) + EPS), f32(1) / np.sqrt(blk(0, 0) + EPS)]
+    h = [np.minimum(mag * nk, f32(0.2)).astype(f32) for nk in ns]
+    osum = (f32(0.5) * (((h[0] + h[1]) + h[2]) + h[3])).astype(f32)
+    out = np.zeros((31, n, n), f32)
+    valid = np.zeros((n, n), bool)
+    valid[1:-1, 1:-1] = True
+    for o in range(18):
+        out[o] = np.where(valid & (best_o == o), osum, 0)
+    for o in range(9):
+        out[18 + o] = np.where(valid & ((best_o % 9) == o), osum, 0)
+    for k in range(4):
+        out[27 + k] = np.where(valid, f32(0.2357) * h[k], 0)
+    return out
+
+
+def hann2d(n=FS):
+    w = (f32(0.5) - f32(0.5) * np.cos(2 * np.pi * np.arange(n) / (n - 1))).astype(f32)
+    return (w[:, None] * w[None, :]).astype(f32)
+
+
+def gaussian_target(px, py, n=FS):
+    x = np.arange(n, dtype=f32)[None, :]
+    y = np.arange(n, dtype=f32)[:, None]
+    return np.exp(-(((x - f32(px)) ** 2) + ((y - f32(py)) ** 2)) / f32(3.0)).astype(f32)
+
+
+class CorrelationTracker(object):
+    def _features(self, rgb, rect):
+        chip, tf = extract_chip(rgb, rect)
+        F = fhog_cell1(chip) * hann2d()[None]
+        return np.fft.fft2(F.astype(np.float64)), tf
+
+    def start_track(self, rgb, rect):
+        self.position = tuple(float(v) for v in rect)
+        F, _ = self._features(rgb, self.position)
+        c = (FS - 1) / 2.0
+        G = np.conj(np.fft.fft2(gaussian_target(c, c).astype(np.float64)))
+        self.A = G[None] * F
+        self.B = (np.abs(F) ** 2).sum(0)
+
+    def update(self, rgb):
+        guess = self.position
+        F, (rl, rt, sx, sy) = self._features(rgb, guess)
+        R = np.real(np.fft.ifft2((F * np.conj(self.A)).sum(0) / (self.B + LAMBDA)))
+        py, px = np.unravel_index(int(np.argmax(R)), R.shape)
+        ppx, ppy = float(px), float(py)
+        if 0 < px < FS - 1 and 0 < py < FS - 1:
+            dxx = R[py, px - 1] - 2 * R[py, px] + R[py, px + 1]
+            dyy = R[py - 1, px] - 2 * R[py, px] + R[py + 1, px]
+            if dxx != 0:
+                ppx += 0.5 * (R[py, px - 1] - R[py, px + 1]) / dxx
+            if dyy != 0:
+                ppy += 0.5 * (R[py - 1, px] - R[py + 1, px]) / dyy
+        mask = np.ones_like(R, bool)
+        mask[max(py - 4, 0):py + 4, max(px - 4, 0):px + 4] = False
+        side = R[mask]
+        psr = float((R[py, px] - side.mean()) / side.std(ddof=1))
+        ix, iy = float(rl) + ppx * float(sx), float(rt) + ppy * float(sy)
+        cx, cy = 0.5 * (guess[0] + guess[2]), 0.5 * (guess[1] + guess[3])
+        ddx, ddy = ix - cx, iy - cy
+        self.position = (guess[0] + ddx, guess[1] + ddy, guess[2] + ddx, guess[3] + ddy)
+        G = np.conj(np.fft.fft2(gaussian_target(ppx, ppy).astype(np.float64)))
+        self.A = (1 - NU) * self.A + NU * (G[None] * F)
+        self.B = (1 - NU) * self.B + NU * (np.abs(F) ** 2).sum(0)
+        return psr
+
+    def get_position(self):
+        return self.position
