@@ -58,17 +58,24 @@ int64_t pv_launch_count(void);
  * swizzled shared memory and consumed by tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16).
  * ------------------------------------------------------------------------------------------ */
 #define PV_SR_MAX_TAPS 9
-#define PV_SR_MAX_STAGES 192
+#define PV_SR_MAX_ENTRIES 192
 
-typedef struct PvSrStage {
-  int32_t a_row_off;   /* first row of the A slab, relative to the tile's first row q0        */
-  int32_t b_row;       /* first row of this stage's weights in the packed matrix of class cls */
-  int16_t a_col;       /* first column (element) of the segment inside X                      */
-  int16_t cls;         /* segment-width class (0 or 1)                                        */
-  int16_t n_taps;      /* taps sharing this slab (1..PV_SR_MAX_TAPS)                          */
-  int16_t use_tail;    /* 1: slab = 128 + tail_rows rows, 0: 128 rows                         */
-  int16_t tap_rel[PV_SR_MAX_TAPS + 1]; /* row offset of each tap inside the slab              */
-} PvSrStage;
+/* one table entry = one A slab (128 + tail rows of one column segment) and the taps that read it.
+ * Consecutive entries between a flag bit0 (opens a ring slot) and bit1 (closes it) share one
+ * shared-memory slot and one mbarrier round trip. */
+typedef struct PvSrEntry {
+  int32_t a_row_off;     /* first row of the A slab, relative to the tile's first row q0          */
+  int32_t b_row;         /* first row of this entry's weights in the packed matrix of class cls   */
+  int32_t a_smem_off;    /* filled by the library: byte offsets inside the slot                   */
+  int32_t b_smem_off;
+  uint32_t slot_tx_bytes;/* filled by the library on the entry that opens a slot                  */
+  int16_t a_col;         /* first column (element) of the segment inside X                        */
+  int16_t cls;           /* segment-width class (0 or 1)                                          */
+  int16_t n_taps;        /* taps sharing this slab (1..PV_SR_MAX_TAPS)                            */
+  int16_t use_tail;      /* 1: slab = 128 + tail_rows rows, 0: 128 rows                           */
+  int16_t flags;         /* bit0: first entry of a slot, bit1: last entry of a slot               */
+  int16_t tap_rel[PV_SR_MAX_TAPS + 2]; /* row offset of each tap inside the slab                  */
+} PvSrEntry;
 
 /* maps an output grid position (n, y, x) to a row of a destination / residual matrix */
 typedef struct PvRowMap {
@@ -93,26 +100,29 @@ typedef struct PvSrgemmDesc {
   const void* w_packed[2]; /* bf16 [w_rows[c], class_width[c]]                                 */
   int64_t w_rows[2];
   int32_t tail_rows;    /* multiple of 8, 0..128                                               */
-  int32_t n_stages;
-  const PvSrStage* stages; /* HOST pointer, copied                                             */
+  int32_t n_entries;
+  const PvSrEntry* entries; /* HOST pointer, copied                                            */
+  int64_t x_row_stride_bytes; /* 0 = dense (x_cols*2); may be smaller than a row (overlapping rows) */
+  int64_t weights_resident_max_bytes; /* keep all weights in smem for the launch if they fit in this many bytes (0 = stream) */
   const float* scale;   /* [N] */
   const float* shift;   /* [N] */
   /* output grid */
   int32_t hq, wq;       /* grid rows / cols per image; q = (n*hq + y)*wq + x                   */
   int32_t oh, ow;       /* valid output extent: y < oh && x < ow                               */
   int32_t relu;
-  int32_t out_mode;     /* 0: bf16 rows via dst map; 2: fp32 channel 0 only, row = dst map     */
+  int32_t out_mode;     /* 0: bf16 rows via dst map; 2: fp32 channel 0 only; 3: fp32 rows (all N) */
   void* out;
   PvRowMap dst;
   const void* resid;    /* bf16 or NULL */
   PvRowMap res;
-  int32_t desc_mode;    /* 0: UMMA descriptor base_offset = 0; 1: base_offset = (addr>>7)&7    */
   int32_t max_ctas;     /* 0 = number of SMs                                                   */
 } PvSrgemmDesc;
 
 int pv_srgemm_create(const PvSrgemmDesc* desc, void** out_handle);
 int pv_srgemm_run(void* handle, int64_t q_rows, void* stream);
 int pv_srgemm_destroy(void* handle);
+/* pipeline shape chosen for a plan (ring depth, slot bytes, weights resident?, TMEM accumulators) */
+int pv_srgemm_info(void* handle, int* n_ring, int* slot_bytes, int* resident, int* n_acc);
 /* reads (and clears) the device-side error flag of a plan; 0 = none. Synchronises the stream. */
 int pv_srgemm_check(void* handle, void* stream);
 
@@ -142,6 +152,10 @@ int pv_embed_head(const void* in, int B, int HW, int C, const float* fc, float* 
 int pv_resize_bilinear(const void* src, int src_channels, int64_t src_img_stride_bytes, int src_pitch_px, int sx0,
                        int sy0, int sw, int sh, void* dst_rgba, int64_t dst_img_stride_px, int dst_pitch_px, int dx0,
                        int dy0, int dw, int dh, float xs, float ys, int B, int copy_only, void* stream);
+/* the 9x9 single-channel last conv runs as a 9x1 conv with the filter columns as channels;
+ * score[n,y,x] = bias + sum_kw D[(n*Hq+y)*Wq + x+kw][kw] re-assembles it (D fp32 [rows, cols]) */
+int pv_det_shift_sum(const float* D, int B, int Hq, int Wq, int cols, int OH, int OW, int KW, float bias, float* scores,
+                     void* stream);
 /* cells of the score map above `thr` -> per-frame candidate lists (counts are zeroed first) */
 int pv_det_candidates(const float* scores, int B, int cells, float thr, int* counts, float* cand_score, int* cand_cell,
                       int cap, void* stream);

@@ -10,22 +10,26 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpvb200.so")
 
 PV_SR_MAX_TAPS = 9
-PV_SR_MAX_STAGES = 192
+PV_SR_MAX_ENTRIES = 192
 
 
 class PvError(RuntimeError):
     pass
 
 
-class PvSrStage(C.Structure):
+class PvSrEntry(C.Structure):
     _fields_ = [
         ("a_row_off", C.c_int32),
         ("b_row", C.c_int32),
+        ("a_smem_off", C.c_int32),
+        ("b_smem_off", C.c_int32),
+        ("slot_tx_bytes", C.c_uint32),
         ("a_col", C.c_int16),
         ("cls", C.c_int16),
         ("n_taps", C.c_int16),
         ("use_tail", C.c_int16),
-        ("tap_rel", C.c_int16 * (PV_SR_MAX_TAPS + 1)),
+        ("flags", C.c_int16),
+        ("tap_rel", C.c_int16 * (PV_SR_MAX_TAPS + 2)),
     ]
 
 
@@ -52,8 +56,10 @@ class PvSrgemmDesc(C.Structure):
         ("w_packed", C.c_void_p * 2),
         ("w_rows", C.c_int64 * 2),
         ("tail_rows", C.c_int32),
-        ("n_stages", C.c_int32),
-        ("stages", C.POINTER(PvSrStage)),
+        ("n_entries", C.c_int32),
+        ("entries", C.POINTER(PvSrEntry)),
+        ("x_row_stride_bytes", C.c_int64),
+        ("weights_resident_max_bytes", C.c_int64),
         ("scale", C.c_void_p),
         ("shift", C.c_void_p),
         ("hq", C.c_int32),
@@ -66,7 +72,6 @@ class PvSrgemmDesc(C.Structure):
         ("dst", PvRowMap),
         ("resid", C.c_void_p),
         ("res", PvRowMap),
-        ("desc_mode", C.c_int32),
         ("max_ctas", C.c_int32),
     ]
 

@@ -4,5 +4,5 @@
 # swizzle-atom aligned), "row" (taps of one filter row share a slab, descriptors start at
 # arbitrary row offsets) or "all".
 SRGEMM_GROUP = "row"   # validated on B200 (gpurun #1): descriptors at arbitrary row offsets read TMA-swizzled slabs correctly
-# UMMA descriptor base_offset policy: 0 -> always 0, 1 -> (smem_addr >> 7) & 7
-SRGEMM_DESC_MODE = 0
+# (gpurun #1 also settled the UMMA descriptor question: base_offset stays 0; the tensor core applies the
+# swizzle XOR to absolute shared-memory address bits, exactly like TMA does when it writes the slab.)

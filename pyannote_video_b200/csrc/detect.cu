@@ -64,6 +64,21 @@ __global__ void resize_bilinear_kernel(const uint8_t* __restrict__ src, long lon
   dst[(long long)n * dst_img_stride + (long long)(dy0 + r) * dst_pitch_px + dx0 + c] = o;
 }
 
+// score[n,y,x] = bias + sum_kw D[(n*Hq + y)*Wq + x + kw][kw]   (D: fp32 rows of `cols` columns)
+__global__ void det_shift_sum_kernel(const float* __restrict__ D, int B, int Hq, int Wq, int cols, int OH, int OW,
+                                     int KW, float bias, float* __restrict__ scores) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * OH * OW) return;
+  const int x = (int)(idx % OW);
+  long long r = idx / OW;
+  const int y = (int)(r % OH);
+  const int n = (int)(r / OH);
+  const float* base = D + (((long long)n * Hq + y) * Wq + x) * cols;
+  float s = bias;
+  for (int kw = 0; kw < KW; ++kw) s += base[(long long)kw * cols + kw];
+  scores[idx] = s;
+}
+
 // ---- candidates -----------------------------------------------------------------------------
 __global__ void det_candidates_kernel(const float* __restrict__ scores, int B, int cells, float thr,
                                       int* __restrict__ counts, float* __restrict__ cand_score,
@@ -230,6 +245,19 @@ extern "C" int pv_resize_bilinear(const void* src, int src_channels, int64_t src
                                                          sx0, sy0, sw, sh, static_cast<uchar4*>(dst_rgba),
                                                          dst_img_stride_px, dst_pitch_px, dx0, dy0, dw, dh, xs, ys, B,
                                                          copy_only);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_det_shift_sum(const float* D, int B, int Hq, int Wq, int cols, int OH, int OW, int KW, float bias,
+                                float* scores, void* stream) {
+  PV_REQUIRE(D && scores, "pv_det_shift_sum: null argument");
+  PV_REQUIRE(KW <= cols && OW + KW - 1 <= Wq && OH <= Hq, "pv_det_shift_sum: geometry");
+  const long long total = (long long)B * OH * OW;
+  const int threads = 256;
+  det_shift_sum_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      D, B, Hq, Wq, cols, OH, OW, KW, bias, scores);
   g_pv_launches.fetch_add(1);
   PV_CUDA_CHECK(cudaGetLastError());
   return PV_OK;

@@ -6,9 +6,11 @@
 // contract and DESIGN.md §"srgemm" for the data layout.
 //
 // One persistent CTA per SM, 6 warps:
-//   warp 0  (1 lane)  TMA producer: A slabs (activation rows) + B tiles (weights) -> smem ring
-//   warp 1  (1 lane)  tcgen05.mma issuer, accumulators in TMEM (2 buffers of N columns)
-//   warps 2-5         epilogue: tcgen05.ld -> affine (+residual) (+ReLU) -> bf16 -> global
+//   warp 0   TMA producer: activation slabs (+ weights, unless resident) -> ring of smem slots
+//   warp 1   tcgen05.mma issuer (one elected lane), accumulators in a ring of TMEM buffers
+//   warps 2-5 epilogue: tcgen05.ld -> affine (+residual) (+ReLU) -> bf16/f32 -> global
+// A ring slot holds several table entries (slab + taps) so one mbarrier round trip covers up to
+// ~48 KB of operands; weights of small layers stay resident in shared memory for the whole launch.
 #include <cuda.h>
 #include <atomic>
 #include <vector>
@@ -21,13 +23,14 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kMaxRing = 8;
+constexpr int kMaxAcc = 8;
 constexpr int kTileM = 128;
 
 struct SrParams {
   CUtensorMap a_main[2];
   CUtensorMap a_tail[2];
   CUtensorMap b[2];
-  const PvSrStage* stages;
+  const PvSrEntry* entries;
   const float* scale;
   const float* shift;
   void* out;
@@ -36,9 +39,14 @@ struct SrParams {
   PvRowMap res;
   long long q_rows;
   int num_tiles;
-  int n_out, n_stages, n_ring, stage_bytes, a_bytes, tail_rows;
+  int n_out, n_entries, n_ring, slot_bytes, tail_rows;
   int cls_width[2];
-  int hq, wq, oh, ow, relu, out_mode, has_resid, desc_mode;
+  int resident;          // weights live in smem for the whole launch
+  int res_bytes;         // bytes of the resident region (0 if streamed)
+  int res_cls_off[2];    // byte offset of each class inside the resident region
+  int res_tiles[2];      // number of N-row weight tiles per class
+  int n_acc;             // TMEM accumulator buffers
+  int hq, wq, oh, ow, relu, out_mode, has_resid;
   uint32_t tmem_cols;
   int* err;
 };
@@ -50,11 +58,11 @@ __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint3
   return (long long)plane * m.plane_rows + (long long)n * m.img + (long long)(Y >> 1) * m.w + (X >> 1);
 }
 
-// Issue the MMAs of one pipeline stage: n_taps taps x KSTEPS k16-steps.  KSTEPS = width/16, so the
+// Issue the MMAs of one table entry: n_taps taps x KSTEPS k16-steps.  KSTEPS = width/16, so the
 // operand rows are 32*KSTEPS bytes, 8-row groups are 256*KSTEPS bytes apart, and the swizzle mode
 // is 32B/64B/128B for KSTEPS = 1/2/4.  Descriptor hi word is a compile-time constant.
 template <int KSTEPS>
-__device__ __forceinline__ void issue_stage(const PvSrStage& st, int n_taps, int N, uint32_t a_lo, uint32_t b_lo,
+__device__ __forceinline__ void issue_entry(const PvSrEntry& st, int n_taps, int N, uint32_t a_lo, uint32_t b_lo,
                                             uint32_t tmem_d, uint32_t idesc, uint32_t accum, bool leader) {
   constexpr uint32_t kLayout = (KSTEPS == 4) ? 2u : (KSTEPS == 2 ? 4u : 6u);
   constexpr uint32_t kSbo16 = (256u * KSTEPS) >> 4;                       // SBO in 16-byte units
@@ -76,27 +84,31 @@ __device__ __forceinline__ void issue_stage(const PvSrStage& st, int n_taps, int
   }
 }
 
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+
 __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_constant__ SrParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  uint8_t* ring = smem;
-  PvSrStage* s_stage = reinterpret_cast<PvSrStage*>(ring + (size_t)p.n_ring * p.stage_bytes);
-  float* s_scale = reinterpret_cast<float*>(s_stage + PV_SR_MAX_STAGES);
+  uint8_t* resw = smem;                                  // resident weights (may be empty)
+  uint8_t* ring = smem + p.res_bytes;                    // res_bytes is a multiple of 1024
+  PvSrEntry* s_entry = reinterpret_cast<PvSrEntry*>(ring + (size_t)p.n_ring * p.slot_bytes);
+  float* s_scale = reinterpret_cast<float*>(s_entry + PV_SR_MAX_ENTRIES);
   float* s_shift = s_scale + 256;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_shift + 256);
   uint64_t* bar_empty = bar_full + kMaxRing;
   uint64_t* bar_tfull = bar_empty + kMaxRing;
-  uint64_t* bar_tempty = bar_tfull + 2;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint64_t* bar_tempty = bar_tfull + kMaxAcc;
+  uint64_t* bar_res = bar_tempty + kMaxAcc;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_res + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int N = p.n_out;
 
   // ---- one-time setup -------------------------------------------------------
-  for (int i = threadIdx.x; i < p.n_stages * (int)(sizeof(PvSrStage) / 4); i += kThreads)
-    reinterpret_cast<uint32_t*>(s_stage)[i] = reinterpret_cast<const uint32_t*>(p.stages)[i];
+  for (int i = threadIdx.x; i < p.n_entries * (int)(sizeof(PvSrEntry) / 4); i += kThreads)
+    reinterpret_cast<uint32_t*>(s_entry)[i] = reinterpret_cast<const uint32_t*>(p.entries)[i];
   for (int i = threadIdx.x; i < N; i += kThreads) {
     s_scale[i] = p.scale[i];
     s_shift[i] = p.shift[i];
@@ -108,10 +120,11 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
       pv_mbar_init(&bar_full[i], 1);
       pv_mbar_init(&bar_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < p.n_acc; ++i) {
       pv_mbar_init(&bar_tfull[i], 1);
       pv_mbar_init(&bar_tempty[i], 4);
     }
+    pv_mbar_init(bar_res, 1);
     pv_fence_mbar_init();
   }
   if (warp == 1) pv_tmem_alloc(s_tmem, p.tmem_cols);
@@ -124,30 +137,43 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
     // ===================== TMA producer =====================
     // the whole warp runs the (uniform) loop, one elected lane issues
     const bool leader = pv_elect_one();
+    if (p.resident && leader) {
+      pv_mbar_arrive_expect_tx(bar_res, (uint32_t)(p.res_tiles[0] * N * p.cls_width[0] * 2 +
+                                                   p.res_tiles[1] * N * p.cls_width[1] * 2));
+      for (int c = 0; c < 2; ++c) {
+        const int rowb = p.cls_width[c] * 2;
+        for (int t = 0; t < p.res_tiles[c]; ++t)
+          pv_tma_load_2d(resw + p.res_cls_off[c] + (size_t)t * N * rowb, &p.b[c], bar_res, 0, t * N);
+      }
+    }
+    __syncwarp();
     int slot = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const long long q0 = (long long)tile * kTileM;
-      for (int s = 0; s < p.n_stages; ++s) {
-        const PvSrStage& st = s_stage[s];
+      for (int e = 0; e < p.n_entries; ++e) {
+        const PvSrEntry& st = s_entry[e];
         const int cls = st.cls;
         const int rowb = p.cls_width[cls] * 2;
-        pv_mbar_wait(&bar_empty[slot], phase ^ 1u, p.err, 1);
+        if (st.flags & 1) pv_mbar_wait(&bar_empty[slot], phase ^ 1u, p.err, 1);
         if (leader) {
-          uint8_t* a_dst = ring + (size_t)slot * p.stage_bytes;
-          uint8_t* b_dst = a_dst + p.a_bytes;
-          const int slab_rows = kTileM + (st.use_tail ? p.tail_rows : 0);
-          const uint32_t bytes = (uint32_t)(slab_rows * rowb + st.n_taps * N * rowb);
-          pv_mbar_arrive_expect_tx(&bar_full[slot], bytes);
+          uint8_t* base = ring + (size_t)slot * p.slot_bytes;
+          if (st.flags & 1) pv_mbar_arrive_expect_tx(&bar_full[slot], st.slot_tx_bytes);
+          uint8_t* a_dst = base + st.a_smem_off;
           const int32_t r0 = (int32_t)(q0 + st.a_row_off);
           pv_tma_load_2d(a_dst, &p.a_main[cls], &bar_full[slot], st.a_col, r0);
           if (st.use_tail)
             pv_tma_load_2d(a_dst + kTileM * rowb, &p.a_tail[cls], &bar_full[slot], st.a_col, r0 + kTileM);
-          for (int t = 0; t < st.n_taps; ++t)
-            pv_tma_load_2d(b_dst + (size_t)t * N * rowb, &p.b[cls], &bar_full[slot], 0, st.b_row + t * N);
+          if (!p.resident) {
+            uint8_t* b_dst = base + st.b_smem_off;
+            for (int t = 0; t < st.n_taps; ++t)
+              pv_tma_load_2d(b_dst + (size_t)t * N * rowb, &p.b[cls], &bar_full[slot], 0, st.b_row + t * N);
+          }
         }
         __syncwarp();
-        if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
+        if (st.flags & 2) {
+          if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -157,48 +183,59 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
     const bool leader = pv_elect_one();
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
                            ((uint32_t)(kTileM >> 4) << 24);
+    if (p.resident) {
+      pv_mbar_wait(bar_res, 0, p.err, 5);
+      pv_tc_fence_after();
+    }
+    const uint32_t res_base = pv_smem_u32(resw);
     int slot = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      pv_mbar_wait(&bar_tempty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u, p.err, 2);
+    int buf = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      pv_mbar_wait(&bar_tempty[buf], aphase ^ 1u, p.err, 2);
       pv_tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * N);
       uint32_t accum = 0;
-      for (int s = 0; s < p.n_stages; ++s) {
-        const PvSrStage& st = s_stage[s];
+      for (int e = 0; e < p.n_entries; ++e) {
+        const PvSrEntry& st = s_entry[e];
         const int width = p.cls_width[st.cls];
         const int n_taps = st.n_taps;
-        pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
-        pv_tc_fence_after();
-        const uint32_t a_base = pv_smem_u32(ring + (size_t)slot * p.stage_bytes);
-        // descriptor = hi (constant per width) : lo (start address >> 4, LBO field = 1)
-        const uint32_t a_lo = ((a_base & 0x3FFFFu) >> 4) | (1u << 16);
-        const uint32_t b_lo = (((a_base + (uint32_t)p.a_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+        if (st.flags & 1) {
+          pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
+          pv_tc_fence_after();
+        }
+        const uint32_t base = pv_smem_u32(ring + (size_t)slot * p.slot_bytes);
+        const uint32_t a_lo = desc_lo(base + (uint32_t)st.a_smem_off);
+        const uint32_t b_addr = p.resident ? res_base + (uint32_t)p.res_cls_off[st.cls] + (uint32_t)st.b_row * (uint32_t)(width * 2)
+                                           : base + (uint32_t)st.b_smem_off;
+        const uint32_t b_lo = desc_lo(b_addr);
         if (width == 64) {
-          issue_stage<4>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
+          issue_entry<4>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
         } else if (width == 32) {
-          issue_stage<2>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
+          issue_entry<2>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
         } else {
-          issue_stage<1>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
+          issue_entry<1>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
         }
         accum = 1;
-        if (leader) pv_umma_commit(&bar_empty[slot]);  // frees the smem slot once these MMAs retire
-        __syncwarp();
-        if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
+        if (st.flags & 2) {
+          if (leader) pv_umma_commit(&bar_empty[slot]);  // frees the smem slot once these MMAs retire
+          __syncwarp();
+          if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
+        }
       }
       if (leader) pv_umma_commit(&bar_tfull[buf]);  // accumulator complete
       __syncwarp();
+      if (++buf == p.n_acc) { buf = 0; aphase ^= 1u; }
     }
   } else {
     // ===================== epilogue =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32)
     const int m = quarter * 32 + lane;
     const uint32_t img = (uint32_t)p.hq * (uint32_t)p.wq;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
+    int buf = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const uint32_t q = (uint32_t)tile * kTileM + (uint32_t)m;   // q_rows < 2^31
       bool valid = (long long)q < p.q_rows;
       const uint32_t n = q / img;
@@ -209,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
       const long long drow = row_of(p.dst, n, y, x);
       const long long rrow = p.has_resid ? row_of(p.res, n, y, x) : 0;
 
-      pv_mbar_wait(&bar_tfull[buf], ((uint32_t)it >> 1) & 1u, p.err, 4);
+      pv_mbar_wait(&bar_tfull[buf], aphase, p.err, 4);
       pv_tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N);
 
@@ -255,6 +292,12 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
               uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + drow * p.dst.cols + cb);
               dp[0] = o0;
               dp[1] = o1;
+            } else if (p.out_mode == 3) {
+              float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + drow * p.dst.cols + cb);
+              dp[0] = make_float4(f[0], f[1], f[2], f[3]);
+              dp[1] = make_float4(f[4], f[5], f[6], f[7]);
+              dp[2] = make_float4(f[8], f[9], f[10], f[11]);
+              dp[3] = make_float4(f[12], f[13], f[14], f[15]);
             } else if (cb == 0) {
               reinterpret_cast<float*>(p.out)[drow] = f[0];
             }
@@ -264,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
       pv_tc_fence_before();
       __syncwarp();
       if (lane == 0) pv_mbar_arrive(&bar_tempty[buf]);
+      if (++buf == p.n_acc) { buf = 0; aphase ^= 1u; }
     }
   }
 
@@ -295,15 +339,17 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
-              uint32_t box_rows) {
+// 2-D bf16 map: `cols` elements per row, rows `row_stride_bytes` apart (may be smaller than a row:
+// overlapping rows are how a first conv can read pixel runs straight out of an NHWC plane).
+int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+              uint32_t box_cols, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     pv_set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     return PV_ERR_CUDA;
   }
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * 2};
+  cuuint64_t gstride[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapSwizzle sw = box_cols == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -313,8 +359,9 @@ int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, 
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    pv_set_error("cuTensorMapEncodeTiled failed: CUresult %d (cols=%llu rows=%llu box=%ux%u)", (int)r,
-                 (unsigned long long)cols, (unsigned long long)rows, box_cols, box_rows);
+    pv_set_error("cuTensorMapEncodeTiled failed: CUresult %d (cols=%llu rows=%llu stride=%llu box=%ux%u)", (int)r,
+                 (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_cols,
+                 box_rows);
     return PV_ERR_CUDA;
   }
   return PV_OK;
@@ -322,13 +369,14 @@ int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, 
 
 struct SrPlan {
   SrParams p;
-  PvSrStage* d_stages = nullptr;
+  PvSrEntry* d_entries = nullptr;
   int* d_err = nullptr;
   size_t smem_bytes = 0;
-  long long q_cap = 0;
   int num_sms = 0;
   int max_ctas = 0;
 };
+
+inline int align1k(int v) { return (v + 1023) & ~1023; }
 
 }  // namespace
 
@@ -336,48 +384,86 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   PV_REQUIRE(d && out_handle, "pv_srgemm_create: null argument");
   PV_REQUIRE(d->n_out >= 16 && d->n_out <= 256 && d->n_out % 16 == 0, "srgemm: n_out=%d must be a multiple of 16 in [16,256]", d->n_out);
   PV_REQUIRE(d->n_classes == 1 || d->n_classes == 2, "srgemm: n_classes=%d", d->n_classes);
-  PV_REQUIRE(d->n_stages >= 1 && d->n_stages <= PV_SR_MAX_STAGES, "srgemm: n_stages=%d out of range", d->n_stages);
+  PV_REQUIRE(d->n_entries >= 1 && d->n_entries <= PV_SR_MAX_ENTRIES, "srgemm: n_entries=%d out of range", d->n_entries);
   PV_REQUIRE(d->tail_rows >= 0 && d->tail_rows <= 128 && d->tail_rows % 8 == 0, "srgemm: tail_rows=%d", d->tail_rows);
   PV_REQUIRE(d->x_cols % 8 == 0 && d->x_cols >= 16, "srgemm: x_cols=%d must be a multiple of 8", d->x_cols);
   PV_REQUIRE(d->x_rows > 0 && d->x_rows < (1ll << 31), "srgemm: x_rows=%lld out of range", (long long)d->x_rows);
   PV_REQUIRE(d->hq > 0 && d->wq > 0 && d->oh > 0 && d->ow > 0, "srgemm: bad grid");
-  PV_REQUIRE(d->out_mode == 0 || d->out_mode == 2, "srgemm: out_mode=%d", d->out_mode);
-  PV_REQUIRE(d->x && d->out && d->scale && d->shift && d->stages, "srgemm: null operand");
-  int maxw = 0;
+  PV_REQUIRE(d->out_mode == 0 || d->out_mode == 2 || d->out_mode == 3, "srgemm: out_mode=%d", d->out_mode);
+  PV_REQUIRE(d->x && d->out && d->scale && d->shift && d->entries, "srgemm: null operand");
+  const long long row_stride = d->x_row_stride_bytes > 0 ? d->x_row_stride_bytes : (long long)d->x_cols * 2;
+  PV_REQUIRE(row_stride % 16 == 0, "srgemm: x_row_stride_bytes=%lld must be a multiple of 16", row_stride);
   for (int c = 0; c < d->n_classes; ++c) {
     const int w = d->class_width[c];
     PV_REQUIRE(w == 16 || w == 32 || w == 64, "srgemm: class_width[%d]=%d", c, w);
-    PV_REQUIRE(d->w_packed[c] && d->w_rows[c] > 0, "srgemm: missing weights for class %d", c);
-    if (w > maxw) maxw = w;
+    PV_REQUIRE(d->w_packed[c] && d->w_rows[c] > 0 && d->w_rows[c] % d->n_out == 0, "srgemm: bad weights for class %d", c);
   }
-  if (d->out_mode == 0) {
+  if (d->out_mode == 0 || d->out_mode == 3) {
     PV_REQUIRE(d->dst.cols % 8 == 0 && d->dst.cols >= d->n_out, "srgemm: dst.cols=%d < n_out=%d", d->dst.cols, d->n_out);
   }
   if (d->resid) PV_REQUIRE(d->res.cols % 8 == 0 && d->res.cols >= d->n_out, "srgemm: res.cols=%d", d->res.cols);
 
-  int b_bytes = 0;
-  for (int s = 0; s < d->n_stages; ++s) {
-    const PvSrStage& st = d->stages[s];
-    PV_REQUIRE(st.cls >= 0 && st.cls < d->n_classes, "srgemm: stage %d class %d", s, st.cls);
-    PV_REQUIRE(st.n_taps >= 1 && st.n_taps <= PV_SR_MAX_TAPS, "srgemm: stage %d n_taps %d", s, st.n_taps);
-    const int w = d->class_width[st.cls];
-    PV_REQUIRE(st.a_col >= 0 && st.a_col + w <= d->x_cols, "srgemm: stage %d column segment out of range", s);
-    for (int t = 0; t < st.n_taps; ++t) {
-      const int rel = st.tap_rel[t];
-      PV_REQUIRE(rel >= 0 && rel <= (st.use_tail ? d->tail_rows : 0), "srgemm: stage %d tap %d rel %d outside slab", s, t, rel);
+  // ---- resident weights? ----
+  int res_bytes = 0, res_cls_off[2] = {0, 0}, res_tiles[2] = {0, 0};
+  long long wbytes = 0;
+  for (int c = 0; c < d->n_classes; ++c) wbytes += d->w_rows[c] * d->class_width[c] * 2;
+  const bool resident = d->weights_resident_max_bytes > 0 && wbytes <= d->weights_resident_max_bytes;
+  if (resident) {
+    int off = 0;
+    for (int c = 0; c < d->n_classes; ++c) {
+      res_cls_off[c] = off;
+      res_tiles[c] = (int)(d->w_rows[c] / d->n_out);
+      off = align1k(off + (int)(d->w_rows[c] * d->class_width[c] * 2));
     }
-    PV_REQUIRE(st.b_row >= 0 && (long long)st.b_row + (long long)st.n_taps * d->n_out <= d->w_rows[st.cls], "srgemm: stage %d weights out of range", s);
-    const int bb = st.n_taps * d->n_out * w * 2;
-    if (bb > b_bytes) b_bytes = bb;
+    res_bytes = off;
   }
-  const int a_bytes = (((kTileM + d->tail_rows) * maxw * 2) + 1023) & ~1023;
-  b_bytes = (b_bytes + 1023) & ~1023;
-  const int stage_bytes = a_bytes + b_bytes;
-  const size_t fixed = sizeof(PvSrStage) * PV_SR_MAX_STAGES + 2 * 256 * sizeof(float) + (2 * kMaxRing + 4) * sizeof(uint64_t) + 16;
-  const size_t budget = 227 * 1024 - 1024 - fixed;
-  int n_ring = (int)(budget / stage_bytes);
+
+  // ---- validate entries, lay out slots ----
+  std::vector<PvSrEntry> ent(d->entries, d->entries + d->n_entries);
+  int slot_bytes = 0;
+  {
+    int cur = 0;
+    uint32_t tx = 0;
+    int first = -1;
+    for (int e = 0; e < d->n_entries; ++e) {
+      PvSrEntry& st = ent[e];
+      PV_REQUIRE(st.cls >= 0 && st.cls < d->n_classes, "srgemm: entry %d class %d", e, st.cls);
+      PV_REQUIRE(st.n_taps >= 1 && st.n_taps <= PV_SR_MAX_TAPS, "srgemm: entry %d n_taps %d", e, st.n_taps);
+      const int w = d->class_width[st.cls];
+      PV_REQUIRE(st.a_col >= 0 && st.a_col + w <= d->x_cols, "srgemm: entry %d column segment out of range", e);
+      for (int t = 0; t < st.n_taps; ++t) {
+        const int rel = st.tap_rel[t];
+        PV_REQUIRE(rel >= 0 && rel <= (st.use_tail ? d->tail_rows : 0), "srgemm: entry %d tap %d rel %d outside slab", e, t, rel);
+      }
+      PV_REQUIRE(st.b_row >= 0 && st.b_row % d->n_out == 0 &&
+                     (long long)st.b_row + (long long)st.n_taps * d->n_out <= d->w_rows[st.cls],
+                 "srgemm: entry %d weights out of range", e);
+      if (e == 0) PV_REQUIRE(st.flags & 1, "srgemm: first entry must open a slot");
+      if (st.flags & 1) { cur = 0; tx = 0; first = e; }
+      const int slab_rows = kTileM + (st.use_tail ? d->tail_rows : 0);
+      st.a_smem_off = cur;
+      cur = align1k(cur + slab_rows * w * 2);
+      tx += (uint32_t)(slab_rows * w * 2);
+      if (!resident) {
+        st.b_smem_off = cur;
+        cur = align1k(cur + st.n_taps * d->n_out * w * 2);
+        tx += (uint32_t)(st.n_taps * d->n_out * w * 2);
+      } else {
+        st.b_smem_off = 0;
+      }
+      ent[first].slot_tx_bytes = tx;
+      if (cur > slot_bytes) slot_bytes = cur;
+      if (e == d->n_entries - 1) PV_REQUIRE(st.flags & 2, "srgemm: last entry must close its slot");
+      if ((st.flags & 2) && e + 1 < d->n_entries) PV_REQUIRE(ent[e + 1].flags & 1, "srgemm: entry %d must open a slot", e + 1);
+      if (!(st.flags & 2)) PV_REQUIRE(e + 1 < d->n_entries && !(ent[e + 1].flags & 1), "srgemm: slot flags inconsistent at entry %d", e);
+    }
+  }
+  const size_t fixed = sizeof(PvSrEntry) * PV_SR_MAX_ENTRIES + 2 * 256 * sizeof(float) +
+                       (2 * kMaxRing + 2 * kMaxAcc + 1) * sizeof(uint64_t) + 16;
+  const long long budget = 227 * 1024 - 1024 - (long long)fixed - res_bytes;
+  int n_ring = (int)(budget / slot_bytes);
   if (n_ring > kMaxRing) n_ring = kMaxRing;
-  PV_REQUIRE(n_ring >= 2, "srgemm: stage of %d bytes does not fit a 2-deep ring", stage_bytes);
+  PV_REQUIRE(n_ring >= 2, "srgemm: slot of %d bytes (+%d resident) does not fit a 2-deep ring", slot_bytes, res_bytes);
 
   SrPlan* plan = new SrPlan();
   memset(&plan->p, 0, sizeof(SrParams));
@@ -395,24 +481,24 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   int rc = PV_OK;
   for (int c = 0; c < d->n_classes && rc == PV_OK; ++c) {
     const int w = d->class_width[c];
-    rc = encode_2d(&p.a_main[c], d->x, d->x_cols, d->x_rows, w, kTileM);
-    if (rc == PV_OK && d->tail_rows > 0) rc = encode_2d(&p.a_tail[c], d->x, d->x_cols, d->x_rows, w, d->tail_rows);
-    if (rc == PV_OK) rc = encode_2d(&p.b[c], d->w_packed[c], w, d->w_rows[c], w, d->n_out);
+    rc = encode_2d(&p.a_main[c], d->x, d->x_cols, d->x_rows, row_stride, w, kTileM);
+    if (rc == PV_OK && d->tail_rows > 0) rc = encode_2d(&p.a_tail[c], d->x, d->x_cols, d->x_rows, row_stride, w, d->tail_rows);
+    if (rc == PV_OK) rc = encode_2d(&p.b[c], d->w_packed[c], w, d->w_rows[c], (uint64_t)w * 2, w, d->n_out);
   }
   if (rc != PV_OK) {
     delete plan;
     return rc;
   }
-  if (cudaMalloc(&plan->d_stages, sizeof(PvSrStage) * d->n_stages) != cudaSuccess ||
+  if (cudaMalloc(&plan->d_entries, sizeof(PvSrEntry) * d->n_entries) != cudaSuccess ||
       cudaMalloc(&plan->d_err, sizeof(int)) != cudaSuccess) {
     pv_set_error("pv_srgemm_create: cudaMalloc failed");
     delete plan;
     return PV_ERR_CUDA;
   }
-  cudaMemcpy(plan->d_stages, d->stages, sizeof(PvSrStage) * d->n_stages, cudaMemcpyHostToDevice);
+  cudaMemcpy(plan->d_entries, ent.data(), sizeof(PvSrEntry) * d->n_entries, cudaMemcpyHostToDevice);
   cudaMemset(plan->d_err, 0, sizeof(int));
 
-  p.stages = plan->d_stages;
+  p.entries = plan->d_entries;
   p.scale = d->scale;
   p.shift = d->shift;
   p.out = d->out;
@@ -420,13 +506,18 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   p.dst = d->dst;
   p.res = d->res;
   p.n_out = d->n_out;
-  p.n_stages = d->n_stages;
+  p.n_entries = d->n_entries;
   p.n_ring = n_ring;
-  p.stage_bytes = stage_bytes;
-  p.a_bytes = a_bytes;
+  p.slot_bytes = slot_bytes;
   p.tail_rows = d->tail_rows;
   p.cls_width[0] = d->class_width[0];
   p.cls_width[1] = d->n_classes > 1 ? d->class_width[1] : d->class_width[0];
+  p.resident = resident ? 1 : 0;
+  p.res_bytes = res_bytes;
+  p.res_cls_off[0] = res_cls_off[0];
+  p.res_cls_off[1] = res_cls_off[1];
+  p.res_tiles[0] = res_tiles[0];
+  p.res_tiles[1] = res_tiles[1];
   p.hq = d->hq;
   p.wq = d->wq;
   p.oh = d->oh;
@@ -434,18 +525,19 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   p.relu = d->relu;
   p.out_mode = d->out_mode;
   p.has_resid = d->resid != nullptr;
-  p.desc_mode = d->desc_mode;
+  int n_acc = 512 / d->n_out;
+  if (n_acc > kMaxAcc) n_acc = kMaxAcc;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * d->n_out)) cols <<= 1;
+  while (cols < (uint32_t)(n_acc * d->n_out)) cols <<= 1;
+  p.n_acc = n_acc;
   p.tmem_cols = cols;
   p.err = plan->d_err;
-  plan->smem_bytes = (size_t)n_ring * stage_bytes + fixed + 1024;
-  plan->q_cap = d->x_rows;
+  plan->smem_bytes = (size_t)res_bytes + (size_t)n_ring * slot_bytes + fixed + 1024;
 
-  e = cudaFuncSetAttribute(srgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  // one function-wide attribute: always the maximum
+  e = cudaFuncSetAttribute(srgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  // function-wide: always the maximum
   if (e != cudaSuccess) {
-    pv_set_error("pv_srgemm_create: cudaFuncSetAttribute(%zu B smem): %s", plan->smem_bytes, cudaGetErrorString(e));
-    cudaFree(plan->d_stages);
+    pv_set_error("pv_srgemm_create: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    cudaFree(plan->d_entries);
     cudaFree(plan->d_err);
     delete plan;
     return PV_ERR_CUDA;
@@ -465,6 +557,16 @@ extern "C" int pv_srgemm_run(void* handle, int64_t q_rows, void* stream) {
   srgemm_kernel<<<grid, kThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
   g_pv_launches.fetch_add(1);
   PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_srgemm_info(void* handle, int* n_ring, int* slot_bytes, int* resident, int* n_acc) {
+  PV_REQUIRE(handle, "pv_srgemm_info: null handle");
+  SrPlan* plan = static_cast<SrPlan*>(handle);
+  if (n_ring) *n_ring = plan->p.n_ring;
+  if (slot_bytes) *slot_bytes = plan->p.slot_bytes;
+  if (resident) *resident = plan->p.resident;
+  if (n_acc) *n_acc = plan->p.n_acc;
   return PV_OK;
 }
 
@@ -489,7 +591,7 @@ extern "C" int pv_srgemm_check(void* handle, void* stream) {
 extern "C" int pv_srgemm_destroy(void* handle) {
   if (!handle) return PV_OK;
   SrPlan* plan = static_cast<SrPlan*>(handle);
-  cudaFree(plan->d_stages);
+  cudaFree(plan->d_entries);
   cudaFree(plan->d_err);
   delete plan;
   return PV_OK;

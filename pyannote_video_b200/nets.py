@@ -37,11 +37,10 @@ def _mean3():
 
 
 class EmbedNet:
-    def __init__(self, model, max_batch, device, group=None, desc_mode=None):
+    def __init__(self, model, max_batch, device, group=None):
         if model.get("kind") != "resnet_v1_embedder":
             raise RuntimeError("EmbedNet: not an embedder model")
         group = config.SRGEMM_GROUP if group is None else group
-        desc_mode = config.SRGEMM_DESC_MODE if desc_mode is None else desc_mode
         self.B = B = int(max_batch)
         self.dev = device
         S = W.EMB_CHIP
@@ -56,7 +55,7 @@ class EmbedNet:
         l1 = RowLayout("padded", B, cp.OH, cp.OW, 32, pad=0)
         b1 = l1.alloc(device)
         sc, sh = _affine(model["conv1"])
-        self._add_conv(cp, self.xg, b1, l1, sc, sh, True, None, None, desc_mode)
+        self._add_conv(cp, self.xg, b1, l1, sc, sh, True, None, None)
         # max_pool 3x3 s2
         H = (cp.OH - 3) // 2 + 1
         blocks = model["blocks"]
@@ -82,16 +81,16 @@ class EmbedNet:
                 assert lcur.kind == "padded" and lcur.pad == 1
                 la = RowLayout("padded", B, lcur.H, lcur.W, ch, pad=1)
                 t = la.alloc(device)
-                self._add_conv(ConvPlan(lcur, wa, 1, 1, group=group), cur, t, la, sca, sha, True, None, None, desc_mode)
+                self._add_conv(ConvPlan(lcur, wa, 1, 1, group=group), cur, t, la, sca, sha, True, None, None)
                 lo = out_layout(lcur.H, lcur.W)
                 o = lo.alloc(device)
-                self._add_conv(ConvPlan(la, wb, 1, 1, group=group), t, o, lo, scb, shb, True, cur, lcur, desc_mode)
+                self._add_conv(ConvPlan(la, wb, 1, 1, group=group), t, o, lo, scb, shb, True, cur, lcur)
             else:
                 assert lcur.kind == "parity" and lcur.pad == 0
                 cpa = ConvPlan(lcur, wa, 2, 0, group=group)
                 la = RowLayout("padded", B, cpa.OH, cpa.OW, ch, pad=1)
                 t = la.alloc(device)
-                self._add_conv(cpa, cur, t, la, sca, sha, True, None, None, desc_mode)
+                self._add_conv(cpa, cur, t, la, sca, sha, True, None, None)
                 ph, pw = (lcur.H - 2) // 2 + 1, (lcur.W - 2) // 2 + 1
                 ho, wo = max(ph, cpa.OH), max(pw, cpa.OW)
                 assert (ho, wo) == (ph, pw)
@@ -99,7 +98,7 @@ class EmbedNet:
                 o = lo.alloc(device)
                 skip = lo.alloc(device)
                 self.ops.append(("avgpool", (cur, lcur, skip, o, ph, pw, ch, lo.rowmap())))
-                self._add_conv(ConvPlan(la, wb, 1, 1, group=group), t, o, lo, scb, shb, True, skip, lo, desc_mode)
+                self._add_conv(ConvPlan(la, wb, 1, 1, group=group), t, o, lo, scb, shb, True, skip, lo)
             cur, lcur = o, lo
         assert lcur.kind == "padded" and lcur.pad == 0
         self.fc = _t(model["fc"]).float().contiguous().to(device)
@@ -107,8 +106,8 @@ class EmbedNet:
         self.ops.append(("head", (cur, lcur.H * lcur.W, lcur.C)))
         self.final_layout = lcur
 
-    def _add_conv(self, cp, x, out, lout, sc, sh, relu, resid, lres, desc_mode):
-        op = Srgemm(cp, x, out, lout, sc, sh, relu, resid=resid, lres=lres, desc_mode=desc_mode)
+    def _add_conv(self, cp, x, out, lout, sc, sh, relu, resid, lres):
+        op = Srgemm(cp, x, out, lout, sc, sh, relu, resid=resid, lres=lres)
         self.ops.append(("conv", (op, cp.lin.img)))
         Cin = cp.lin.C if cp.lin.kind != "gathered" else 3
         self.flops_per_face += 2 * cp.OH * cp.OW * cp.Cout * Cin * cp.KH * cp.KW
@@ -151,11 +150,10 @@ class DetectorNet:
     MAX_CAND = 4096
     MAX_DET = 256
 
-    def __init__(self, model, H, W_, upsample, max_batch, device, group=None, desc_mode=None):
+    def __init__(self, model, H, W_, upsample, max_batch, device, group=None):
         if model.get("kind") != "mmod_detector":
             raise RuntimeError("DetectorNet: not a detector model")
         group = config.SRGEMM_GROUP if group is None else group
-        desc_mode = config.SRGEMM_DESC_MODE if desc_mode is None else desc_mode
         self.model = model
         self.B = B = int(max_batch)
         self.H, self.W, self.upsample, self.dev = H, W_, int(upsample), device
@@ -172,23 +170,38 @@ class DetectorNet:
         for i, c in enumerate(convs):
             cout, cin, k, s = W.DET_CONVS[i]
             pad = W.conv_pad(k, s)
-            cp = ConvPlan(lcur, _t(c["w"]), s, pad, group=group)
             last = i == n - 1
             sc, sh = _affine(c, affine=not last)
             if last:
-                self.OH, self.OW = cp.OH, cp.OW
-                self.scores = torch.zeros(B, cp.OH, cp.OW, dtype=torch.float32, device=device)
-                op = Srgemm(cp, cur, self.scores, None, sc, sh, relu=False, out_f32=True, desc_mode=desc_mode)
+                # 9x9, one output channel: the 9 filter columns become 9 output channels of a 9x1
+                # conv (K = 9 taps x 48 instead of 81 taps x 48); pv_det_shift_sum adds the
+                # kw-shifted channels back together.
+                assert cout == 1 and lcur.kind == "padded" and lcur.pad == pad
+                wt = _t(c["w"]).float()                       # [1, cin, k, k]
+                taps = []
+                for kh in range(k):
+                    m = torch.zeros(16, lcur.cols)
+                    m[:k, :cin] = wt[0, :, kh, :].t()         # row kw, col c
+                    taps.append((kh * lcur.Wq, m))
+                OHs, OWs = lcur.H + 2 * pad - k + 1, lcur.W + 2 * pad - k + 1
+                cp = ConvPlan.from_taps(lcur, taps, k, OHs, lcur.Wq, group="tap", kernel=(k, 1))
+                self.OH, self.OW = OHs, OWs
+                self.lpart = RowLayout("padded", B, lcur.Hq, lcur.Wq, 16, pad=0)
+                self.partial = torch.zeros(self.lpart.rows, 16, dtype=torch.float32, device=device)
+                self.scores = torch.zeros(B, OHs, OWs, dtype=torch.float32, device=device)
+                self.score_bias = float(sh[0])
+                op = Srgemm(cp, cur, self.partial, self.lpart, torch.ones(k), torch.zeros(k), relu=False, out_rows_f32=True)
             else:
+                cp = ConvPlan(lcur, _t(c["w"]), s, pad, group=group)
                 _, _, nk, ns = W.DET_CONVS[i + 1]
                 if ns == 2:
                     lo = RowLayout("parity", B, cp.OH, cp.OW, cp.N, pad=0)
                 else:
                     lo = RowLayout("padded", B, cp.OH, cp.OW, cp.N, pad=W.conv_pad(nk, ns))
                 o = lo.alloc(device)
-                op = Srgemm(cp, cur, o, lo, sc, sh, relu=True, desc_mode=desc_mode)
+                op = Srgemm(cp, cur, o, lo, sc, sh, relu=True)
             self.convs.append((op, cp.lin.img))
-            self.flops_per_frame += 2 * cp.OH * cp.OW * cout * cin * k * k
+            self.flops_per_frame += 2 * (self.OH * self.OW if last else cp.OH * cp.OW) * cout * cin * k * k
             if not last:
                 lcur, cur = lo, o
         rects, fxy = geo.level_table()
@@ -237,6 +250,9 @@ class DetectorNet:
                                       C.c_int64(self.lg.plane_rows), _mean3(), st), "pv_pack_gathered")
         for op, img in self.convs:
             op.run(M * img)
+        lp = self.lpart
+        _lib.check(L.pv_det_shift_sum(_lib.ptr(self.partial), M, lp.Hq, lp.Wq, 16, self.OH, self.OW, 9,
+                                      C.c_float(self.score_bias), _lib.ptr(self.scores), st), "pv_det_shift_sum")
         return self.scores[:M]
 
     def decode(self, M):

@@ -126,18 +126,22 @@ def _segments(kc):
     return segs, widths
 
 
+RESIDENT_MAX_BYTES = 120 * 1024     # weights at most this large stay in shared memory for the launch
+SLOT_TARGET_BYTES = 40 * 1024        # operands per ring slot (one mbarrier round trip)
+SMEM_AVAILABLE = 227 * 1024 - 16 * 1024
+
+
 class ConvPlan:
     """Tap table + packed weights for one convolution over a RowLayout."""
 
-    def __init__(self, lin, weight, stride, pad, group="tap", max_b_bytes=40 * 1024):
+    def __init__(self, lin, weight, stride, pad, group="tap", max_b_bytes=40 * 1024, resident_max=RESIDENT_MAX_BYTES):
         """weight: float tensor [Cout, Cin, KH, KW] (dlib/torch order), CPU."""
         Cout, Cin, KH, KW = weight.shape
         self.lin, self.stride, self.pad, self.KH, self.KW = lin, stride, pad, KH, KW
-        self.Cout = Cout
-        self.N = N = round_up(Cout, 16)
+        N = round_up(Cout, 16)
         Kc = lin.cols
-        self.OH = conv_out_size(lin.H, KH, stride, pad)
-        self.OW = conv_out_size(lin.W, KW, stride, pad)
+        OH = conv_out_size(lin.H, KH, stride, pad)
+        OW = conv_out_size(lin.W, KW, stride, pad)
         taps = []  # (row offset, W_t [N, Kc])
         w = weight.float()
         if lin.kind == "padded":
@@ -164,10 +168,29 @@ class ConvPlan:
                 # gathered row = [kw][c]
                 wt[:Cout, :KW * Cin] = w[:, :, kh, :].permute(0, 2, 1).reshape(Cout, KW * Cin)
                 taps.append(((kh & 1) * lin.plane_rows + (kh >> 1) * lin.Wq, wt))
+        self._build(taps, Cout, OH, OW, group, max_b_bytes, resident_max)
+
+    @classmethod
+    def from_taps(cls, lin, taps, Cout, OH, OW, group="tap", max_b_bytes=40 * 1024, resident_max=RESIDENT_MAX_BYTES,
+                  kernel=(1, 1)):
+        """taps: list of (row offset, W_t float [round_up(Cout,16), lin.cols])"""
+        self = cls.__new__(cls)
+        self.lin, self.stride, self.pad = lin, 1, 0
+        self.KH, self.KW = kernel
+        self._build(list(taps), Cout, OH, OW, group, max_b_bytes, resident_max)
+        return self
+
+    def _build(self, taps, Cout, OH, OW, group, max_b_bytes, resident_max):
+        lin = self.lin
+        self.Cout, self.OH, self.OW = Cout, OH, OW
+        self.N = N = round_up(Cout, 16)
         self.n_taps_total = len(taps)
-        self.Kc = Kc
+        self.Kc = Kc = lin.cols
         segs, widths = _segments(Kc)
         self.widths = widths
+        w_bytes = len(taps) * N * Kc * 2
+        self.resident = w_bytes <= resident_max
+        self.resident_max = resident_max if self.resident else 0
         # ---- group taps that share a slab ----
         taps.sort(key=lambda t: t[0])
         if group == "tap":
@@ -179,7 +202,7 @@ class ConvPlan:
         else:
             max_span = int(group)
         maxw = max(widths)
-        max_taps = max(1, min(_lib.PV_SR_MAX_TAPS, max_b_bytes // (N * maxw * 2)))
+        max_taps = _lib.PV_SR_MAX_TAPS if self.resident else max(1, min(_lib.PV_SR_MAX_TAPS, max_b_bytes // (N * maxw * 2)))
         groups = []
         for off, wt in taps:
             if groups and off - groups[-1][0][0] <= max_span and len(groups[-1]) < max_taps:
@@ -189,14 +212,14 @@ class ConvPlan:
         span = max(g[-1][0] - g[0][0] for g in groups)
         self.tail_rows = round_up(span, 8)
         assert self.tail_rows <= 128
-        # ---- stages + packed weights ----
-        stages = []
+        # ---- entries + packed weights ----
+        entries = []
         packed = {wd: [] for wd in widths}
         nrows = {wd: 0 for wd in widths}
         for g in groups:
             base = g[0][0]
             for col, wd in segs:
-                st = _lib.PvSrStage()
+                st = _lib.PvSrEntry()
                 st.a_row_off = base
                 st.b_row = nrows[wd]
                 st.a_col = col
@@ -207,11 +230,37 @@ class ConvPlan:
                     st.tap_rel[i] = off - base
                     packed[wd].append(wt[:, col:col + wd])
                     nrows[wd] += N
-                stages.append(st)
-        assert len(stages) <= _lib.PV_SR_MAX_STAGES, "too many stages: %d" % len(stages)
-        self.stages = stages
+                entries.append(st)
+        assert len(entries) <= _lib.PV_SR_MAX_ENTRIES, "too many entries: %d" % len(entries)
+        # ---- pack entries into ring slots ----
+        res_bytes = round_up(w_bytes, 1024) + 1024 if self.resident else 0
+        slot_cap = min(SLOT_TARGET_BYTES, (SMEM_AVAILABLE - res_bytes) // 3)
+
+        def ebytes(st):
+            wd = widths[st.cls]
+            b = round_up((128 + (self.tail_rows if st.use_tail else 0)) * wd * 2, 1024)
+            if not self.resident:
+                b += round_up(st.n_taps * N * wd * 2, 1024)
+            return b
+
+        cur = 0
+        for i, st in enumerate(entries):
+            eb = ebytes(st)
+            if i == 0 or cur + eb > slot_cap:
+                st.flags = 1
+                if i > 0:
+                    entries[i - 1].flags |= 2
+                cur = 0
+            cur += eb
+        entries[-1].flags |= 2
+        self.entries = entries
+        self.n_slots = sum(1 for st in entries if st.flags & 1)
         self.w_packed = [torch.cat(packed[wd], dim=0).to(torch.bfloat16).contiguous() for wd in widths]
-        self.mma_per_tile = sum(st.n_taps * (widths[st.cls] // 16) for st in stages)
+        self.mma_per_tile = sum(st.n_taps * (widths[st.cls] // 16) for st in entries)
+
+    @property
+    def stages(self):
+        return self.entries
 
     def flops_per_row(self):
         return 2 * self.N * 16 * self.mma_per_tile
@@ -221,10 +270,11 @@ class Srgemm:
     """A bound srgemm plan: conv + fused affine/residual/ReLU epilogue between device buffers."""
 
     def __init__(self, cp, x, out, lout, scale, shift, relu, resid=None, lres=None, out_f32=False,
-                 desc_mode=0, max_ctas=0):
+                 out_rows_f32=False, max_ctas=0, x_rows=None, x_row_stride_bytes=0):
         lin = cp.lin
         dev = x.device
-        assert x.dtype == torch.bfloat16 and x.shape == (lin.rows, lin.cols) and x.is_contiguous()
+        if x_rows is None:
+            assert x.dtype == torch.bfloat16 and x.shape == (lin.rows, lin.cols) and x.is_contiguous()
         self.cp = cp
         self.keep = [x, out, resid]
         self.w_dev = [w.to(dev) for w in cp.w_packed]
@@ -236,7 +286,9 @@ class Srgemm:
         self.scale, self.shift = sc.to(dev), sh.to(dev)
         d = _lib.PvSrgemmDesc()
         d.x = x.data_ptr()
-        d.x_rows, d.x_cols = lin.rows, lin.cols
+        d.x_rows, d.x_cols = (x_rows if x_rows is not None else lin.rows), lin.cols
+        d.x_row_stride_bytes = x_row_stride_bytes
+        d.weights_resident_max_bytes = cp.resident_max
         d.n_out = N
         d.n_classes = len(cp.widths)
         for i, wd in enumerate(cp.widths):
@@ -244,9 +296,9 @@ class Srgemm:
             d.w_packed[i] = self.w_dev[i].data_ptr()
             d.w_rows[i] = self.w_dev[i].shape[0]
         d.tail_rows = cp.tail_rows
-        d.n_stages = len(cp.stages)
-        self._stages = (_lib.PvSrStage * len(cp.stages))(*cp.stages)
-        d.stages = C.cast(self._stages, C.POINTER(_lib.PvSrStage))
+        d.n_entries = len(cp.entries)
+        self._entries = (_lib.PvSrEntry * len(cp.entries))(*cp.entries)
+        d.entries = C.cast(self._entries, C.POINTER(_lib.PvSrEntry))
         d.scale, d.shift = self.scale.data_ptr(), self.shift.data_ptr()
         d.hq, d.wq, d.oh, d.ow = lin.Hq, lin.Wq, cp.OH, cp.OW
         d.relu = int(relu)
@@ -257,6 +309,10 @@ class Srgemm:
             m = _lib.PvRowMap()
             m.kind, m.cols, m.w, m.py, m.px, m.img, m.plane_rows = 0, 1, cp.OW, 0, 0, cp.OH * cp.OW, 0
             d.dst = m
+        elif out_rows_f32:
+            assert out.dtype == torch.float32 and out.shape == (lout.rows, lout.cols)
+            d.out_mode = 3
+            d.dst = lout.rowmap()
         else:
             assert out.dtype == torch.bfloat16 and out.shape == (lout.rows, lout.cols)
             assert (lout.H, lout.W) == (cp.OH, cp.OW) or (lout.H >= cp.OH and lout.W >= cp.OW)
@@ -266,13 +322,17 @@ class Srgemm:
             assert resid.dtype == torch.bfloat16 and resid.shape == (lres.rows, lres.cols)
             d.resid = resid.data_ptr()
             d.res = lres.rowmap()
-        d.desc_mode = desc_mode
         d.max_ctas = max_ctas
         self.desc = d
         self.q_rows = lin.plane_rows
         h = C.c_void_p()
         _lib.check(_lib.lib().pv_srgemm_create(C.byref(d), C.byref(h)), "pv_srgemm_create")
         self.h = h
+
+    def info(self):
+        a, b, c, e = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.check(_lib.lib().pv_srgemm_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(e)), "pv_srgemm_info")
+        return dict(n_ring=a.value, slot_bytes=b.value, resident=c.value, n_acc=e.value)
 
     def run(self, q_rows=None):
         _lib.check(_lib.lib().pv_srgemm_run(self.h, C.c_int64(q_rows or self.q_rows), _lib.stream_ptr()),

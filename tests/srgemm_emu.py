@@ -13,7 +13,8 @@ def _rowmap_index(layout, n, y, x):
     return layout.row_index(n, y, x)
 
 
-def emulate(cp, x_rows, out, lout, scale, shift, relu, resid=None, lres=None, out_f32=False, q_rows=None):
+def emulate(cp, x_rows, out, lout, scale, shift, relu, resid=None, lres=None, out_f32=False, q_rows=None,
+            out_rows_f32=False):
     """x_rows: bf16 [rows, cols] CPU.  Writes into `out` (bf16 matrix of lout, or f32 [B,OH,OW])."""
     lin = cp.lin
     X = x_rows.float()
@@ -53,5 +54,5 @@ def emulate(cp, x_rows, out, lout, scale, shift, relu, resid=None, lres=None, ou
         out.view(-1)[torch.from_numpy((n * cp.OH * cp.OW + y * cp.OW + x).astype(np.int64))] = Yv[:, 0]
     else:
         dr = torch.from_numpy(_rowmap_index(lout, n, y, x).astype(np.int64))
-        out[dr, :N] = Yv.to(torch.bfloat16)
+        out[dr, :N] = Yv if out_rows_f32 else Yv.to(torch.bfloat16)
     return out

@@ -90,3 +90,39 @@ def test_residual_and_f32_out():
     emulate(cp1, xr, o, None, torch.ones(1), torch.zeros(1), relu=False, out_f32=True)
     ref1 = F.conv2d(x.permute(0, 3, 1, 2), w1, padding=1)[:, 0]
     assert torch.allclose(o, ref1, atol=1e-3, rtol=1e-3)
+
+
+def test_single_channel_9x9_as_columns_in_n():
+    """detector last layer: 9x9 conv with one output channel computed as a 9x1 conv whose 9 output
+    channels are the filter columns, then re-assembled by a kw-shifted sum."""
+    torch.manual_seed(7)
+    B, H, W, C, k, pad = 2, 12, 15, 48, 9, 4
+    x = _bf(torch.randn(B, H, W, 45))
+    w = _bf(torch.randn(1, 45, k, k) * 0.05)
+    lin = RowLayout("padded", B, H, W, C, pad=pad)
+    taps = []
+    for kh in range(k):
+        m = torch.zeros(16, lin.cols)
+        m[:k, :45] = w[0, :, kh, :].t()
+        taps.append((kh * lin.Wq, m))
+    OH, OW = H, W
+    cp = ConvPlan.from_taps(lin, taps, k, OH, lin.Wq, group="tap", kernel=(k, 1))
+    assert cp.mma_per_tile == 9 * 3 and cp.resident
+    lpart = RowLayout("padded", B, lin.Hq, lin.Wq, 16, pad=0)
+    D = torch.zeros(lpart.rows, 16)
+    emulate(cp, lin.to_rows(x), D, lpart, torch.ones(k), torch.zeros(k), relu=False, out_rows_f32=True)
+    D = D.reshape(B, lin.Hq, lin.Wq, 16)
+    score = sum(D[:, :OH, kw:kw + OW, kw] for kw in range(k))
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, padding=pad)[:, 0]
+    assert torch.allclose(score, ref, atol=2e-3, rtol=2e-3)
+
+
+def test_slots_cover_entries():
+    w = _bf(torch.randn(45, 48, 5, 5) * 0.1)
+    lin = RowLayout("padded", 1, 20, 30, 48, pad=2)
+    cp = ConvPlan(lin, w, 1, 2, group="row")
+    flags = [e.flags for e in cp.entries]
+    assert flags[0] & 1 and flags[-1] & 2
+    for a, b in zip(flags[:-1], flags[1:]):
+        assert bool(a & 2) == bool(b & 1)
+    assert cp.resident and 1 <= cp.n_slots <= len(cp.entries)

@@ -34,8 +34,7 @@ def test_srgemm_matches_emulator(cuda, kind, B, H, W, cin, cout, k, stride, pad)
     xr = lin.to_rows(x)
     resid = torch.randn(lout.rows, lout.cols).to(torch.bfloat16)
     out = lout.alloc(cuda)
-    op = Srgemm(cp, xr.to(cuda), out, lout, scale, shift, relu=True, resid=resid.to(cuda), lres=lout,
-                desc_mode=config.SRGEMM_DESC_MODE)
+    op = Srgemm(cp, xr.to(cuda), out, lout, scale, shift, relu=True, resid=resid.to(cuda), lres=lout)
     op.run()
     op.check()
     ref = torch.zeros(lout.rows, lout.cols, dtype=torch.bfloat16)

@@ -1,0 +1,88 @@
+"""GPU parity: the correlation-tracker bank (csrc/tracker.cu) against the CPU restatement
+oracle/dsst.py on the same frames.  The chip / FHOG stages are float32-identical by construction;
+the filters are float32 FFTs on the GPU and float64 in the oracle, so PSR and positions are compared
+with a stated tolerance: |dpos| < 0.05 px, |dPSR| < 2 % (after 8 chained updates)."""
+import numpy as np
+import pytest
+import torch
+
+from pyannote_video_b200.geometry import DRect
+from pyannote_video_b200.synth import make_frames
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 0.05
+PSR_RTOL = 0.02
+
+
+def test_tracker_bank_matches_oracle(cuda):
+    from oracle.dsst import CorrelationTracker as OracleTracker
+    from pyannote_video_b200.tracker import TrackerBank
+    frames = make_frames(9, 360, 640, seed=3, shift_per_frame=(2.0, 1.0))
+    rects = [(200.0, 100.0, 296.0, 196.0), (400.5, 150.25, 460.5, 230.0), (-10.0, 20.0, 70.0, 120.0)]
+    bank = TrackerBank(capacity=8, device=cuda)
+    dev_frames = [bank.prepare_frame(f) for f in frames]
+    handles = [bank.start(dev_frames[0], DRect(*r)) for r in rects]
+    oracle = []
+    for r in rects:
+        t = OracleTracker()
+        t.start_track(frames[0].numpy(), r)
+        oracle.append(t)
+    for i in range(1, 9):
+        conf = bank.update(dev_frames[i], handles)
+        for k, t in enumerate(oracle):
+            ref_psr = t.update(frames[i].numpy())
+            ref_pos = t.get_position()
+            got = bank.position(handles[k])
+            got_pos = (got.left(), got.top(), got.right(), got.bottom())
+            assert np.allclose(got_pos, ref_pos, atol=POS_TOL), (i, k, got_pos, ref_pos)
+            assert abs(conf[k] - ref_psr) <= PSR_RTOL * abs(ref_psr), (i, k, conf[k], ref_psr)
+    # known answer: the canvas moves by (-2,-1) px per frame and the trackers follow it with PSR >> 10
+    p = bank.position(handles[0])
+    assert abs((p.left() - 200.0) - (-2.0 * 8)) < 1.0 and abs((p.top() - 100.0) - (-1.0 * 8)) < 1.0
+    assert min(conf[:2]) > 10
+
+
+def test_tracking_by_detection_on_gpu_bank(cuda):
+    """the control loop drives the CUDA bank exactly like a per-object tracker: same tracks as with the
+    oracle tracker plugged in per object."""
+    from oracle.dsst import CorrelationTracker as OracleTracker
+    from pyannote_video_b200.tracker import TrackerBank
+    from pyannote_video_b200.tracking import TrackingByDetection, PerObjectBank
+
+    frames = make_frames(12, 240, 320, seed=5, shift_per_frame=(1.5, 0.5))
+
+    class Seg(object):
+        def __init__(self, end):
+            self.end = end
+
+    class Video(object):
+        frame_rate, size = 25.0, (320, 240)
+        frame_size = (320, 240)
+
+        def __iter__(self):
+            for i in range(frames.shape[0]):
+                yield (i / 25.0, frames[i].numpy())
+
+    def detect(frame):
+        return [(100, 60, 160, 120)] if not hasattr(detect, "done") and not setattr(detect, "done", 1) else []
+
+    def run(bank, prepare):
+        if hasattr(detect, "done"):
+            del detect.done
+        tbd = TrackingByDetection(detect, track_min_confidence=5.0, tracker_bank=bank, prepare_frame=prepare)
+        return [t for t in tbd(Video(), [Seg(10.0)])]
+
+    class OT(OracleTracker):
+        def start_track(self, frame, rect):
+            OracleTracker.start_track(self, frame, (rect.left(), rect.top(), rect.right(), rect.bottom()))
+
+        def get_position(self):
+            return DRect(*self.position)
+
+    ref = run(PerObjectBank(OT), None)
+    gbank = TrackerBank(capacity=8, device=cuda)
+    got = run(gbank, gbank.prepare_frame)
+    assert len(got) == len(ref) == 1
+    for (t1, b1, s1), (t2, b2, s2) in zip(got[0], ref[0]):
+        assert t1 == t2 and s1 == s2 and np.allclose(b1, b2, atol=1.5 / 240)
