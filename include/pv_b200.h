@@ -134,6 +134,11 @@ int pv_srgemm_check(void* handle, void* stream);
  * dlib input_rgb_image(_pyramid/_sized)::to_tensor. kw = 5 (16 cols) or 7 (32 cols). mean_host: 3 floats (HOST). */
 int pv_pack_gathered(const void* rgba, void* out, int B, int H, int W, int kw, int64_t layout_plane_rows,
                      const float* mean_host, void* stream);
+/* RGBA u8 plane -> normalised bf16 RGBX pixels split by row parity (the in-place first-layer input:
+ * srgemm reads 8-pixel runs with x_row_stride_bytes = 16).  layout_plane_rows = rows of one parity plane
+ * of the layout (pixel pairs), W even. */
+int pv_plane_to_pixrows(const void* rgba, void* out, int B, int H, int W, int64_t layout_plane_rows,
+                        const float* mean_host, void* stream);
 /* dlib max_pool<3,3,2,2> (pad 0) on bf16 NHWC [B,H,W,C] -> rows of `dst` */
 int pv_maxpool3x3s2(const void* in, void* out, int B, int H, int W, int C, const PvRowMap* dst, void* stream);
 /* dlib avg_pool<2,2,2,2> skip path of ares_down: parity-layout input -> skip (zero-extended to Cout)

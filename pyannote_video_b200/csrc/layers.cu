@@ -65,6 +65,34 @@ __global__ void pack_gathered_kernel(const uchar4* __restrict__ img, __nv_bfloat
 }
 
 // ---------------------------------------------------------------------------------------------
+// plane_to_pixrows: RGBA u8 [B,H,W,4] -> normalised bf16 RGBX pixels split by row parity
+//   out[((ph*Bcap + n)*Hq + i)*W + x] = A ? ((r,g,b) - mean)/256 : 0, X = 0     (y = 2i + ph)
+// The first conv then reads 8-pixel runs of this buffer in place (overlapping TMA rows).
+// ---------------------------------------------------------------------------------------------
+__global__ void plane_to_pixrows_kernel(const uchar4* __restrict__ img, uint2* __restrict__ out, int B, int H, int W,
+                                        int Hq, long long plane_px, float m0, float m1, float m2) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = 2ll * B * Hq * W;
+  if (idx >= total) return;
+  const int x = (int)(idx % W);
+  long long r = idx / W;
+  const int i = (int)(r % Hq);
+  r /= Hq;
+  const int n = (int)(r % B);
+  const int ph = (int)(r / B);
+  const int y = 2 * i + ph;
+  uint2 o = make_uint2(0u, 0u);
+  if (y < H) {
+    const uchar4 p = img[((long long)n * H + y) * W + x];
+    if (p.w) {
+      o.x = pv_pack_bf16x2(__fmul_rn(__fsub_rn((float)p.x, m0), 0.00390625f), __fmul_rn(__fsub_rn((float)p.y, m1), 0.00390625f));
+      o.y = pv_pack_bf16x2(__fmul_rn(__fsub_rn((float)p.z, m2), 0.00390625f), 0.f);
+    }
+  }
+  out[(long long)ph * plane_px + ((long long)n * Hq + i) * W + x] = o;
+}
+
+// ---------------------------------------------------------------------------------------------
 // maxpool 3x3 stride 2 pad 0 on padded-layout (pad 0) bf16 [B, H, W, C]; 8 channels per thread
 // ---------------------------------------------------------------------------------------------
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
@@ -201,6 +229,22 @@ extern "C" int pv_pack_gathered(const void* rgba, void* out, int B, int H, int W
     pack_gathered_kernel<7, 32><<<(unsigned)blocks, threads, 0, s>>>(
         static_cast<const uchar4*>(rgba), static_cast<__nv_bfloat16*>(out), B, H, W, Hq, Wq, layout_plane_rows, mean_host[0],
         mean_host[1], mean_host[2]);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_plane_to_pixrows(const void* rgba, void* out, int B, int H, int W, int64_t layout_plane_rows,
+                                   const float* mean_host, void* stream) {
+  PV_REQUIRE(rgba && out && mean_host, "pv_plane_to_pixrows: null argument");
+  PV_REQUIRE(W % 2 == 0, "pv_plane_to_pixrows: W=%d must be even", W);
+  const int Hq = (H + 1) / 2;
+  const long long total = 2ll * B * Hq * W;
+  PV_REQUIRE(layout_plane_rows * 2 >= (long long)B * Hq * W, "pv_plane_to_pixrows: layout too small");
+  const int threads = 256;
+  plane_to_pixrows_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uchar4*>(rgba), static_cast<uint2*>(out), B, H, W, Hq, layout_plane_rows * 2, mean_host[0],
+      mean_host[1], mean_host[2]);
   g_pv_launches.fetch_add(1);
   PV_CUDA_CHECK(cudaGetLastError());
   return PV_OK;

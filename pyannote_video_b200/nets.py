@@ -150,7 +150,7 @@ class DetectorNet:
     MAX_CAND = 4096
     MAX_DET = 256
 
-    def __init__(self, model, H, W_, upsample, max_batch, device, group=None):
+    def __init__(self, model, H, W_, upsample, max_batch, device, group=None, conv1_mode=None):
         if model.get("kind") != "mmod_detector":
             raise RuntimeError("DetectorNet: not a detector model")
         group = config.SRGEMM_GROUP if group is None else group
@@ -160,7 +160,8 @@ class DetectorNet:
         self.geo = geo = pyramid_geometry(H, W_, upsample)
         Hp, Wp = geo.plane_h, geo.plane_w
         self.plane = torch.zeros(B, Hp, Wp, 4, dtype=torch.uint8, device=device)
-        lg = RowLayout("gathered", B, Hp, Wp, 3, kw=5)
+        self.conv1_mode = config.DET_CONV1 if conv1_mode is None else conv1_mode
+        lg = RowLayout(self.conv1_mode, B, Hp, Wp, 3, kw=5)
         self.lg, self.xg = lg, lg.alloc(device)
         self.convs = []
         self.flops_per_frame = 0
@@ -246,8 +247,14 @@ class DetectorNet:
         L = _lib.lib()
         st = _lib.stream_ptr()
         geo = self.geo
-        _lib.check(L.pv_pack_gathered(_lib.ptr(self.plane), _lib.ptr(self.xg), M, geo.plane_h, geo.plane_w, 5,
-                                      C.c_int64(self.lg.plane_rows), _mean3(), st), "pv_pack_gathered")
+        if self.conv1_mode == "pixrows":
+            # NB: the pixel buffer is [2, Bcap, Hq, W]; a partial batch writes the first M images of
+            # each parity plane, which is where rows n < M of the layout live.
+            _lib.check(L.pv_plane_to_pixrows(_lib.ptr(self.plane), _lib.ptr(self.xg), M, geo.plane_h, geo.plane_w,
+                                             C.c_int64(self.lg.plane_rows), _mean3(), st), "pv_plane_to_pixrows")
+        else:
+            _lib.check(L.pv_pack_gathered(_lib.ptr(self.plane), _lib.ptr(self.xg), M, geo.plane_h, geo.plane_w, 5,
+                                          C.c_int64(self.lg.plane_rows), _mean3(), st), "pv_pack_gathered")
         for op, img in self.convs:
             op.run(M * img)
         lp = self.lpart

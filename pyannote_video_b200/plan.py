@@ -29,8 +29,9 @@ def round_up(x, m):
 
 class RowLayout:
     def __init__(self, kind, B, H, W, C, pad=0, kw=None):
-        assert kind in ("padded", "parity", "gathered")
+        assert kind in ("padded", "parity", "gathered", "pixrows")
         self.kind, self.B, self.H, self.W, self.C, self.pad, self.kw = kind, B, H, W, C, pad, kw
+        self.row_stride_bytes = 0
         if kind == "padded":
             self.Hq, self.Wq = H + 2 * pad, W + 2 * pad
             self.planes = 1
@@ -39,6 +40,14 @@ class RowLayout:
             self.Hq, self.Wq = (H + 2 * pad + 1) // 2, (W + 2 * pad + 1) // 2
             self.planes = 4
             self.cols = C
+        elif kind == "pixrows":
+            # first-layer input read in place: bf16 RGBX pixels (8 B) of the two row-parity half
+            # planes; matrix row j = the 8 pixels starting at pixel pair j (rows overlap: stride 16 B)
+            assert pad == 0 and C == 3 and kw is not None and kw <= 8 and W % 2 == 0
+            self.Hq, self.Wq = (H + 1) // 2, W // 2
+            self.planes = 2
+            self.cols = 32
+            self.row_stride_bytes = 16
         else:
             assert pad == 0 and kw is not None
             self.Hq, self.Wq = (H + 1) // 2, (W + 1) // 2
@@ -63,6 +72,9 @@ class RowLayout:
         return m
 
     def alloc(self, device):
+        if self.kind == "pixrows":
+            # physical buffer: [2, B, Hq, W] pixels of 4 bf16 + 8 pixels of zero slack
+            return torch.zeros(self.rows * 8 + 32, dtype=torch.bfloat16, device=device)
         return torch.zeros(self.rows, self.cols, dtype=torch.bfloat16, device=device)
 
     # ---- CPU reference scatter/gather (tests, emulator) ----
@@ -80,6 +92,14 @@ class RowLayout:
         B, H, W, Cc = x_nhwc.shape
         assert (B, H, W) == (self.B, self.H, self.W)
         out = torch.zeros(self.rows, self.cols, dtype=torch.float32)
+        if self.kind == "pixrows":
+            phys = torch.zeros(self.rows * 8 + 32)
+            v = phys[:self.rows * 8].view(2, B, self.Hq, W, 4)
+            for ph in range(2):
+                rows_ph = x_nhwc[:, ph::2]
+                v[ph, :, :rows_ph.shape[1], :, :Cc] = rows_ph
+            idx = (torch.arange(self.rows)[:, None] * 8 + torch.arange(32)[None, :])
+            return phys[idx].to(torch.bfloat16)
         if self.kind == "gathered":
             xp = torch.zeros(B, 2 * self.Hq, 2 * self.Wq + self.kw, Cc)
             xp[:, :H, :W] = x_nhwc
@@ -161,6 +181,12 @@ class ConvPlan:
                     wt[:Cout, :Cin] = w[:, :, kh, kw]
                     plane = ((kh + d) & 1) * 2 + ((kw + d) & 1)
                     taps.append((plane * lin.plane_rows + ((kh + d) >> 1) * lin.Wq + ((kw + d) >> 1), wt))
+        elif lin.kind == "pixrows":
+            assert stride == 2 and pad == 0 and KW == lin.kw and Cin == 3
+            for kh in range(KH):
+                wt = torch.zeros(N, 8, 4)
+                wt[:Cout, :KW, :3] = w[:, :, kh, :].permute(0, 2, 1)     # [n][kw][c]
+                taps.append(((kh & 1) * lin.plane_rows + (kh >> 1) * lin.Wq, wt.reshape(N, 32)))
         else:
             assert stride == 2 and pad == 0 and KW == lin.kw and Cin == lin.C
             for kh in range(KH):
@@ -273,6 +299,9 @@ class Srgemm:
                  out_rows_f32=False, max_ctas=0, x_rows=None, x_row_stride_bytes=0):
         lin = cp.lin
         dev = x.device
+        if lin.kind == "pixrows":
+            x_rows, x_row_stride_bytes = lin.rows, lin.row_stride_bytes
+            assert x.dtype == torch.bfloat16 and x.numel() == lin.rows * 8 + 32 and x.is_contiguous()
         if x_rows is None:
             assert x.dtype == torch.bfloat16 and x.shape == (lin.rows, lin.cols) and x.is_contiguous()
         self.cp = cp

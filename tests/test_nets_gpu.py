@@ -50,15 +50,15 @@ def test_embed_net_matches_oracle(cuda):
     assert torch.equal(out2, out[:2])
 
 
-@pytest.mark.parametrize("upsample", [0, 1])
-def test_detector_matches_oracle(cuda, upsample):
+@pytest.mark.parametrize("upsample,conv1_mode", [(0, "gathered"), (1, "gathered"), (1, "pixrows"), (0, "pixrows")])
+def test_detector_matches_oracle(cuda, upsample, conv1_mode):
     from oracle import nets as onets
     from oracle import pyramid as opyr
     from pyannote_video_b200.nets import DetectorNet
     H, Wd = 120, 168
     model = W.make_detector(seed=2, score_bias=0.0)
     frames = make_frames(2, H, Wd, seed=4)
-    net = DetectorNet(model, H, Wd, upsample, max_batch=2, device=cuda)
+    net = DetectorNet(model, H, Wd, upsample, max_batch=2, device=cuda, conv1_mode=conv1_mode)
     fd = frames.to(cuda)
     net.build_plane(fd, 2)
     plane = net.plane[:2].cpu().numpy()

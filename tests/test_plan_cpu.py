@@ -126,3 +126,19 @@ def test_slots_cover_entries():
     for a, b in zip(flags[:-1], flags[1:]):
         assert bool(a & 2) == bool(b & 1)
     assert cp.resident and 1 <= cp.n_slots <= len(cp.entries)
+
+
+def test_stride2_first_layer_read_in_place():
+    """'pixrows': conv1 reads 8-pixel runs straight out of a bf16 RGBX plane (overlapping matrix rows)."""
+    torch.manual_seed(8)
+    B, H, W, k, cout = 2, 23, 30, 5, 16
+    x = _bf(torch.randn(B, H, W, 3))
+    w = _bf(torch.randn(cout, 3, k, k) * 0.1)
+    lin = RowLayout("pixrows", B, H, W, 3, kw=k)
+    cp = ConvPlan(lin, w, 2, 0, group="tap")
+    assert cp.mma_per_tile == 10
+    lout = RowLayout("parity", B, cp.OH, cp.OW, cp.N, pad=0)
+    out = torch.zeros(lout.rows, lout.cols, dtype=torch.bfloat16)
+    emulate(cp, lin.to_rows(x), out, lout, torch.ones(cout), torch.zeros(cout), relu=False)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, stride=2).permute(0, 2, 3, 1)
+    assert torch.allclose(lout.from_rows(out, C=cout), ref, atol=3e-2, rtol=3e-2)
