@@ -269,7 +269,7 @@ def main():
 
     # ---------------- roofline leg: CUDA events around every srgemm launch ----------------
     roof = None
-    if rank == 0:
+    if rank == 0 and args.profile_convs > 0:
         det = face._detector_for(H, W)
         net = face.face_recognition_
         conv_ops = [op for op, _ in det.convs] + [a[0] for k, a in net.ops if k == "conv"]
@@ -285,11 +285,33 @@ def main():
                 b.record()
                 evs.append((a, b))
             op.run = timed_run
+        # coarse stage timing of the same instrumented steps (CUDA events on the launch stream)
+        stage_ev = {}
+
+        def timed_stage(name, fn):
+            def wrapped(*a, **k):
+                e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e_a.record()
+                r = fn(*a, **k)
+                e_b.record()
+                stage_ev.setdefault(name, []).append((e_a, e_b))
+                return r
+            return wrapped
+
+        patched = [(det, "build_plane", "pyramid"), (det, "forward_scores", "pack+convs+shift_sum"), (det, "decode", "decode+nms"),
+                   (face.shape_predictor_, "predict", "landmarks"), (face._chipper, "extract", "chips"),
+                   (net, "forward_chips", "embed")]
+        saved = [(o, n, getattr(o, n)) for o, n, _ in patched]
+        for o, n, label in patched:
+            setattr(o, n, timed_stage(label, getattr(o, n)))
         for s in range(args.profile_convs):
             step_resident(s)
         torch.cuda.synchronize(dev)
+        for o, n, f in saved:
+            setattr(o, n, f)
         for op in conv_ops:
             op.run = orig[id(op)]
+        stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / max(1, args.profile_convs) for k, v in stage_ev.items()}
         conv_ms = sum(a.elapsed_time(b) for a, b in evs)
         flops = args.profile_convs * (B * det.flops_per_frame + B * FACES_PER_FRAME * net.flops_per_face)
         peaks = load_peaks()
@@ -297,7 +319,8 @@ def main():
         roof = dict(bound="tensor", achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
                     frac=achieved / peaks["tf_sustained"], traffic=None, peak_source=peaks["source"],
                     kernel="srgemm_kernel (all %d conv launches/step)" % len(conv_ops),
-                    conv_ms_per_step=conv_ms / args.profile_convs, launches_timed=len(evs))
+                    conv_ms_per_step=conv_ms / args.profile_convs, launches_timed=len(evs),
+                    stage_ms_per_step={k: round(v, 3) for k, v in stage_ms.items()})
 
     if rank != 0:
         if world > 1:

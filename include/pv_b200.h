@@ -116,13 +116,14 @@ typedef struct PvSrgemmDesc {
   const void* resid;    /* bf16 or NULL */
   PvRowMap res;
   int32_t max_ctas;     /* 0 = number of SMs                                                   */
+  int32_t acc_split;    /* TMEM accumulators per tile that consecutive MMAs rotate over (0 = auto) */
 } PvSrgemmDesc;
 
 int pv_srgemm_create(const PvSrgemmDesc* desc, void** out_handle);
 int pv_srgemm_run(void* handle, int64_t q_rows, void* stream);
 int pv_srgemm_destroy(void* handle);
 /* pipeline shape chosen for a plan (ring depth, slot bytes, weights resident?, TMEM accumulators) */
-int pv_srgemm_info(void* handle, int* n_ring, int* slot_bytes, int* resident, int* n_acc);
+int pv_srgemm_info(void* handle, int* n_ring, int* slot_bytes, int* resident, int* n_acc, int* acc_split);
 /* reads (and clears) the device-side error flag of a plan; 0 = none. Synchronises the stream. */
 int pv_srgemm_check(void* handle, void* stream);
 

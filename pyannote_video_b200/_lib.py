@@ -73,6 +73,7 @@ class PvSrgemmDesc(C.Structure):
         ("resid", C.c_void_p),
         ("res", PvRowMap),
         ("max_ctas", C.c_int32),
+        ("acc_split", C.c_int32),
     ]
 
 

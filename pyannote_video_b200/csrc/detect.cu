@@ -43,15 +43,30 @@ __global__ void resize_bilinear_kernel(const uint8_t* __restrict__ src, long lon
     const int bot = min(top + 1, sh - 1), right = min(left + 1, sw - 1);
     const float tb = __fsub_rn(y, (float)top), lr = __fsub_rn(x, (float)left);
     const float omlr = __fsub_rn(1.0f, lr), omtb = __fsub_rn(1.0f, tb);
-    const uint8_t* ptl = s + ((long long)(sy0 + top) * src_pitch_px + sx0 + left) * SRC_CH;
-    const uint8_t* ptr_ = s + ((long long)(sy0 + top) * src_pitch_px + sx0 + right) * SRC_CH;
-    const uint8_t* pbl = s + ((long long)(sy0 + bot) * src_pitch_px + sx0 + left) * SRC_CH;
-    const uint8_t* pbr = s + ((long long)(sy0 + bot) * src_pitch_px + sx0 + right) * SRC_CH;
+    uint8_t tl[3], tr[3], bl[3], br[3];
+    if (SRC_CH == 4) {   // one 4-byte load per tap
+      const uchar4* s4 = reinterpret_cast<const uchar4*>(s);
+      const uchar4 a = s4[(long long)(sy0 + top) * src_pitch_px + sx0 + left];
+      const uchar4 b = s4[(long long)(sy0 + top) * src_pitch_px + sx0 + right];
+      const uchar4 c = s4[(long long)(sy0 + bot) * src_pitch_px + sx0 + left];
+      const uchar4 d = s4[(long long)(sy0 + bot) * src_pitch_px + sx0 + right];
+      tl[0] = a.x; tl[1] = a.y; tl[2] = a.z;
+      tr[0] = b.x; tr[1] = b.y; tr[2] = b.z;
+      bl[0] = c.x; bl[1] = c.y; bl[2] = c.z;
+      br[0] = d.x; br[1] = d.y; br[2] = d.z;
+    } else {
+      const uint8_t* ptl = s + ((long long)(sy0 + top) * src_pitch_px + sx0 + left) * SRC_CH;
+      const uint8_t* ptr_ = s + ((long long)(sy0 + top) * src_pitch_px + sx0 + right) * SRC_CH;
+      const uint8_t* pbl = s + ((long long)(sy0 + bot) * src_pitch_px + sx0 + left) * SRC_CH;
+      const uint8_t* pbr = s + ((long long)(sy0 + bot) * src_pitch_px + sx0 + right) * SRC_CH;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) { tl[ch] = ptl[ch]; tr[ch] = ptr_[ch]; bl[ch] = pbl[ch]; br[ch] = pbr[ch]; }
+    }
     uint8_t res[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-      const float a = __fadd_rn(__fmul_rn(omlr, (float)ptl[ch]), __fmul_rn(lr, (float)ptr_[ch]));
-      const float b = __fadd_rn(__fmul_rn(omlr, (float)pbl[ch]), __fmul_rn(lr, (float)pbr[ch]));
+      const float a = __fadd_rn(__fmul_rn(omlr, (float)tl[ch]), __fmul_rn(lr, (float)tr[ch]));
+      const float b = __fadd_rn(__fmul_rn(omlr, (float)bl[ch]), __fmul_rn(lr, (float)br[ch]));
       float v = __fadd_rn(__fmul_rn(omtb, a), __fmul_rn(tb, b));
       v = floorf(__fadd_rn(v, 0.5f));
       v = fminf(fmaxf(v, 0.f), 255.f);

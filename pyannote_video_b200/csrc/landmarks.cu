@@ -16,6 +16,8 @@ namespace {
 constexpr int kPts = 68;
 constexpr int kMaxPool = 512;
 constexpr int kMaxTrees = 512;
+constexpr int kChunk = 64;            // trees staged per shared-memory chunk
+constexpr int kRow4 = 2 * kPts / 4;    // float4 per leaf row (136 floats)
 
 struct Sim {
   float m00, m01, m10, m11, tx, ty;
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256) ert_kernel(const uint8_t* __restrict__ fr
   __shared__ float s_cur[2 * kPts];
   __shared__ float s_feat[kMaxPool];
   __shared__ uint8_t s_leaf[kMaxTrees];
+  __shared__ float4 s_rows[kChunk * kRow4];
   __shared__ Sim s_sim;
   const int face = blockIdx.x;
   const int tid = threadIdx.x;
@@ -114,13 +117,27 @@ __global__ void __launch_bounds__(256) ert_kernel(const uint8_t* __restrict__ fr
       s_leaf[tr] = (uint8_t)(node - 15);
     }
     __syncthreads();
-    if (tid < 2 * kPts) {
-      float acc = s_cur[tid];
-      const float* lv = m.leaf_values + (long long)s * m.trees * 16 * (2 * kPts) + tid;
-#pragma unroll 8
-      for (int tr = 0; tr < m.trees; ++tr)
-        acc = __fadd_rn(acc, lv[((long long)tr * 16 + s_leaf[tr]) * (2 * kPts)]);
-      s_cur[tid] = acc;
+    // leaf-vector accumulation: rows are staged through shared memory in chunks of kChunk trees
+    // (coalesced 16-byte loads, many in flight), then each coordinate adds its column in tree
+    // order — the oracle's summation order, so the float32 result is bit-identical.
+    {
+      const float4* lv4 = reinterpret_cast<const float4*>(m.leaf_values + (long long)s * m.trees * 16 * (2 * kPts));
+      float acc = (tid < 2 * kPts) ? s_cur[tid] : 0.f;
+      for (int t0 = 0; t0 < m.trees; t0 += kChunk) {
+        const int nt = min(kChunk, m.trees - t0);
+        for (int e = tid; e < nt * kRow4; e += blockDim.x) {
+          const int tr = e / kRow4, c4 = e - tr * kRow4;
+          s_rows[e] = lv4[((long long)(t0 + tr) * 16 + s_leaf[t0 + tr]) * kRow4 + c4];
+        }
+        __syncthreads();
+        if (tid < 2 * kPts) {
+          const float* rows = reinterpret_cast<const float*>(s_rows);
+#pragma unroll 4
+          for (int tr = 0; tr < nt; ++tr) acc = __fadd_rn(acc, rows[tr * (2 * kPts) + tid]);
+        }
+        __syncthreads();
+      }
+      if (tid < 2 * kPts) s_cur[tid] = acc;
     }
     __syncthreads();
   }

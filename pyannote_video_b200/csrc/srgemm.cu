@@ -45,7 +45,9 @@ struct SrParams {
   int res_bytes;         // bytes of the resident region (0 if streamed)
   int res_cls_off[2];    // byte offset of each class inside the resident region
   int res_tiles[2];      // number of N-row weight tiles per class
-  int n_acc;             // TMEM accumulator buffers
+  int n_acc;             // TMEM accumulator buffers (tiles in flight)
+  int acc_split;         // accumulators per tile: consecutive MMAs rotate over them (independent chains)
+  int acc_cols;          // TMEM columns per tile = acc_split * n_out
   int hq, wq, oh, ow, relu, out_mode, has_resid;
   uint32_t tmem_cols;
   int* err;
@@ -63,7 +65,8 @@ __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint3
 // is 32B/64B/128B for KSTEPS = 1/2/4.  Descriptor hi word is a compile-time constant.
 template <int KSTEPS>
 __device__ __forceinline__ void issue_entry(const PvSrEntry& st, int n_taps, int N, uint32_t a_lo, uint32_t b_lo,
-                                            uint32_t tmem_d, uint32_t idesc, uint32_t accum, bool leader) {
+                                            uint32_t tmem_d, uint32_t idesc, uint32_t& mma_idx, uint32_t split,
+                                            bool leader) {
   constexpr uint32_t kLayout = (KSTEPS == 4) ? 2u : (KSTEPS == 2 ? 4u : 6u);
   constexpr uint32_t kSbo16 = (256u * KSTEPS) >> 4;                       // SBO in 16-byte units
   constexpr uint32_t kHi = kSbo16 | (1u << 14) | (kLayout << 29);         // bits [32,64): SBO, version=1, layout
@@ -77,9 +80,12 @@ __device__ __forceinline__ void issue_entry(const PvSrEntry& st, int n_taps, int
       for (int k = 0; k < KSTEPS; ++k) {
         const uint64_t da = ((uint64_t)kHi << 32) | (uint64_t)(aa + 2u * k);
         const uint64_t db = ((uint64_t)kHi << 32) | (uint64_t)(bb + 2u * k);
-        pv_umma_bf16(tmem_d, da, db, idesc, (accum | (uint32_t)t | (uint32_t)k) != 0u ? 1u : 0u);
+        // consecutive MMAs rotate over `split` accumulators: independent dependency chains
+        const uint32_t which = (mma_idx + (uint32_t)k) % split;
+        pv_umma_bf16(tmem_d + which * (uint32_t)N, da, db, idesc, (mma_idx + (uint32_t)k) >= split ? 1u : 0u);
       }
     }
+    mma_idx += KSTEPS;
     bb += b_tap16;
   }
 }
@@ -195,8 +201,9 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       pv_mbar_wait(&bar_tempty[buf], aphase ^ 1u, p.err, 2);
       pv_tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * N);
-      uint32_t accum = 0;
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.acc_cols);
+      uint32_t mma_idx = 0;
+      const uint32_t split = (uint32_t)p.acc_split;
       for (int e = 0; e < p.n_entries; ++e) {
         const PvSrEntry& st = s_entry[e];
         const int width = p.cls_width[st.cls];
@@ -211,13 +218,12 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
                                            : base + (uint32_t)st.b_smem_off;
         const uint32_t b_lo = desc_lo(b_addr);
         if (width == 64) {
-          issue_entry<4>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
+          issue_entry<4>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, mma_idx, split, leader);
         } else if (width == 32) {
-          issue_entry<2>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
+          issue_entry<2>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, mma_idx, split, leader);
         } else {
-          issue_entry<1>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, accum, leader);
+          issue_entry<1>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, mma_idx, split, leader);
         }
-        accum = 1;
         if (st.flags & 2) {
           if (leader) pv_umma_commit(&bar_empty[slot]);  // frees the smem slot once these MMAs retire
           __syncwarp();
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
 
       pv_mbar_wait(&bar_tfull[buf], aphase, p.err, 4);
       pv_tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.acc_cols);
 
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[2][16];
@@ -256,6 +262,17 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
         pv_tmem_ld16(taddr + c0, v[0]);
         if (two) pv_tmem_ld16(taddr + c0 + 16, v[1]);
         pv_tmem_ld_wait();
+        for (int sp = 1; sp < p.acc_split; ++sp) {   // add the other partial accumulators of this tile
+          uint32_t w[2][16];
+          pv_tmem_ld16(taddr + sp * N + c0, w[0]);
+          if (two) pv_tmem_ld16(taddr + sp * N + c0 + 16, w[1]);
+          pv_tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            v[0][j] = __float_as_uint(__uint_as_float(v[0][j]) + __uint_as_float(w[0][j]));
+            if (two) v[1][j] = __float_as_uint(__uint_as_float(v[1][j]) + __uint_as_float(w[1][j]));
+          }
+        }
         if (valid) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -525,11 +542,19 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   p.relu = d->relu;
   p.out_mode = d->out_mode;
   p.has_resid = d->resid != nullptr;
-  int n_acc = 512 / d->n_out;
+  int mma_per_tile = 0;
+  for (int k = 0; k < d->n_entries; ++k) mma_per_tile += ent[k].n_taps * (d->class_width[ent[k].cls] / 16);
+  int split = d->acc_split;
+  if (split <= 0) split = (d->n_out <= 64) ? 4 : (d->n_out <= 128 ? 2 : 1);   // small N: MMAs are latency-, not throughput-bound
+  while (split > 1 && (split > mma_per_tile || split * d->n_out * 2 > 512)) split >>= 1;
+  const int acc_cols = split * d->n_out;
+  int n_acc = 512 / acc_cols;
   if (n_acc > kMaxAcc) n_acc = kMaxAcc;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(n_acc * d->n_out)) cols <<= 1;
+  while (cols < (uint32_t)(n_acc * acc_cols)) cols <<= 1;
   p.n_acc = n_acc;
+  p.acc_split = split;
+  p.acc_cols = acc_cols;
   p.tmem_cols = cols;
   p.err = plan->d_err;
   plan->smem_bytes = (size_t)res_bytes + (size_t)n_ring * slot_bytes + fixed + 1024;
@@ -560,13 +585,14 @@ extern "C" int pv_srgemm_run(void* handle, int64_t q_rows, void* stream) {
   return PV_OK;
 }
 
-extern "C" int pv_srgemm_info(void* handle, int* n_ring, int* slot_bytes, int* resident, int* n_acc) {
+extern "C" int pv_srgemm_info(void* handle, int* n_ring, int* slot_bytes, int* resident, int* n_acc, int* acc_split) {
   PV_REQUIRE(handle, "pv_srgemm_info: null handle");
   SrPlan* plan = static_cast<SrPlan*>(handle);
   if (n_ring) *n_ring = plan->p.n_ring;
   if (slot_bytes) *slot_bytes = plan->p.slot_bytes;
   if (resident) *resident = plan->p.resident;
   if (n_acc) *n_acc = plan->p.n_acc;
+  if (acc_split) *acc_split = plan->p.acc_split;
   return PV_OK;
 }
 

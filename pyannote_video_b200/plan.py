@@ -296,7 +296,7 @@ class Srgemm:
     """A bound srgemm plan: conv + fused affine/residual/ReLU epilogue between device buffers."""
 
     def __init__(self, cp, x, out, lout, scale, shift, relu, resid=None, lres=None, out_f32=False,
-                 out_rows_f32=False, max_ctas=0, x_rows=None, x_row_stride_bytes=0):
+                 out_rows_f32=False, max_ctas=0, x_rows=None, x_row_stride_bytes=0, acc_split=0):
         lin = cp.lin
         dev = x.device
         if lin.kind == "pixrows":
@@ -352,6 +352,7 @@ class Srgemm:
             d.resid = resid.data_ptr()
             d.res = lres.rowmap()
         d.max_ctas = max_ctas
+        d.acc_split = acc_split
         self.desc = d
         self.q_rows = lin.plane_rows
         h = C.c_void_p()
@@ -359,9 +360,10 @@ class Srgemm:
         self.h = h
 
     def info(self):
-        a, b, c, e = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-        _lib.check(_lib.lib().pv_srgemm_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(e)), "pv_srgemm_info")
-        return dict(n_ring=a.value, slot_bytes=b.value, resident=c.value, n_acc=e.value)
+        a, b, c, e, f = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.check(_lib.lib().pv_srgemm_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(e), C.byref(f)),
+                   "pv_srgemm_info")
+        return dict(n_ring=a.value, slot_bytes=b.value, resident=c.value, n_acc=e.value, acc_split=f.value)
 
     def run(self, q_rows=None):
         _lib.check(_lib.lib().pv_srgemm_run(self.h, C.c_int64(q_rows or self.q_rows), _lib.stream_ptr()),

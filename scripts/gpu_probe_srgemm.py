@@ -70,7 +70,7 @@ def run_case(idx):
         out = torch.zeros(B, cp.OH, cp.OW, dtype=torch.float32, device=dev)
     else:
         out = lout.alloc(dev)
-    op = Srgemm(cp, xr, out, lout, scale, shift, relu=not f32, out_f32=f32)
+    op = Srgemm(cp, xr, out, lout, scale, shift, relu=not f32, out_f32=f32, acc_split=int(os.environ.get('PV_ACC_SPLIT', '0')))
     res.update(op.info())
     res.update(n_slots=cp.n_slots)
     op.run()
@@ -125,15 +125,18 @@ def main():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     outp = os.path.join(ROOT, "gpurun_out", "probe_srgemm.jsonl")
     with open(outp, "a") as f:
-        for i, c in enumerate(CASES):
+        splits = [s_ for s_ in os.environ.get("PV_SPLITS", "0").split(",")]
+        for sp_, i, c in [(sp_, i_, c_) for sp_ in splits for (i_, c_) in enumerate(CASES)]:
             if quick and c[-1]:
                 continue
             if only_timing and not c[-1]:
                 continue
             t0 = time.time()
             try:
+                env = dict(os.environ)
+                env["PV_ACC_SPLIT"] = sp_
                 p = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", str(i)],
-                                   capture_output=True, text=True, timeout=300)
+                                   capture_output=True, text=True, timeout=300, env=env)
                 line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
                 if line:
                     rec = json.loads(line[-1][7:])
@@ -142,6 +145,7 @@ def main():
             except subprocess.TimeoutExpired:
                 rec = dict(case=c[0], group=c[10], desc_mode=c[11], error="timeout")
             rec["wall_s"] = round(time.time() - t0, 1)
+            rec["req_split"] = sp_
             f.write(json.dumps(rec) + "\n")
             f.flush()
             print(json.dumps(rec), flush=True)
