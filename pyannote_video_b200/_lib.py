@@ -74,6 +74,7 @@ class PvSrgemmDesc(C.Structure):
         ("res", PvRowMap),
         ("max_ctas", C.c_int32),
         ("acc_split", C.c_int32),
+        ("ctas_per_sm", C.c_int32),
     ]
 
 

@@ -150,8 +150,7 @@ __device__ __forceinline__ void pv_umma_bf16(uint32_t tmem_d, uint64_t desc_a, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n"
       :
-      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
 }
 // single thread: arrive on mbarrier when all previously issued MMAs complete
 __device__ __forceinline__ void pv_umma_commit(uint64_t* bar) {

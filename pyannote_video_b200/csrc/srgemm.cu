@@ -26,11 +26,30 @@ constexpr int kMaxRing = 8;
 constexpr int kMaxAcc = 8;
 constexpr int kTileM = 128;
 
+// One record per tcgen05.mma of a tile, expanded on the host from the entry table so that the
+// single issuing lane does no address arithmetic beyond two adds:
+//   x = A operand offset inside the ring slot (16-byte units), y = B operand offset (inside the slot,
+//   or inside the resident weight region), z = flags:
+//   bit0 wait for the slot's TMA data before issuing, bit1 release the slot after issuing,
+//   bit2 segment class, bit3 accumulate, bits 8.. index of the TMEM accumulator of this tile.
+struct MmaRec {
+  uint32_t a_rel16, b_rel16, flags, pad;
+};
+constexpr int kMaxMma = 320;
+
+__host__ __device__ inline uint32_t desc_hi(int width) {
+  const uint32_t rowb = (uint32_t)width * 2u;
+  const uint32_t layout = width == 64 ? 2u : (width == 32 ? 4u : 6u);
+  return ((8u * rowb) >> 4) | (1u << 14) | (layout << 29);   // SBO, version = 1, swizzle mode
+}
+
 struct SrParams {
   CUtensorMap a_main[2];
   CUtensorMap a_tail[2];
   CUtensorMap b[2];
   const PvSrEntry* entries;
+  const MmaRec* mma;     // [n_mma] per-tile MMA records
+  int n_mma;
   const float* scale;
   const float* shift;
   void* out;
@@ -60,53 +79,24 @@ __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint3
   return (long long)plane * m.plane_rows + (long long)n * m.img + (long long)(Y >> 1) * m.w + (X >> 1);
 }
 
-// Issue the MMAs of one table entry: n_taps taps x KSTEPS k16-steps.  KSTEPS = width/16, so the
-// operand rows are 32*KSTEPS bytes, 8-row groups are 256*KSTEPS bytes apart, and the swizzle mode
-// is 32B/64B/128B for KSTEPS = 1/2/4.  Descriptor hi word is a compile-time constant.
-template <int KSTEPS>
-__device__ __forceinline__ void issue_entry(const PvSrEntry& st, int n_taps, int N, uint32_t a_lo, uint32_t b_lo,
-                                            uint32_t tmem_d, uint32_t idesc, uint32_t& mma_idx, uint32_t split,
-                                            bool leader) {
-  constexpr uint32_t kLayout = (KSTEPS == 4) ? 2u : (KSTEPS == 2 ? 4u : 6u);
-  constexpr uint32_t kSbo16 = (256u * KSTEPS) >> 4;                       // SBO in 16-byte units
-  constexpr uint32_t kHi = kSbo16 | (1u << 14) | (kLayout << 29);         // bits [32,64): SBO, version=1, layout
-  constexpr uint32_t kRow16 = 2u * KSTEPS;                                // one operand row in 16-byte units
-  const uint32_t b_tap16 = (uint32_t)N * kRow16;
-  uint32_t bb = b_lo;
-  for (int t = 0; t < n_taps; ++t) {
-    const uint32_t aa = a_lo + (uint32_t)st.tap_rel[t] * kRow16;
-    if (leader) {
-#pragma unroll
-      for (int k = 0; k < KSTEPS; ++k) {
-        const uint64_t da = ((uint64_t)kHi << 32) | (uint64_t)(aa + 2u * k);
-        const uint64_t db = ((uint64_t)kHi << 32) | (uint64_t)(bb + 2u * k);
-        // consecutive MMAs rotate over `split` accumulators: independent dependency chains
-        const uint32_t which = (mma_idx + (uint32_t)k) % split;
-        pv_umma_bf16(tmem_d + which * (uint32_t)N, da, db, idesc, (mma_idx + (uint32_t)k) >= split ? 1u : 0u);
-      }
-    }
-    mma_idx += KSTEPS;
-    bb += b_tap16;
-  }
-}
-
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 
-__global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_constant__ SrParams p) {
+__global__ void __launch_bounds__(kThreads, 4) srgemm_kernel(const __grid_constant__ SrParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   uint8_t* resw = smem;                                  // resident weights (may be empty)
   uint8_t* ring = smem + p.res_bytes;                    // res_bytes is a multiple of 1024
-  PvSrEntry* s_entry = reinterpret_cast<PvSrEntry*>(ring + (size_t)p.n_ring * p.slot_bytes);
-  float* s_scale = reinterpret_cast<float*>(s_entry + PV_SR_MAX_ENTRIES);
-  float* s_shift = s_scale + 256;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_shift + 256);
+  MmaRec* s_mma = reinterpret_cast<MmaRec*>(ring + (size_t)p.n_ring * p.slot_bytes);       // 16-byte records first
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_mma + p.n_mma);
   uint64_t* bar_empty = bar_full + kMaxRing;
   uint64_t* bar_tfull = bar_empty + kMaxRing;
   uint64_t* bar_tempty = bar_tfull + kMaxAcc;
   uint64_t* bar_res = bar_tempty + kMaxAcc;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_res + 1);
+  float* s_scale = reinterpret_cast<float*>(bar_res + 1);
+  float* s_shift = s_scale + p.n_out;
+  PvSrEntry* s_entry = reinterpret_cast<PvSrEntry*>(s_shift + p.n_out);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_entry + p.n_entries);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,6 +105,8 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
   // ---- one-time setup -------------------------------------------------------
   for (int i = threadIdx.x; i < p.n_entries * (int)(sizeof(PvSrEntry) / 4); i += kThreads)
     reinterpret_cast<uint32_t*>(s_entry)[i] = reinterpret_cast<const uint32_t*>(p.entries)[i];
+  for (int i = threadIdx.x; i < p.n_mma * 4; i += kThreads)
+    reinterpret_cast<uint32_t*>(s_mma)[i] = reinterpret_cast<const uint32_t*>(p.mma)[i];
   for (int i = threadIdx.x; i < N; i += kThreads) {
     s_scale[i] = p.scale[i];
     s_shift[i] = p.shift[i];
@@ -193,7 +185,10 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
       pv_mbar_wait(bar_res, 0, p.err, 5);
       pv_tc_fence_after();
     }
-    const uint32_t res_base = pv_smem_u32(resw);
+    const uint32_t res_lo = desc_lo(pv_smem_u32(resw));
+    const uint32_t ring_base = pv_smem_u32(ring);
+    const uint32_t hi0 = desc_hi(p.cls_width[0]), hi1 = desc_hi(p.cls_width[1]);
+    const int n_mma = p.n_mma;
     int slot = 0;
     uint32_t phase = 0;
     int buf = 0;
@@ -202,29 +197,23 @@ __global__ void __launch_bounds__(kThreads, 1) srgemm_kernel(const __grid_consta
       pv_mbar_wait(&bar_tempty[buf], aphase ^ 1u, p.err, 2);
       pv_tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.acc_cols);
-      uint32_t mma_idx = 0;
-      const uint32_t split = (uint32_t)p.acc_split;
-      for (int e = 0; e < p.n_entries; ++e) {
-        const PvSrEntry& st = s_entry[e];
-        const int width = p.cls_width[st.cls];
-        const int n_taps = st.n_taps;
-        if (st.flags & 1) {
+      uint32_t slot_lo = 0;
+      uint4 rec = *reinterpret_cast<const uint4*>(&s_mma[0]);
+      for (int i = 0; i < n_mma; ++i) {
+        const uint4 cur = rec;
+        if (i + 1 < n_mma) rec = *reinterpret_cast<const uint4*>(&s_mma[i + 1]);   // prefetch the next record
+        if (cur.z & 1u) {
           pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
           pv_tc_fence_after();
+          slot_lo = desc_lo(ring_base + (uint32_t)(slot * p.slot_bytes));
         }
-        const uint32_t base = pv_smem_u32(ring + (size_t)slot * p.slot_bytes);
-        const uint32_t a_lo = desc_lo(base + (uint32_t)st.a_smem_off);
-        const uint32_t b_addr = p.resident ? res_base + (uint32_t)p.res_cls_off[st.cls] + (uint32_t)st.b_row * (uint32_t)(width * 2)
-                                           : base + (uint32_t)st.b_smem_off;
-        const uint32_t b_lo = desc_lo(b_addr);
-        if (width == 64) {
-          issue_entry<4>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, mma_idx, split, leader);
-        } else if (width == 32) {
-          issue_entry<2>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, mma_idx, split, leader);
-        } else {
-          issue_entry<1>(st, n_taps, N, a_lo, b_lo, tmem_d, idesc, mma_idx, split, leader);
-        }
-        if (st.flags & 2) {
+        const uint32_t hi = (cur.z & 4u) ? hi1 : hi0;
+        const uint32_t alo = slot_lo + cur.x;
+        const uint32_t blo = (p.resident ? res_lo : slot_lo) + cur.y;
+        if (leader)
+          pv_umma_bf16(tmem_d + (cur.z >> 8) * (uint32_t)N, ((uint64_t)hi << 32) | alo, ((uint64_t)hi << 32) | blo, idesc,
+                       (cur.z >> 3) & 1u);
+        if (cur.z & 2u) {
           if (leader) pv_umma_commit(&bar_empty[slot]);  // frees the smem slot once these MMAs retire
           __syncwarp();
           if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
@@ -387,6 +376,7 @@ int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, 
 struct SrPlan {
   SrParams p;
   PvSrEntry* d_entries = nullptr;
+  MmaRec* d_mma = nullptr;
   int* d_err = nullptr;
   size_t smem_bytes = 0;
   int num_sms = 0;
@@ -475,9 +465,15 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
       if (!(st.flags & 2)) PV_REQUIRE(e + 1 < d->n_entries && !(ent[e + 1].flags & 1), "srgemm: slot flags inconsistent at entry %d", e);
     }
   }
-  const size_t fixed = sizeof(PvSrEntry) * PV_SR_MAX_ENTRIES + 2 * 256 * sizeof(float) +
-                       (2 * kMaxRing + 2 * kMaxAcc + 1) * sizeof(uint64_t) + 16;
-  const long long budget = 227 * 1024 - 1024 - (long long)fixed - res_bytes;
+  int mma_per_tile = 0;
+  for (int k = 0; k < d->n_entries; ++k) mma_per_tile += ent[k].n_taps * (d->class_width[ent[k].cls] / 16);
+  PV_REQUIRE(mma_per_tile <= kMaxMma, "srgemm: %d MMAs per tile exceed %d", mma_per_tile, kMaxMma);
+  const int cps = d->ctas_per_sm > 1 ? d->ctas_per_sm : 1;
+  PV_REQUIRE(cps == 1 || cps == 2 || cps == 4, "srgemm: ctas_per_sm=%d (1, 2 or 4)", cps);
+  const size_t fixed = sizeof(PvSrEntry) * d->n_entries + sizeof(MmaRec) * mma_per_tile + 2 * d->n_out * sizeof(float) +
+                       (2 * kMaxRing + 2 * kMaxAcc + 1) * sizeof(uint64_t) + 64;
+  // each resident CTA costs 1 KB of reserved shared memory on top of its dynamic allocation
+  const long long budget = (227 * 1024) / cps - 1024 - 1024 - (long long)fixed - res_bytes;
   int n_ring = (int)(budget / slot_bytes);
   if (n_ring > kMaxRing) n_ring = kMaxRing;
   PV_REQUIRE(n_ring >= 2, "srgemm: slot of %d bytes (+%d resident) does not fit a 2-deep ring", slot_bytes, res_bytes);
@@ -493,7 +489,7 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
     delete plan;
     return PV_ERR_CUDA;
   }
-  plan->max_ctas = d->max_ctas > 0 ? d->max_ctas : plan->num_sms;
+  plan->max_ctas = (d->max_ctas > 0 ? d->max_ctas : plan->num_sms) * (d->ctas_per_sm > 1 ? d->ctas_per_sm : 1);
 
   int rc = PV_OK;
   for (int c = 0; c < d->n_classes && rc == PV_OK; ++c) {
@@ -542,19 +538,59 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   p.relu = d->relu;
   p.out_mode = d->out_mode;
   p.has_resid = d->resid != nullptr;
-  int mma_per_tile = 0;
-  for (int k = 0; k < d->n_entries; ++k) mma_per_tile += ent[k].n_taps * (d->class_width[ent[k].cls] / 16);
   int split = d->acc_split;
   if (split <= 0) split = (d->n_out <= 64) ? 4 : (d->n_out <= 128 ? 2 : 1);   // small N: MMAs are latency-, not throughput-bound
-  while (split > 1 && (split > mma_per_tile || split * d->n_out * 2 > 512)) split >>= 1;
+  const int tmem_cap = 512 / cps;
+  while (split > 1 && (split > mma_per_tile || split * d->n_out * 2 > tmem_cap)) split >>= 1;
   const int acc_cols = split * d->n_out;
-  int n_acc = 512 / acc_cols;
+  PV_REQUIRE(acc_cols <= tmem_cap, "srgemm: n_out=%d does not fit %d TMEM columns (ctas_per_sm=%d)", d->n_out, tmem_cap, cps);
+  int n_acc = tmem_cap / acc_cols;
   if (n_acc > kMaxAcc) n_acc = kMaxAcc;
   uint32_t cols = 32;
   while (cols < (uint32_t)(n_acc * acc_cols)) cols <<= 1;
   p.n_acc = n_acc;
   p.acc_split = split;
   p.acc_cols = acc_cols;
+  // ---- expand entries into per-MMA records ----
+  std::vector<MmaRec> recs;
+  {
+    uint32_t idx = 0;
+    for (int k = 0; k < d->n_entries; ++k) {
+      const PvSrEntry& st = ent[k];
+      const int w = d->class_width[st.cls];
+      const int rowb = w * 2;
+      const long long b0 = resident ? (long long)res_cls_off[st.cls] + (long long)st.b_row * rowb : (long long)st.b_smem_off;
+      for (int t = 0; t < st.n_taps; ++t)
+        for (int ks = 0; ks < w / 16; ++ks) {
+          MmaRec r;
+          r.a_rel16 = (uint32_t)((st.a_smem_off + st.tap_rel[t] * rowb + ks * 32) >> 4);
+          r.b_rel16 = (uint32_t)((b0 + (long long)t * d->n_out * rowb + ks * 32) >> 4);
+          r.flags = ((st.cls & 1) << 2) | ((idx >= (uint32_t)split ? 1u : 0u) << 3) | ((idx % (uint32_t)split) << 8);
+          r.pad = 0;
+          if (t == 0 && ks == 0 && (st.flags & 1)) r.flags |= 1u;
+          if (t == st.n_taps - 1 && ks == w / 16 - 1 && (st.flags & 2)) r.flags |= 2u;
+          recs.push_back(r);
+          ++idx;
+        }
+    }
+  }
+  if ((int)recs.size() > kMaxMma) {
+    pv_set_error("srgemm: %d MMAs per tile exceed the table size %d", (int)recs.size(), kMaxMma);
+    cudaFree(plan->d_entries);
+    cudaFree(plan->d_err);
+    delete plan;
+    return PV_ERR_INVALID;
+  }
+  if (cudaMalloc(&plan->d_mma, sizeof(MmaRec) * recs.size()) != cudaSuccess) {
+    pv_set_error("pv_srgemm_create: cudaMalloc failed");
+    cudaFree(plan->d_entries);
+    cudaFree(plan->d_err);
+    delete plan;
+    return PV_ERR_CUDA;
+  }
+  cudaMemcpy(plan->d_mma, recs.data(), sizeof(MmaRec) * recs.size(), cudaMemcpyHostToDevice);
+  p.mma = plan->d_mma;
+  p.n_mma = (int)recs.size();
   p.tmem_cols = cols;
   p.err = plan->d_err;
   plan->smem_bytes = (size_t)res_bytes + (size_t)n_ring * slot_bytes + fixed + 1024;
@@ -618,6 +654,7 @@ extern "C" int pv_srgemm_destroy(void* handle) {
   if (!handle) return PV_OK;
   SrPlan* plan = static_cast<SrPlan*>(handle);
   cudaFree(plan->d_entries);
+  cudaFree(plan->d_mma);
   cudaFree(plan->d_err);
   delete plan;
   return PV_OK;

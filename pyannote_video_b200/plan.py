@@ -154,8 +154,10 @@ SMEM_AVAILABLE = 227 * 1024 - 16 * 1024
 class ConvPlan:
     """Tap table + packed weights for one convolution over a RowLayout."""
 
-    def __init__(self, lin, weight, stride, pad, group="tap", max_b_bytes=40 * 1024, resident_max=RESIDENT_MAX_BYTES):
+    def __init__(self, lin, weight, stride, pad, group="tap", max_b_bytes=40 * 1024, resident_max=RESIDENT_MAX_BYTES,
+                 ctas_per_sm=0):
         """weight: float tensor [Cout, Cin, KH, KW] (dlib/torch order), CPU."""
+        self.ctas_req = ctas_per_sm
         Cout, Cin, KH, KW = weight.shape
         self.lin, self.stride, self.pad, self.KH, self.KW = lin, stride, pad, KH, KW
         N = round_up(Cout, 16)
@@ -198,9 +200,10 @@ class ConvPlan:
 
     @classmethod
     def from_taps(cls, lin, taps, Cout, OH, OW, group="tap", max_b_bytes=40 * 1024, resident_max=RESIDENT_MAX_BYTES,
-                  kernel=(1, 1)):
+                  kernel=(1, 1), ctas_per_sm=0):
         """taps: list of (row offset, W_t float [round_up(Cout,16), lin.cols])"""
         self = cls.__new__(cls)
+        self.ctas_req = ctas_per_sm
         self.lin, self.stride, self.pad = lin, 1, 0
         self.KH, self.KW = kernel
         self._build(list(taps), Cout, OH, OW, group, max_b_bytes, resident_max)
@@ -258,9 +261,9 @@ class ConvPlan:
                     nrows[wd] += N
                 entries.append(st)
         assert len(entries) <= _lib.PV_SR_MAX_ENTRIES, "too many entries: %d" % len(entries)
-        # ---- pack entries into ring slots ----
+        # ---- co-resident CTAs per SM and ring-slot packing ----
         res_bytes = round_up(w_bytes, 1024) + 1024 if self.resident else 0
-        slot_cap = min(SLOT_TARGET_BYTES, (SMEM_AVAILABLE - res_bytes) // 3)
+        n_mma = sum(st.n_taps * (widths[st.cls] // 16) for st in entries)
 
         def ebytes(st):
             wd = widths[st.cls]
@@ -268,6 +271,21 @@ class ConvPlan:
             if not self.resident:
                 b += round_up(st.n_taps * N * wd * 2, 1024)
             return b
+
+        max_entry = max(ebytes(st) for st in entries)
+        fixed = 52 * len(entries) + 16 * n_mma + 8 * N + 512
+
+        def per_cta(cps):
+            return (227 * 1024) // cps - 2048 - fixed - res_bytes
+
+        cands = [self.ctas_req] if self.ctas_req else ([4, 2, 1] if N <= 64 else ([2, 1] if N <= 128 else [1]))
+        cps = 1
+        for c in cands:
+            if per_cta(c) >= 2 * max_entry and 2 * N <= 512 // c:
+                cps = c
+                break
+        self.ctas_per_sm = cps
+        slot_cap = max(max_entry, min(SLOT_TARGET_BYTES // cps, per_cta(cps) // 3))
 
         cur = 0
         for i, st in enumerate(entries):
@@ -296,7 +314,7 @@ class Srgemm:
     """A bound srgemm plan: conv + fused affine/residual/ReLU epilogue between device buffers."""
 
     def __init__(self, cp, x, out, lout, scale, shift, relu, resid=None, lres=None, out_f32=False,
-                 out_rows_f32=False, max_ctas=0, x_rows=None, x_row_stride_bytes=0, acc_split=0):
+                 out_rows_f32=False, max_ctas=0, x_rows=None, x_row_stride_bytes=0, acc_split=0, ctas_per_sm=None):
         lin = cp.lin
         dev = x.device
         if lin.kind == "pixrows":
@@ -353,6 +371,7 @@ class Srgemm:
             d.res = lres.rowmap()
         d.max_ctas = max_ctas
         d.acc_split = acc_split
+        d.ctas_per_sm = cp.ctas_per_sm if ctas_per_sm is None else ctas_per_sm
         self.desc = d
         self.q_rows = lin.plane_rows
         h = C.c_void_p()

@@ -55,8 +55,8 @@ def run_case(idx):
         lin = RowLayout("gathered", B, H, W, 3, kw=k)
     else:
         lin = RowLayout(kind, B, H, W, cin, pad=pad)
-    cp = ConvPlan(lin, w, stride, pad, group=grp)
-    res.update(stages=len(cp.stages), tail=cp.tail_rows, mma_per_tile=cp.mma_per_tile, N=cp.N)
+    cp = ConvPlan(lin, w, stride, pad, group=grp, ctas_per_sm=int(os.environ.get('PV_CTAS', '0')))
+    res.update(ctas=cp.ctas_per_sm, stages=len(cp.stages), tail=cp.tail_rows, mma_per_tile=cp.mma_per_tile, N=cp.N)
     f32 = cout == 1
     lout = RowLayout("padded", B, cp.OH, cp.OW, cp.N, pad=1)
     scale = torch.rand(cout) + 0.5
