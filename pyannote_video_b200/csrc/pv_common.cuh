@@ -47,6 +47,12 @@ __device__ __forceinline__ uint32_t pv_smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+__device__ __forceinline__ uint4 pv_lds128(uint32_t smem_addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr));
+  return v;
+}
+
 // one lane of a converged warp (elect.sync)
 __device__ __forceinline__ bool pv_elect_one() {
   uint32_t pred;

@@ -187,8 +187,11 @@ __global__ void __launch_bounds__(kThreads, 4) srgemm_kernel(const __grid_consta
     }
     const uint32_t res_lo = desc_lo(pv_smem_u32(resw));
     const uint32_t ring_base = pv_smem_u32(ring);
-    const uint32_t hi0 = desc_hi(p.cls_width[0]), hi1 = desc_hi(p.cls_width[1]);
     const int n_mma = p.n_mma;
+    const bool resident = p.resident != 0;
+    const uint32_t slot_bytes = (uint32_t)p.slot_bytes;
+    const int n_ring = p.n_ring, n_acc = p.n_acc, acc_cols = p.acc_cols;
+    const uint32_t mma_tab = pv_smem_u32(s_mma);
     int slot = 0;
     uint32_t phase = 0;
     int buf = 0;
@@ -196,32 +199,32 @@ __global__ void __launch_bounds__(kThreads, 4) srgemm_kernel(const __grid_consta
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       pv_mbar_wait(&bar_tempty[buf], aphase ^ 1u, p.err, 2);
       pv_tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.acc_cols);
-      uint32_t slot_lo = 0;
-      uint4 rec = *reinterpret_cast<const uint4*>(&s_mma[0]);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * acc_cols);
+      uint32_t slot_lo = 0, b_base = res_lo;
+      uint4 rec = pv_lds128(mma_tab);
       for (int i = 0; i < n_mma; ++i) {
         const uint4 cur = rec;
-        if (i + 1 < n_mma) rec = *reinterpret_cast<const uint4*>(&s_mma[i + 1]);   // prefetch the next record
+        if (i + 1 < n_mma) rec = pv_lds128(mma_tab + 16u * (uint32_t)(i + 1));   // prefetch the next record
         if (cur.z & 1u) {
           pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
           pv_tc_fence_after();
-          slot_lo = desc_lo(ring_base + (uint32_t)(slot * p.slot_bytes));
+          slot_lo = desc_lo(ring_base + (uint32_t)slot * slot_bytes);
+          b_base = resident ? res_lo : slot_lo;
         }
-        const uint32_t hi = (cur.z & 4u) ? hi1 : hi0;
+        // record: x/y = operand offsets (16-byte units), w = descriptor hi word, z = flags | TMEM offset << 16
         const uint32_t alo = slot_lo + cur.x;
-        const uint32_t blo = (p.resident ? res_lo : slot_lo) + cur.y;
+        const uint32_t blo = b_base + cur.y;
         if (leader)
-          pv_umma_bf16(tmem_d + (cur.z >> 8) * (uint32_t)N, ((uint64_t)hi << 32) | alo, ((uint64_t)hi << 32) | blo, idesc,
-                       (cur.z >> 3) & 1u);
+          pv_umma_bf16(tmem_d + (cur.z >> 16), ((uint64_t)cur.w << 32) | alo, ((uint64_t)cur.w << 32) | blo, idesc, cur.z & 8u);
         if (cur.z & 2u) {
           if (leader) pv_umma_commit(&bar_empty[slot]);  // frees the smem slot once these MMAs retire
           __syncwarp();
-          if (++slot == p.n_ring) { slot = 0; phase ^= 1u; }
+          if (++slot == n_ring) { slot = 0; phase ^= 1u; }
         }
       }
       if (leader) pv_umma_commit(&bar_tfull[buf]);  // accumulator complete
       __syncwarp();
-      if (++buf == p.n_acc) { buf = 0; aphase ^= 1u; }
+      if (++buf == n_acc) { buf = 0; aphase ^= 1u; }
     }
   } else {
     // ===================== epilogue =====================
@@ -565,8 +568,8 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
           MmaRec r;
           r.a_rel16 = (uint32_t)((st.a_smem_off + st.tap_rel[t] * rowb + ks * 32) >> 4);
           r.b_rel16 = (uint32_t)((b0 + (long long)t * d->n_out * rowb + ks * 32) >> 4);
-          r.flags = ((st.cls & 1) << 2) | ((idx >= (uint32_t)split ? 1u : 0u) << 3) | ((idx % (uint32_t)split) << 8);
-          r.pad = 0;
+          r.flags = ((idx >= (uint32_t)split ? 1u : 0u) << 3) | (((idx % (uint32_t)split) * (uint32_t)d->n_out) << 16);
+          r.pad = desc_hi(w);
           if (t == 0 && ks == 0 && (st.flags & 1)) r.flags |= 1u;
           if (t == st.n_taps - 1 && ks == w / 16 - 1 && (st.flags & 2)) r.flags |= 2u;
           recs.push_back(r);
