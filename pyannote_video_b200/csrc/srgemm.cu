@@ -542,7 +542,8 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   p.out_mode = d->out_mode;
   p.has_resid = d->resid != nullptr;
   int split = d->acc_split;
-  if (split <= 0) split = (d->n_out <= 64) ? 4 : (d->n_out <= 128 ? 2 : 1);   // small N: MMAs are latency-, not throughput-bound
+  if (split <= 0) split = 1;   // measured (gpurun #5): rotating accumulators does not help — the issue loop, not the
+                               // accumulate dependency, bounds small-N layers; kept as an explicit option
   const int tmem_cap = 512 / cps;
   while (split > 1 && (split > mma_per_tile || split * d->n_out * 2 > tmem_cap)) split >>= 1;
   const int acc_cols = split * d->n_out;
