@@ -118,6 +118,7 @@ typedef struct PvSrgemmDesc {
   int32_t max_ctas;     /* 0 = number of SMs                                                   */
   int32_t acc_split;    /* TMEM accumulators per tile that consecutive MMAs rotate over (0 = auto) */
   int32_t ctas_per_sm;  /* 1, 2 or 4 co-resident CTAs per SM (each gets 1/n of smem and TMEM); 0 = 1 */
+  int32_t mma_warps;    /* 1, 2 or 4 MMA-issuing warps per CTA, each with its own accumulator; 0 = 1 */
 } PvSrgemmDesc;
 
 int pv_srgemm_create(const PvSrgemmDesc* desc, void** out_handle);

@@ -75,6 +75,7 @@ class PvSrgemmDesc(C.Structure):
         ("max_ctas", C.c_int32),
         ("acc_split", C.c_int32),
         ("ctas_per_sm", C.c_int32),
+        ("mma_warps", C.c_int32),
     ]
 
 

@@ -21,7 +21,7 @@ extern std::atomic<long long> g_pv_launches;
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreadsBase = 160;   // producer warp + 4 epilogue warps; + 32 per MMA-issuing warp
 constexpr int kMaxRing = 8;
 constexpr int kMaxAcc = 8;
 constexpr int kTileM = 128;
@@ -81,7 +81,9 @@ __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint3
 
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 
-__global__ void __launch_bounds__(kThreads, 4) srgemm_kernel(const __grid_constant__ SrParams p) {
+template <int MMAW>
+__global__ void __launch_bounds__(kThreadsBase + 32 * MMAW, (MMAW == 1 ? 4 : 2)) srgemm_kernel(const __grid_constant__ SrParams p) {
+  constexpr int kThreads = kThreadsBase + 32 * MMAW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -116,16 +118,16 @@ __global__ void __launch_bounds__(kThreads, 4) srgemm_kernel(const __grid_consta
     pv_tma_prefetch_desc(&p.b[0]);
     for (int i = 0; i < p.n_ring; ++i) {
       pv_mbar_init(&bar_full[i], 1);
-      pv_mbar_init(&bar_empty[i], 1);
+      pv_mbar_init(&bar_empty[i], MMAW);     // every MMA warp commits its own MMAs of the slot
     }
     for (int i = 0; i < p.n_acc; ++i) {
-      pv_mbar_init(&bar_tfull[i], 1);
+      pv_mbar_init(&bar_tfull[i], MMAW);
       pv_mbar_init(&bar_tempty[i], 4);
     }
     pv_mbar_init(bar_res, 1);
     pv_fence_mbar_init();
   }
-  if (warp == 1) pv_tmem_alloc(s_tmem, p.tmem_cols);
+  if (warp == 1) pv_tmem_alloc(s_tmem, p.tmem_cols);   // warp 1 owns the TMEM allocation
   pv_tc_fence_before();
   __syncthreads();
   pv_tc_fence_after();
@@ -174,8 +176,11 @@ __global__ void __launch_bounds__(kThreads, 4) srgemm_kernel(const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp <= MMAW) {
+    // ===================== MMA issuer(s) =====================
+    // With MMAW > 1 the MMAs of a tile are dealt round-robin to MMAW warps, each accumulating into its
+    // own TMEM accumulator (the epilogue adds them): MMAW independent single-lane issue streams.
+    const int my = warp - 1;
     // Warp-uniform loop (so descriptors live in uniform registers), one elected lane issues.
     // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, M=128, N
     const bool leader = pv_elect_one();
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 4) srgemm_kernel(const __grid_consta
         // record: x/y = operand offsets (16-byte units), w = descriptor hi word, z = flags | TMEM offset << 16
         const uint32_t alo = slot_lo + cur.x;
         const uint32_t blo = b_base + cur.y;
-        if (leader)
+        if (leader && (MMAW == 1 || (i % MMAW) == my))
           pv_umma_bf16(tmem_d + (cur.z >> 16), ((uint64_t)cur.w << 32) | alo, ((uint64_t)cur.w << 32) | blo, idesc, cur.z & 8u);
         if (cur.z & 2u) {
           if (leader) pv_umma_commit(&bar_empty[slot]);  // frees the smem slot once these MMAs retire
@@ -384,6 +389,7 @@ struct SrPlan {
   size_t smem_bytes = 0;
   int num_sms = 0;
   int max_ctas = 0;
+  int mmaw = 1;
 };
 
 inline int align1k(int v) { return (v + 1023) & ~1023; }
@@ -541,17 +547,21 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   p.relu = d->relu;
   p.out_mode = d->out_mode;
   p.has_resid = d->resid != nullptr;
-  int split = d->acc_split;
+  const int mmaw = (d->mma_warps == 2 || d->mma_warps == 4) ? d->mma_warps : 1;
+  int split = mmaw > 1 ? mmaw : d->acc_split;
   if (split <= 0) split = 1;   // measured (gpurun #5): rotating accumulators does not help — the issue loop, not the
                                // accumulate dependency, bounds small-N layers; kept as an explicit option
   const int tmem_cap = 512 / cps;
-  while (split > 1 && (split > mma_per_tile || split * d->n_out * 2 > tmem_cap)) split >>= 1;
+  if (mmaw == 1)
+    while (split > 1 && (split > mma_per_tile || split * d->n_out * 2 > tmem_cap)) split >>= 1;
+  PV_REQUIRE(mmaw == 1 || (mma_per_tile >= mmaw && cps <= 2), "srgemm: mma_warps=%d needs >= that many MMAs per tile and ctas_per_sm <= 2", mmaw);
   const int acc_cols = split * d->n_out;
   PV_REQUIRE(acc_cols <= tmem_cap, "srgemm: n_out=%d does not fit %d TMEM columns (ctas_per_sm=%d)", d->n_out, tmem_cap, cps);
   int n_acc = tmem_cap / acc_cols;
   if (n_acc > kMaxAcc) n_acc = kMaxAcc;
   uint32_t cols = 32;
   while (cols < (uint32_t)(n_acc * acc_cols)) cols <<= 1;
+  plan->mmaw = mmaw;
   p.n_acc = n_acc;
   p.acc_split = split;
   p.acc_cols = acc_cols;
@@ -599,7 +609,9 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   p.err = plan->d_err;
   plan->smem_bytes = (size_t)res_bytes + (size_t)n_ring * slot_bytes + fixed + 1024;
 
-  e = cudaFuncSetAttribute(srgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  // function-wide: always the maximum
+  e = cudaFuncSetAttribute(srgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);  // function-wide: always the maximum
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(srgemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(srgemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) {
     pv_set_error("pv_srgemm_create: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     cudaFree(plan->d_entries);
@@ -619,7 +631,13 @@ extern "C" int pv_srgemm_run(void* handle, int64_t q_rows, void* stream) {
   p.q_rows = q_rows;
   p.num_tiles = (int)((q_rows + kTileM - 1) / kTileM);
   int grid = p.num_tiles < plan->max_ctas ? p.num_tiles : plan->max_ctas;
-  srgemm_kernel<<<grid, kThreads, plan->smem_bytes, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (plan->mmaw == 4)
+    srgemm_kernel<4><<<grid, kThreadsBase + 128, plan->smem_bytes, st>>>(p);
+  else if (plan->mmaw == 2)
+    srgemm_kernel<2><<<grid, kThreadsBase + 64, plan->smem_bytes, st>>>(p);
+  else
+    srgemm_kernel<1><<<grid, kThreadsBase + 32, plan->smem_bytes, st>>>(p);
   g_pv_launches.fetch_add(1);
   PV_CUDA_CHECK(cudaGetLastError());
   return PV_OK;

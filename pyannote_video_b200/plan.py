@@ -314,7 +314,7 @@ class Srgemm:
     """A bound srgemm plan: conv + fused affine/residual/ReLU epilogue between device buffers."""
 
     def __init__(self, cp, x, out, lout, scale, shift, relu, resid=None, lres=None, out_f32=False,
-                 out_rows_f32=False, max_ctas=0, x_rows=None, x_row_stride_bytes=0, acc_split=0, ctas_per_sm=None):
+                 out_rows_f32=False, max_ctas=0, x_rows=None, x_row_stride_bytes=0, acc_split=0, ctas_per_sm=None, mma_warps=None):
         lin = cp.lin
         dev = x.device
         if lin.kind == "pixrows":
@@ -372,6 +372,10 @@ class Srgemm:
         d.max_ctas = max_ctas
         d.acc_split = acc_split
         d.ctas_per_sm = cp.ctas_per_sm if ctas_per_sm is None else ctas_per_sm
+        if mma_warps is None:
+            # one CTA per SM (big resident weights): spread the issue work over 4 warps instead
+            mma_warps = 4 if (d.ctas_per_sm == 1 and cp.N <= 64 and cp.mma_per_tile >= 8) else 1
+        d.mma_warps = mma_warps
         self.desc = d
         self.q_rows = lin.plane_rows
         h = C.c_void_p()
