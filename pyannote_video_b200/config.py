@@ -1,4 +1,5 @@
 """Build-time decisions that were settled by measurement on B200."""
+import os
 
 # how taps share an A slab in shared memory: "tap" (one TMA slab per tap, always
 # swizzle-atom aligned), "row" (taps of one filter row share a slab, descriptors start at
@@ -10,4 +11,4 @@ SRGEMM_GROUP = "row"   # validated on B200 (gpurun #1): descriptors at arbitrary
 # first detector conv input: "gathered" (pack kernel writes kw*3-wide rows, 16 B/pixel) or
 # "pixrows" (conv reads 8-pixel runs of a bf16 RGBX plane in place through an overlapping-row
 # tensor map, 8 B/pixel; needs cuTensorMapEncodeTiled to accept a 16-byte row stride)
-DET_CONV1 = "gathered"
+DET_CONV1 = os.environ.get("PV_DET_CONV1", "gathered")

@@ -70,7 +70,8 @@ def run_case(idx):
         out = torch.zeros(B, cp.OH, cp.OW, dtype=torch.float32, device=dev)
     else:
         out = lout.alloc(dev)
-    op = Srgemm(cp, xr, out, lout, scale, shift, relu=not f32, out_f32=f32, acc_split=int(os.environ.get('PV_ACC_SPLIT', '0')))
+    op = Srgemm(cp, xr, out, lout, scale, shift, relu=not f32, out_f32=f32, acc_split=int(os.environ.get('PV_ACC_SPLIT', '0')),
+                mma_warps=(int(os.environ['PV_MMAW']) if 'PV_MMAW' in os.environ else None))
     res.update(op.info())
     res.update(n_slots=cp.n_slots)
     op.run()
