@@ -158,6 +158,30 @@ __device__ __forceinline__ void pv_umma_bf16(uint32_t tmem_d, uint64_t desc_a, u
       :
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
 }
+// warp-uniform variant: every lane executes the instruction slot, only lanes with `issue` != 0 issue the
+// MMA (no divergent branch around it, so operands can stay in uniform registers)
+__device__ __forceinline__ void pv_umma_bf16_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue));
+}
+__device__ __forceinline__ void pv_umma_commit_pred(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(pv_smem_u32(bar)),
+      "r"(issue)
+      : "memory");
+}
 // single thread: arrive on mbarrier when all previously issued MMAs complete
 __device__ __forceinline__ void pv_umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(

@@ -35,7 +35,7 @@ constexpr int kTileM = 128;
 struct MmaRec {
   uint32_t a_rel16, b_rel16, flags, pad;
 };
-constexpr int kMaxMma = 320;
+constexpr int kMaxMma = 160;   // records live in the kernel parameter block (constant bank -> uniform loads)
 
 __host__ __device__ inline uint32_t desc_hi(int width) {
   const uint32_t rowb = (uint32_t)width * 2u;
@@ -48,7 +48,6 @@ struct SrParams {
   CUtensorMap a_tail[2];
   CUtensorMap b[2];
   const PvSrEntry* entries;
-  const MmaRec* mma;     // [n_mma] per-tile MMA records
   int n_mma;
   const float* scale;
   const float* shift;
@@ -70,6 +69,7 @@ struct SrParams {
   int hq, wq, oh, ow, relu, out_mode, has_resid;
   uint32_t tmem_cols;
   int* err;
+  uint4 mma[kMaxMma];    // per-tile MMA records (x,y operand offsets, z flags | tmem offset << 16, w descriptor hi)
 };
 
 __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint32_t y, uint32_t x) {
@@ -89,8 +89,7 @@ __global__ void __launch_bounds__(kThreadsBase + 32 * MMAW, (MMAW == 1 ? 4 : 2))
 
   uint8_t* resw = smem;                                  // resident weights (may be empty)
   uint8_t* ring = smem + p.res_bytes;                    // res_bytes is a multiple of 1024
-  MmaRec* s_mma = reinterpret_cast<MmaRec*>(ring + (size_t)p.n_ring * p.slot_bytes);       // 16-byte records first
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_mma + p.n_mma);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(ring + (size_t)p.n_ring * p.slot_bytes);
   uint64_t* bar_empty = bar_full + kMaxRing;
   uint64_t* bar_tfull = bar_empty + kMaxRing;
   uint64_t* bar_tempty = bar_tfull + kMaxAcc;
@@ -107,8 +106,6 @@ __global__ void __launch_bounds__(kThreadsBase + 32 * MMAW, (MMAW == 1 ? 4 : 2))
   // ---- one-time setup -------------------------------------------------------
   for (int i = threadIdx.x; i < p.n_entries * (int)(sizeof(PvSrEntry) / 4); i += kThreads)
     reinterpret_cast<uint32_t*>(s_entry)[i] = reinterpret_cast<const uint32_t*>(p.entries)[i];
-  for (int i = threadIdx.x; i < p.n_mma * 4; i += kThreads)
-    reinterpret_cast<uint32_t*>(s_mma)[i] = reinterpret_cast<const uint32_t*>(p.mma)[i];
   for (int i = threadIdx.x; i < N; i += kThreads) {
     s_scale[i] = p.scale[i];
     s_shift[i] = p.shift[i];
@@ -181,6 +178,7 @@ __global__ void __launch_bounds__(kThreadsBase + 32 * MMAW, (MMAW == 1 ? 4 : 2))
     // With MMAW > 1 the MMAs of a tile are dealt round-robin to MMAW warps, each accumulating into its
     // own TMEM accumulator (the epilogue adds them): MMAW independent single-lane issue streams.
     const int my = warp - 1;
+    const uint32_t lead = pv_elect_one() ? 1u : 0u;
     // Warp-uniform loop (so descriptors live in uniform registers), one elected lane issues.
     // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, M=128, N
     const bool leader = pv_elect_one();
@@ -196,7 +194,6 @@ __global__ void __launch_bounds__(kThreadsBase + 32 * MMAW, (MMAW == 1 ? 4 : 2))
     const bool resident = p.resident != 0;
     const uint32_t slot_bytes = (uint32_t)p.slot_bytes;
     const int n_ring = p.n_ring, n_acc = p.n_acc, acc_cols = p.acc_cols;
-    const uint32_t mma_tab = pv_smem_u32(s_mma);
     int slot = 0;
     uint32_t phase = 0;
     int buf = 0;
@@ -206,10 +203,8 @@ __global__ void __launch_bounds__(kThreadsBase + 32 * MMAW, (MMAW == 1 ? 4 : 2))
       pv_tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * acc_cols);
       uint32_t slot_lo = 0, b_base = res_lo;
-      uint4 rec = pv_lds128(mma_tab);
       for (int i = 0; i < n_mma; ++i) {
-        const uint4 cur = rec;
-        if (i + 1 < n_mma) rec = pv_lds128(mma_tab + 16u * (uint32_t)(i + 1));   // prefetch the next record
+        const uint4 cur = p.mma[i];   // constant-bank load with a uniform index: stays in uniform registers
         if (cur.z & 1u) {
           pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
           pv_tc_fence_after();
@@ -219,16 +214,15 @@ __global__ void __launch_bounds__(kThreadsBase + 32 * MMAW, (MMAW == 1 ? 4 : 2))
         // record: x/y = operand offsets (16-byte units), w = descriptor hi word, z = flags | TMEM offset << 16
         const uint32_t alo = slot_lo + cur.x;
         const uint32_t blo = b_base + cur.y;
-        if (leader && (MMAW == 1 || (i % MMAW) == my))
-          pv_umma_bf16(tmem_d + (cur.z >> 16), ((uint64_t)cur.w << 32) | alo, ((uint64_t)cur.w << 32) | blo, idesc, cur.z & 8u);
+        const uint32_t mine = (MMAW == 1 || (i % MMAW) == my) ? lead : 0u;
+        pv_umma_bf16_pred(tmem_d + (cur.z >> 16), ((uint64_t)cur.w << 32) | alo, ((uint64_t)cur.w << 32) | blo, idesc,
+                          cur.z & 8u, mine);
         if (cur.z & 2u) {
-          if (leader) pv_umma_commit(&bar_empty[slot]);  // frees the smem slot once these MMAs retire
-          __syncwarp();
+          pv_umma_commit_pred(&bar_empty[slot], lead);  // frees the smem slot once these MMAs retire
           if (++slot == n_ring) { slot = 0; phase ^= 1u; }
         }
       }
-      if (leader) pv_umma_commit(&bar_tfull[buf]);  // accumulator complete
-      __syncwarp();
+      pv_umma_commit_pred(&bar_tfull[buf], lead);  // accumulator complete
       if (++buf == n_acc) { buf = 0; aphase ^= 1u; }
     }
   } else {
@@ -384,7 +378,6 @@ int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, 
 struct SrPlan {
   SrParams p;
   PvSrEntry* d_entries = nullptr;
-  MmaRec* d_mma = nullptr;
   int* d_err = nullptr;
   size_t smem_bytes = 0;
   int num_sms = 0;
@@ -479,7 +472,7 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   PV_REQUIRE(mma_per_tile <= kMaxMma, "srgemm: %d MMAs per tile exceed %d", mma_per_tile, kMaxMma);
   const int cps = d->ctas_per_sm > 1 ? d->ctas_per_sm : 1;
   PV_REQUIRE(cps == 1 || cps == 2 || cps == 4, "srgemm: ctas_per_sm=%d (1, 2 or 4)", cps);
-  const size_t fixed = sizeof(PvSrEntry) * d->n_entries + sizeof(MmaRec) * mma_per_tile + 2 * d->n_out * sizeof(float) +
+  const size_t fixed = sizeof(PvSrEntry) * d->n_entries + 2 * d->n_out * sizeof(float) +
                        (2 * kMaxRing + 2 * kMaxAcc + 1) * sizeof(uint64_t) + 64;
   // each resident CTA costs 1 KB of reserved shared memory on top of its dynamic allocation
   const long long budget = (227 * 1024) / cps - 1024 - 1024 - (long long)fixed - res_bytes;
@@ -588,22 +581,7 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
         }
     }
   }
-  if ((int)recs.size() > kMaxMma) {
-    pv_set_error("srgemm: %d MMAs per tile exceed the table size %d", (int)recs.size(), kMaxMma);
-    cudaFree(plan->d_entries);
-    cudaFree(plan->d_err);
-    delete plan;
-    return PV_ERR_INVALID;
-  }
-  if (cudaMalloc(&plan->d_mma, sizeof(MmaRec) * recs.size()) != cudaSuccess) {
-    pv_set_error("pv_srgemm_create: cudaMalloc failed");
-    cudaFree(plan->d_entries);
-    cudaFree(plan->d_err);
-    delete plan;
-    return PV_ERR_CUDA;
-  }
-  cudaMemcpy(plan->d_mma, recs.data(), sizeof(MmaRec) * recs.size(), cudaMemcpyHostToDevice);
-  p.mma = plan->d_mma;
+  for (size_t k = 0; k < recs.size(); ++k) p.mma[k] = make_uint4(recs[k].a_rel16, recs[k].b_rel16, recs[k].flags, recs[k].pad);
   p.n_mma = (int)recs.size();
   p.tmem_cols = cols;
   p.err = plan->d_err;
@@ -676,7 +654,6 @@ extern "C" int pv_srgemm_destroy(void* handle) {
   if (!handle) return PV_OK;
   SrPlan* plan = static_cast<SrPlan*>(handle);
   cudaFree(plan->d_entries);
-  cudaFree(plan->d_mma);
   cudaFree(plan->d_err);
   delete plan;
   return PV_OK;
