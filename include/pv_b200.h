@@ -160,6 +160,11 @@ int pv_embed_head(const void* in, int B, int HW, int C, const float* fc, float* 
 int pv_resize_bilinear(const void* src, int src_channels, int64_t src_img_stride_bytes, int src_pitch_px, int sx0,
                        int sy0, int sw, int sh, void* dst_rgba, int64_t dst_img_stride_px, int dst_pitch_px, int dx0,
                        int dy0, int dw, int dh, float xs, float ys, int B, int copy_only, void* stream);
+/* the small levels of the pyramid in ONE launch: one CTA per image builds levels k0..L-1 in order, each
+ * from its predecessor inside the plane. rects_host i32 [(n_levels+1),4] (source level first), scales_host
+ * f32 [n_levels,2]; both HOST arrays. */
+int pv_pyramid_tail(void* plane_rgba, int64_t img_stride_px, int pitch_px, int B, int n_levels, const int* rects_host,
+                    const float* scales_host, void* stream);
 /* the 9x9 single-channel last conv runs as a 9x1 conv with the filter columns as channels;
  * score[n,y,x] = bias + sum_kw D[(n*Hq+y)*Wq + x+kw][kw] re-assembles it (D fp32 [rows, cols]) */
 int pv_det_shift_sum(const float* D, int B, int Hq, int Wq, int cols, int OH, int OW, int KW, float bias, float* scores,

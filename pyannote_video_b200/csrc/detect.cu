@@ -14,69 +14,104 @@ extern std::atomic<long long> g_pv_launches;
 
 namespace {
 
+// one output pixel of dlib's resize_image/interpolate_bilinear (explicitly rounded, unfused float32)
+template <int SRC_CH>
+__device__ __forceinline__ uchar4 bilinear_px(const uint8_t* __restrict__ s, int src_pitch_px, int sx0, int sy0, int sw,
+                                              int sh, int r, int c, float xs, float ys) {
+  uchar4 o;
+  o.w = 255;
+  const float y = __fmul_rn((float)r, ys);
+  const float x = __fmul_rn((float)c, xs);
+  int top = (int)floorf(y), left = (int)floorf(x);
+  top = min(top, sh - 1);
+  left = min(left, sw - 1);
+  const int bot = min(top + 1, sh - 1), right = min(left + 1, sw - 1);
+  const float tb = __fsub_rn(y, (float)top), lr = __fsub_rn(x, (float)left);
+  const float omlr = __fsub_rn(1.0f, lr), omtb = __fsub_rn(1.0f, tb);
+  uint8_t tl[3], tr[3], bl[3], br[3];
+  if (SRC_CH == 4) {   // one 4-byte load per tap
+    const uchar4* s4 = reinterpret_cast<const uchar4*>(s);
+    const uchar4 a = s4[(long long)(sy0 + top) * src_pitch_px + sx0 + left];
+    const uchar4 b = s4[(long long)(sy0 + top) * src_pitch_px + sx0 + right];
+    const uchar4 cc = s4[(long long)(sy0 + bot) * src_pitch_px + sx0 + left];
+    const uchar4 d = s4[(long long)(sy0 + bot) * src_pitch_px + sx0 + right];
+    tl[0] = a.x; tl[1] = a.y; tl[2] = a.z;
+    tr[0] = b.x; tr[1] = b.y; tr[2] = b.z;
+    bl[0] = cc.x; bl[1] = cc.y; bl[2] = cc.z;
+    br[0] = d.x; br[1] = d.y; br[2] = d.z;
+  } else {
+    const uint8_t* ptl = s + ((long long)(sy0 + top) * src_pitch_px + sx0 + left) * SRC_CH;
+    const uint8_t* ptr_ = s + ((long long)(sy0 + top) * src_pitch_px + sx0 + right) * SRC_CH;
+    const uint8_t* pbl = s + ((long long)(sy0 + bot) * src_pitch_px + sx0 + left) * SRC_CH;
+    const uint8_t* pbr = s + ((long long)(sy0 + bot) * src_pitch_px + sx0 + right) * SRC_CH;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) { tl[ch] = ptl[ch]; tr[ch] = ptr_[ch]; bl[ch] = pbl[ch]; br[ch] = pbr[ch]; }
+  }
+  uint8_t res[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float a = __fadd_rn(__fmul_rn(omlr, (float)tl[ch]), __fmul_rn(lr, (float)tr[ch]));
+    const float b = __fadd_rn(__fmul_rn(omlr, (float)bl[ch]), __fmul_rn(lr, (float)br[ch]));
+    float v = __fadd_rn(__fmul_rn(omtb, a), __fmul_rn(tb, b));
+    v = floorf(__fadd_rn(v, 0.5f));
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    res[ch] = (uint8_t)v;
+  }
+  o.x = res[0];
+  o.y = res[1];
+  o.z = res[2];
+  return o;
+}
+
+// 2-D launch: blockIdx.z = image, (blockIdx.y, blockIdx.x) tiles of 8 x 32 output pixels
 template <int SRC_CH>
 __global__ void resize_bilinear_kernel(const uint8_t* __restrict__ src, long long src_img_stride, int src_pitch_px,
                                        int sx0, int sy0, int sw, int sh, uchar4* __restrict__ dst,
                                        long long dst_img_stride, int dst_pitch_px, int dx0, int dy0, int dw, int dh,
                                        float xs, float ys, int B, int copy_only) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * dw * dh;
-  if (idx >= total) return;
-  const int c = (int)(idx % dw);
-  long long r_ = idx / dw;
-  const int r = (int)(r_ % dh);
-  const int n = (int)(r_ / dh);
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int n = blockIdx.z;
+  if (c >= dw || r >= dh) return;
   const uint8_t* s = src + (long long)n * src_img_stride;
   uchar4 o;
-  o.w = 255;
   if (copy_only) {
     const uint8_t* p = s + ((long long)(sy0 + r) * src_pitch_px + sx0 + c) * SRC_CH;
-    o.x = p[0];
-    o.y = p[1];
-    o.z = p[2];
+    o = make_uchar4(p[0], p[1], p[2], 255);
   } else {
-    const float y = __fmul_rn((float)r, ys);
-    const float x = __fmul_rn((float)c, xs);
-    int top = (int)floorf(y), left = (int)floorf(x);
-    top = min(top, sh - 1);
-    left = min(left, sw - 1);
-    const int bot = min(top + 1, sh - 1), right = min(left + 1, sw - 1);
-    const float tb = __fsub_rn(y, (float)top), lr = __fsub_rn(x, (float)left);
-    const float omlr = __fsub_rn(1.0f, lr), omtb = __fsub_rn(1.0f, tb);
-    uint8_t tl[3], tr[3], bl[3], br[3];
-    if (SRC_CH == 4) {   // one 4-byte load per tap
-      const uchar4* s4 = reinterpret_cast<const uchar4*>(s);
-      const uchar4 a = s4[(long long)(sy0 + top) * src_pitch_px + sx0 + left];
-      const uchar4 b = s4[(long long)(sy0 + top) * src_pitch_px + sx0 + right];
-      const uchar4 c = s4[(long long)(sy0 + bot) * src_pitch_px + sx0 + left];
-      const uchar4 d = s4[(long long)(sy0 + bot) * src_pitch_px + sx0 + right];
-      tl[0] = a.x; tl[1] = a.y; tl[2] = a.z;
-      tr[0] = b.x; tr[1] = b.y; tr[2] = b.z;
-      bl[0] = c.x; bl[1] = c.y; bl[2] = c.z;
-      br[0] = d.x; br[1] = d.y; br[2] = d.z;
-    } else {
-      const uint8_t* ptl = s + ((long long)(sy0 + top) * src_pitch_px + sx0 + left) * SRC_CH;
-      const uint8_t* ptr_ = s + ((long long)(sy0 + top) * src_pitch_px + sx0 + right) * SRC_CH;
-      const uint8_t* pbl = s + ((long long)(sy0 + bot) * src_pitch_px + sx0 + left) * SRC_CH;
-      const uint8_t* pbr = s + ((long long)(sy0 + bot) * src_pitch_px + sx0 + right) * SRC_CH;
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) { tl[ch] = ptl[ch]; tr[ch] = ptr_[ch]; bl[ch] = pbl[ch]; br[ch] = pbr[ch]; }
-    }
-    uint8_t res[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      const float a = __fadd_rn(__fmul_rn(omlr, (float)tl[ch]), __fmul_rn(lr, (float)tr[ch]));
-      const float b = __fadd_rn(__fmul_rn(omlr, (float)bl[ch]), __fmul_rn(lr, (float)br[ch]));
-      float v = __fadd_rn(__fmul_rn(omtb, a), __fmul_rn(tb, b));
-      v = floorf(__fadd_rn(v, 0.5f));
-      v = fminf(fmaxf(v, 0.f), 255.f);
-      res[ch] = (uint8_t)v;
-    }
-    o.x = res[0];
-    o.y = res[1];
-    o.z = res[2];
+    o = bilinear_px<SRC_CH>(s, src_pitch_px, sx0, sy0, sw, sh, r, c, xs, ys);
   }
   dst[(long long)n * dst_img_stride + (long long)(dy0 + r) * dst_pitch_px + dx0 + c] = o;
+}
+
+// the small tail of the pyramid (levels k0 .. L-1, each resized from its predecessor inside the plane):
+// one CTA per image walks the levels in order, __syncthreads() between levels.
+struct PyrLevel {
+  int x0, y0, w, h;
+  float xs, ys;   // scale from the previous level
+};
+constexpr int kMaxTail = 40;
+struct PyrTail {
+  int n;                     // number of levels to build
+  PyrLevel prev;             // rectangle of level k0-1 (source of the first one)
+  PyrLevel lv[kMaxTail];
+};
+
+__global__ void __launch_bounds__(1024) pyramid_tail_kernel(uchar4* __restrict__ plane, long long img_stride_px,
+                                                            int pitch_px, const __grid_constant__ PyrTail t) {
+  uchar4* img = plane + (long long)blockIdx.x * img_stride_px;
+  PyrLevel src = t.prev;
+  for (int k = 0; k < t.n; ++k) {
+    const PyrLevel d = t.lv[k];
+    const int total = d.w * d.h;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int r = i / d.w, c = i - r * d.w;
+      img[(long long)(d.y0 + r) * pitch_px + d.x0 + c] =
+          bilinear_px<4>(reinterpret_cast<const uint8_t*>(img), pitch_px, src.x0, src.y0, src.w, src.h, r, c, d.xs, d.ys);
+    }
+    __syncthreads();   // level k complete (and visible to this CTA) before level k+1 reads it
+    src = d;
+  }
 }
 
 // score[n,y,x] = bias + sum_kw D[(n*Hq + y)*Wq + x + kw][kw]   (D: fp32 rows of `cols` columns)
@@ -246,9 +281,8 @@ extern "C" int pv_resize_bilinear(const void* src, int src_channels, int64_t src
   PV_REQUIRE(src && dst_rgba, "pv_resize_bilinear: null argument");
   PV_REQUIRE(src_channels == 3 || src_channels == 4, "pv_resize_bilinear: src_channels=%d", src_channels);
   PV_REQUIRE(sw > 0 && sh > 0 && dw > 0 && dh > 0 && B > 0, "pv_resize_bilinear: empty rect");
-  const long long total = (long long)B * dw * dh;
   const int threads = 256;
-  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  const dim3 blocks((unsigned)((dw + 31) / 32), (unsigned)((dh + 7) / 8), (unsigned)B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (src_channels == 3)
     resize_bilinear_kernel<3><<<blocks, threads, 0, s>>>(static_cast<const uint8_t*>(src), src_img_stride, src_pitch_px,
@@ -260,6 +294,28 @@ extern "C" int pv_resize_bilinear(const void* src, int src_channels, int64_t src
                                                          sx0, sy0, sw, sh, static_cast<uchar4*>(dst_rgba),
                                                          dst_img_stride_px, dst_pitch_px, dx0, dy0, dw, dh, xs, ys, B,
                                                          copy_only);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_pyramid_tail(void* plane_rgba, int64_t img_stride_px, int pitch_px, int B, int n_levels,
+                               const int* rects_host, const float* scales_host, void* stream) {
+  /* rects_host: [(n_levels+1), 4] x0,y0,w,h with the source level first; scales_host: [n_levels, 2] xs,ys */
+  PV_REQUIRE(plane_rgba && rects_host && scales_host, "pv_pyramid_tail: null argument");
+  PV_REQUIRE(n_levels >= 1 && n_levels <= kMaxTail, "pv_pyramid_tail: n_levels=%d", n_levels);
+  PyrTail t;
+  t.n = n_levels;
+  t.prev.x0 = rects_host[0]; t.prev.y0 = rects_host[1]; t.prev.w = rects_host[2]; t.prev.h = rects_host[3];
+  t.prev.xs = t.prev.ys = 0.f;
+  for (int k = 0; k < n_levels; ++k) {
+    const int* r = rects_host + 4 * (k + 1);
+    t.lv[k].x0 = r[0]; t.lv[k].y0 = r[1]; t.lv[k].w = r[2]; t.lv[k].h = r[3];
+    t.lv[k].xs = scales_host[2 * k];
+    t.lv[k].ys = scales_host[2 * k + 1];
+  }
+  pyramid_tail_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uchar4*>(plane_rgba), img_stride_px,
+                                                                      pitch_px, t);
   g_pv_launches.fetch_add(1);
   PV_CUDA_CHECK(cudaGetLastError());
   return PV_OK;

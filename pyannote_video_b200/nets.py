@@ -149,6 +149,7 @@ class DetectorNet:
 
     MAX_CAND = 4096
     MAX_DET = 256
+    TAIL_PIXELS = 250000      # pyramid levels at most this large are built by the one-launch tail kernel
 
     def __init__(self, model, H, W_, upsample, max_batch, device, group=None, conv1_mode=None):
         if model.get("kind") != "mmod_detector":
@@ -205,6 +206,18 @@ class DetectorNet:
             self.flops_per_frame += 2 * (self.OH * self.OW if last else cp.OH * cp.OW) * cout * cin * k * k
             if not last:
                 lcur, cur = lo, o
+        # pyramid: big levels one launch each, the small tail (<= TAIL_PIXELS per level) in one launch
+        f32 = np.float32
+        tail_from = next((i for i, (w, h) in enumerate(geo.sizes) if i >= 1 and w * h <= self.TAIL_PIXELS), geo.n_levels)
+        self._tail_from = tail_from
+        self._tail_n = geo.n_levels - tail_from
+        if self._tail_n > 0:
+            self._tail_rects = np.asarray(geo.rects[tail_from - 1:], np.int32).reshape(-1, 4).copy()
+            sc = []
+            for lv in range(tail_from, geo.n_levels):
+                (pw, ph), (w, h) = geo.sizes[lv - 1], geo.sizes[lv]
+                sc.append((f32(pw - 1) / f32(max(w - 1, 1)), f32(ph - 1) / f32(max(h - 1, 1))))
+            self._tail_scales = np.asarray(sc, np.float32).reshape(-1, 2).copy()
         rects, fxy = geo.level_table()
         self.level_rects = _t(rects).to(device)
         self.level_fxy = _t(fxy).to(device)
@@ -225,7 +238,8 @@ class DetectorNet:
         Hp, Wp = geo.plane_h, geo.plane_w
         f32 = np.float32
         prev = None
-        for lv, (x0, y0, w, h) in enumerate(geo.rects):
+        tail_from = self._tail_from
+        for lv, (x0, y0, w, h) in enumerate(geo.rects[:tail_from]):
             if lv == 0:
                 sw, sh = self.W, self.H
                 xs = float(f32(sw - 1) / f32(max(w - 1, 1)))
@@ -242,6 +256,10 @@ class DetectorNet:
                                                 _lib.ptr(self.plane), C.c_int64(Hp * Wp), Wp, x0, y0, w, h,
                                                 C.c_float(xs), C.c_float(ys), M, 0, st), "pv_resize_bilinear")
             prev = (x0, y0, w, h)
+        if self._tail_n > 0:
+            _lib.check(L.pv_pyramid_tail(_lib.ptr(self.plane), C.c_int64(Hp * Wp), Wp, M, self._tail_n,
+                                         self._tail_rects.ctypes.data_as(C.POINTER(C.c_int)),
+                                         self._tail_scales.ctypes.data_as(C.POINTER(C.c_float)), st), "pv_pyramid_tail")
 
     def forward_scores(self, M):
         L = _lib.lib()
