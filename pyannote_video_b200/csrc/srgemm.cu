@@ -69,7 +69,9 @@ struct SrParams {
   int hq, wq, oh, ow, relu, out_mode, has_resid;
   uint32_t tmem_cols;
   int* err;
-  uint4 mma[kMaxMma];    // per-tile MMA records (x,y operand offsets, z flags | tmem offset << 16, w descriptor hi)
+  int n_mma_w[4];        // records per MMA warp
+  uint4 mma[kMaxMma];    // per-tile MMA records, warp w's list starts at w * (kMaxMma / MMAW)
+                         // (x,y operand offsets, z flags | tmem offset << 16, w descriptor hi)
 };
 
 __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint32_t y, uint32_t x) {
@@ -190,7 +192,8 @@ __global__ void __launch_bounds__(kThreadsBase + 32 * MMAW, (MMAW == 1 ? 4 : 2))
     }
     const uint32_t res_lo = desc_lo(pv_smem_u32(resw));
     const uint32_t ring_base = pv_smem_u32(ring);
-    const int n_mma = p.n_mma;
+    const int n_mine = p.n_mma_w[my];
+    const int tab0 = my * (kMaxMma / MMAW);
     const bool resident = p.resident != 0;
     const uint32_t slot_bytes = (uint32_t)p.slot_bytes;
     const int n_ring = p.n_ring, n_acc = p.n_acc, acc_cols = p.acc_cols;
@@ -203,8 +206,8 @@ __global__ void __launch_bounds__(kThreadsBase + 32 * MMAW, (MMAW == 1 ? 4 : 2))
       pv_tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * acc_cols);
       uint32_t slot_lo = 0, b_base = res_lo;
-      for (int i = 0; i < n_mma; ++i) {
-        const uint4 cur = p.mma[i];   // constant-bank load with a uniform index: stays in uniform registers
+      for (int i = 0; i < n_mine; ++i) {
+        const uint4 cur = p.mma[tab0 + i];   // constant-bank load
         if (cur.z & 1u) {
           pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
           pv_tc_fence_after();
@@ -214,9 +217,8 @@ __global__ void __launch_bounds__(kThreadsBase + 32 * MMAW, (MMAW == 1 ? 4 : 2))
         // record: x/y = operand offsets (16-byte units), w = descriptor hi word, z = flags | TMEM offset << 16
         const uint32_t alo = slot_lo + cur.x;
         const uint32_t blo = b_base + cur.y;
-        const uint32_t mine = (MMAW == 1 || (i % MMAW) == my) ? lead : 0u;
         pv_umma_bf16_pred(tmem_d + (cur.z >> 16), ((uint64_t)cur.w << 32) | alo, ((uint64_t)cur.w << 32) | blo, idesc,
-                          cur.z & 8u, mine);
+                          cur.z & 8u, lead);
         if (cur.z & 2u) {
           pv_umma_commit_pred(&bar_empty[slot], lead);  // frees the smem slot once these MMAs retire
           if (++slot == n_ring) { slot = 0; phase ^= 1u; }
@@ -558,12 +560,15 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
   p.n_acc = n_acc;
   p.acc_split = split;
   p.acc_cols = acc_cols;
-  // ---- expand entries into per-MMA records ----
-  std::vector<MmaRec> recs;
+  // ---- expand entries into per-MMA records, dealt round-robin to the MMA warps ----
   {
+    std::vector<MmaRec> lists[4];
+    std::vector<int> slot_of[4];
     uint32_t idx = 0;
+    int slot_id = -1;
     for (int k = 0; k < d->n_entries; ++k) {
       const PvSrEntry& st = ent[k];
+      if (st.flags & 1) ++slot_id;
       const int w = d->class_width[st.cls];
       const int rowb = w * 2;
       const long long b0 = resident ? (long long)res_cls_off[st.cls] + (long long)st.b_row * rowb : (long long)st.b_smem_off;
@@ -574,15 +579,38 @@ extern "C" int pv_srgemm_create(const PvSrgemmDesc* d, void** out_handle) {
           r.b_rel16 = (uint32_t)((b0 + (long long)t * d->n_out * rowb + ks * 32) >> 4);
           r.flags = ((idx >= (uint32_t)split ? 1u : 0u) << 3) | (((idx % (uint32_t)split) * (uint32_t)d->n_out) << 16);
           r.pad = desc_hi(w);
-          if (t == 0 && ks == 0 && (st.flags & 1)) r.flags |= 1u;
-          if (t == st.n_taps - 1 && ks == w / 16 - 1 && (st.flags & 2)) r.flags |= 2u;
-          recs.push_back(r);
+          const int wp = mmaw > 1 ? (int)(idx % (uint32_t)mmaw) : 0;
+          lists[wp].push_back(r);
+          slot_of[wp].push_back(slot_id);
           ++idx;
         }
     }
+    const int n_slots = slot_id + 1;
+    const int cap = kMaxMma / mmaw;
+    bool ok = true;
+    for (int wp = 0; wp < mmaw && ok; ++wp) {
+      if ((int)lists[wp].size() > cap) ok = false;
+      // bit0 on the warp's first record of every slot (wait for the data), bit1 on its last (release the slot)
+      int seen = 0;
+      for (size_t k = 0; k < lists[wp].size(); ++k) {
+        if (k == 0 || slot_of[wp][k] != slot_of[wp][k - 1]) { lists[wp][k].flags |= 1u; ++seen; }
+        if (k + 1 == lists[wp].size() || slot_of[wp][k + 1] != slot_of[wp][k]) lists[wp][k].flags |= 2u;
+      }
+      if (seen != n_slots) ok = false;   // every warp must touch every slot (it owes the slot one commit)
+      p.n_mma_w[wp] = (int)lists[wp].size();
+      for (size_t k = 0; k < lists[wp].size(); ++k)
+        p.mma[wp * cap + k] = make_uint4(lists[wp][k].a_rel16, lists[wp][k].b_rel16, lists[wp][k].flags, lists[wp][k].pad);
+    }
+    if (!ok) {
+      pv_set_error("srgemm: MMA table does not fit (mma_warps=%d, %d MMAs/tile, %d slots)", mmaw, mma_per_tile, n_slots);
+      cudaFree(plan->d_entries);
+      cudaFree(plan->d_err);
+      delete plan;
+      return PV_ERR_INVALID;
+    }
   }
-  for (size_t k = 0; k < recs.size(); ++k) p.mma[k] = make_uint4(recs[k].a_rel16, recs[k].b_rel16, recs[k].flags, recs[k].pad);
-  p.n_mma = (int)recs.size();
+  p.n_mma = mma_per_tile;
+
   p.tmem_cols = cols;
   p.err = plan->d_err;
   plan->smem_bytes = (size_t)res_bytes + (size_t)n_ring * slot_bytes + fixed + 1024;

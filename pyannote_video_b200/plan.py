@@ -373,9 +373,22 @@ class Srgemm:
         d.acc_split = acc_split
         d.ctas_per_sm = cp.ctas_per_sm if ctas_per_sm is None else ctas_per_sm
         if mma_warps is None:
-            # one CTA per SM (big resident weights): spread the issue work over 4 warps instead
-            mma_warps = 4 if (d.ctas_per_sm == 1 and cp.N <= 64 and cp.mma_per_tile >= 8) else 1
+            # aim for 4 MMA-issuing lanes per SM: co-resident CTAs x issuing warps per CTA.  Every warp must
+            # own at least one MMA in every ring slot, and the accumulators (warps x N) must leave room
+            # for two tiles in TMEM.
+            per_slot, cur = [], 0
+            for st in cp.entries:
+                cur += st.n_taps * (cp.widths[st.cls] // 16)
+                if st.flags & 2:
+                    per_slot.append(cur)
+                    cur = 0
+            mma_warps = 1
+            for w in (4, 2):
+                if w * d.ctas_per_sm <= 4 and min(per_slot) >= w and 2 * w * cp.N <= 512 // d.ctas_per_sm and cp.N <= 64:
+                    mma_warps = w
+                    break
         d.mma_warps = mma_warps
+        self.mma_warps = mma_warps
         self.desc = d
         self.q_rows = lin.plane_rows
         h = C.c_void_p()
@@ -386,7 +399,8 @@ class Srgemm:
         a, b, c, e, f = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _lib.check(_lib.lib().pv_srgemm_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(e), C.byref(f)),
                    "pv_srgemm_info")
-        return dict(n_ring=a.value, slot_bytes=b.value, resident=c.value, n_acc=e.value, acc_split=f.value)
+        return dict(n_ring=a.value, slot_bytes=b.value, resident=c.value, n_acc=e.value, acc_split=f.value,
+                    mma_warps=self.mma_warps)
 
     def run(self, q_rows=None):
         _lib.check(_lib.lib().pv_srgemm_run(self.h, C.c_int64(q_rows or self.q_rows), _lib.stream_ptr()),
