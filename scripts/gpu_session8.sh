@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -s -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+grep -E "passed|failed|error|Error|assert" gpurun_out/pytest_gpu.log | tail -25
+rm -f gpurun_out/probe_srgemm.jsonl
+PV_SPLITS=1 timeout 600 python scripts/gpu_probe_srgemm.py --timing > gpurun_out/probe_timing_auto.log 2>&1
+PV_MMAW=4 PV_CTAS=1 PV_SPLITS=1 timeout 600 python scripts/gpu_probe_srgemm.py --timing > gpurun_out/probe_timing_w4c1.log 2>&1
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1.log 2>&1; echo "bench rc=$?"; tail -2 gpurun_out/bench_n1.log | cut -c1-2200
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 1 --no-cpu-baseline --profile-convs 0 > gpurun_out/bench_ncu.log 2>&1
+ls -la gpurun_out
