@@ -1,0 +1,85 @@
+"""Throughput of the two non-CNN configs of BASELINE.json on one B200 (numbers for profiles/README.md):
+  C3  correlation_tracker.update: 256 concurrent tracks x F frames at 1080p
+  C5  agglomerative clustering of 100k x 128-d embeddings
+Usage: python scripts/gpu_bench_aux.py [--frames 200]   -> JSON lines in gpurun_out/aux_bench.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+
+def bench_tracker(n_frames):
+    from pyannote_video_b200.geometry import DRect
+    from pyannote_video_b200.synth import make_frames
+    from pyannote_video_b200.tracker import TrackerBank
+    from pyannote_video_b200 import _lib
+    import ctypes as C
+    dev = torch.device("cuda:0")
+    frames = make_frames(min(n_frames, 64), 1080, 1920, seed=11, device=dev, shift_per_frame=(1.0, 0.5))
+    bank = TrackerBank(capacity=256, device=dev)
+    rects = [(100.0 + 110 * (k % 16), 60.0 + 62 * (k // 16), 196.0 + 110 * (k % 16), 156.0 + 62 * (k // 16)) for k in range(256)]
+    handles = [bank.start(frames[0], DRect(*r)) for r in rects]
+    bank._flush()
+    ids = torch.tensor(handles, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+
+    def upd(i):
+        f = frames[i % frames.shape[0]]
+        _lib.check(L.pv_tracker_update(bank.h, _lib.ptr(f), 1080, 1920, _lib.ptr(ids), 256, _lib.stream_ptr()))
+
+    for i in range(1, 6):
+        upd(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_frames):
+        upd(i + 6)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    updates = 256 * n_frames
+    state_bytes = 3 * 31 * 4096 * 8 + 2 * 4096 * 4      # A read twice + written once, B read + written
+    return dict(bench="C3 tracker.update", tracks=256, frames=n_frames, ms=ms, updates_per_s=updates / ms * 1e3,
+                hbm_gbs=updates * state_bytes / ms / 1e6, bytes_per_update=state_bytes)
+
+
+def bench_cluster(n):
+    from pyannote_video_b200.clustering import cluster
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    n_cent = 2000
+    cent = torch.randn(n_cent, 128, generator=g)
+    cent = cent / cent.norm(dim=1, keepdim=True) * 0.9
+    X = (cent[:, None, :] + 0.02 * torch.randn(n_cent, n // n_cent, 128, generator=g)).reshape(-1, 128)
+    X = X[torch.randperm(X.shape[0], generator=g)].contiguous().to(dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tracks, labels, stats = cluster(X, np.arange(X.shape[0]), threshold=0.6, device=dev, return_stats=True)
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    return dict(bench="C5 clustering", n=int(X.shape[0]), seconds=el, rounds=stats["rounds"], clusters=stats["n_clusters"],
+                pdist_flop=2.0 * X.shape[0] ** 2 * 128 * 1.5)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=200)
+    ap.add_argument("--n", type=int, default=100000)
+    a = ap.parse_args()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "aux_bench.jsonl"), "a") as f:
+        for fn, arg in ((bench_tracker, a.frames), (bench_cluster, a.n)):
+            try:
+                r = fn(arg)
+            except Exception as e:  # noqa: BLE001
+                r = dict(bench=fn.__name__, error=repr(e)[:500])
+            f.write(json.dumps(r) + "\n")
+            print(json.dumps(r), flush=True)
