@@ -187,15 +187,28 @@ def main():
         bx, fi = make_boxes(B, FACES_PER_FRAME, H, W, seed=1 + s + 10 * rank)
         box_sets.append((bx.to(dev), fi.to(dev), bx.pin_memory(), fi.pin_memory()))
 
+    # landmarks + chips + embed of the seeded boxes do not depend on the detector (in `extract` the boxes
+    # come from the track file), so they run on a side stream and fill the SM slots the bandwidth-bound
+    # pyramid kernels leave free.
+    side = torch.cuda.Stream(device=dev)
+
+    def embed_branch(fr, bx, fi):
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            parts = face.shape_predictor_.predict(fr, bx, fi)
+            net = face.face_recognition_
+            face._chipper.extract(fr, parts, fi, net.chips)
+            emb = net.forward_chips(bx.shape[0])
+        return parts, emb
+
     def step_resident(s):
         fr = dev_sets[s % n_sets]
         bx, fi, _, _ = box_sets[s % n_sets]
-        det = face._detector_for(H, W)
-        det.detect(fr)
-        parts = face.shape_predictor_.predict(fr, bx, fi)
-        net = face.face_recognition_
-        face._chipper.extract(fr, parts, fi, net.chips)
-        return net.forward_chips(bx.shape[0])
+        parts, emb = embed_branch(fr, bx, fi)
+        face._detector_for(H, W).detect(fr)
+        torch.cuda.current_stream().wait_stream(side)
+        return emb
 
     # end-to-end step: pinned host frames -> device (side stream, one step ahead) -> the same path ->
     # detections / landmarks / embeddings copied back to pinned host memory and read one step later.
@@ -222,11 +235,10 @@ def main():
         fr, bx, fi, ev = staged
         torch.cuda.current_stream().wait_event(ev)
         nxt = upload(s + 1)                       # next step's input travels while this step computes
+        parts, emb = embed_branch(fr, bx, fi)
         boxes, scores, counts = det_e2e.detect(fr)
-        parts = face.shape_predictor_.predict(fr, bx, fi)
-        net = face.face_recognition_
-        face._chipper.extract(fr, parts, fi, net.chips)
-        emb = net.forward_chips(bx.shape[0])
+        torch.cuda.current_stream().wait_stream(side)
+        parts.record_stream(torch.cuda.current_stream())
         o = out_host[s % 2]
         o["boxes"].copy_(boxes, non_blocking=True)
         o["counts"].copy_(counts, non_blocking=True)

@@ -63,25 +63,34 @@ __device__ __forceinline__ uchar4 bilinear_px(const uint8_t* __restrict__ s, int
   return o;
 }
 
-// 2-D launch: blockIdx.z = image, (blockIdx.y, blockIdx.x) tiles of 8 x 32 output pixels
+// 2-D launch: blockIdx.z = image; a CTA covers 8 rows x 128 columns, each thread 4 consecutive columns
+// (independent bilinear samples in flight, 16 contiguous bytes written per thread)
 template <int SRC_CH>
-__global__ void resize_bilinear_kernel(const uint8_t* __restrict__ src, long long src_img_stride, int src_pitch_px,
-                                       int sx0, int sy0, int sw, int sh, uchar4* __restrict__ dst,
-                                       long long dst_img_stride, int dst_pitch_px, int dx0, int dy0, int dw, int dh,
-                                       float xs, float ys, int B, int copy_only) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const uint8_t* __restrict__ src, long long src_img_stride,
+                                                              int src_pitch_px, int sx0, int sy0, int sw, int sh,
+                                                              uchar4* __restrict__ dst, long long dst_img_stride,
+                                                              int dst_pitch_px, int dx0, int dy0, int dw, int dh, float xs,
+                                                              float ys, int B, int copy_only) {
+  const int c0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
   const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int n = blockIdx.z;
-  if (c >= dw || r >= dh) return;
+  if (c0 >= dw || r >= dh) return;
   const uint8_t* s = src + (long long)n * src_img_stride;
-  uchar4 o;
-  if (copy_only) {
-    const uint8_t* p = s + ((long long)(sy0 + r) * src_pitch_px + sx0 + c) * SRC_CH;
-    o = make_uchar4(p[0], p[1], p[2], 255);
-  } else {
-    o = bilinear_px<SRC_CH>(s, src_pitch_px, sx0, sy0, sw, sh, r, c, xs, ys);
+  uchar4 o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = min(c0 + k, dw - 1);
+    if (copy_only) {
+      const uint8_t* p = s + ((long long)(sy0 + r) * src_pitch_px + sx0 + c) * SRC_CH;
+      o[k] = make_uchar4(p[0], p[1], p[2], 255);
+    } else {
+      o[k] = bilinear_px<SRC_CH>(s, src_pitch_px, sx0, sy0, sw, sh, r, c, xs, ys);
+    }
   }
-  dst[(long long)n * dst_img_stride + (long long)(dy0 + r) * dst_pitch_px + dx0 + c] = o;
+  uchar4* d = dst + (long long)n * dst_img_stride + (long long)(dy0 + r) * dst_pitch_px + dx0 + c0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (c0 + k < dw) d[k] = o[k];
 }
 
 // the small tail of the pyramid (levels k0 .. L-1, each resized from its predecessor inside the plane):
@@ -97,19 +106,24 @@ struct PyrTail {
   PyrLevel lv[kMaxTail];
 };
 
-__global__ void __launch_bounds__(1024) pyramid_tail_kernel(uchar4* __restrict__ plane, long long img_stride_px,
-                                                            int pitch_px, const __grid_constant__ PyrTail t) {
-  uchar4* img = plane + (long long)blockIdx.x * img_stride_px;
+constexpr int kTailCluster = 8;   // CTAs cooperating on one image (thread-block cluster, barrier.cluster between levels)
+
+__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(1024)
+    pyramid_tail_kernel(uchar4* __restrict__ plane, long long img_stride_px, int pitch_px, const __grid_constant__ PyrTail t) {
+  uchar4* img = plane + (long long)(blockIdx.x / kTailCluster) * img_stride_px;
+  const int rank = blockIdx.x % kTailCluster;
   PyrLevel src = t.prev;
   for (int k = 0; k < t.n; ++k) {
     const PyrLevel d = t.lv[k];
     const int total = d.w * d.h;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    for (int i = rank * 1024 + threadIdx.x; i < total; i += kTailCluster * 1024) {
       const int r = i / d.w, c = i - r * d.w;
       img[(long long)(d.y0 + r) * pitch_px + d.x0 + c] =
           bilinear_px<4>(reinterpret_cast<const uint8_t*>(img), pitch_px, src.x0, src.y0, src.w, src.h, r, c, d.xs, d.ys);
     }
-    __syncthreads();   // level k complete (and visible to this CTA) before level k+1 reads it
+    // level k complete and visible to the whole cluster before level k+1 reads it
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     src = d;
   }
 }
@@ -282,7 +296,7 @@ extern "C" int pv_resize_bilinear(const void* src, int src_channels, int64_t src
   PV_REQUIRE(src_channels == 3 || src_channels == 4, "pv_resize_bilinear: src_channels=%d", src_channels);
   PV_REQUIRE(sw > 0 && sh > 0 && dw > 0 && dh > 0 && B > 0, "pv_resize_bilinear: empty rect");
   const int threads = 256;
-  const dim3 blocks((unsigned)((dw + 31) / 32), (unsigned)((dh + 7) / 8), (unsigned)B);
+  const dim3 blocks((unsigned)((dw + 127) / 128), (unsigned)((dh + 7) / 8), (unsigned)B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (src_channels == 3)
     resize_bilinear_kernel<3><<<blocks, threads, 0, s>>>(static_cast<const uint8_t*>(src), src_img_stride, src_pitch_px,
@@ -314,7 +328,7 @@ extern "C" int pv_pyramid_tail(void* plane_rgba, int64_t img_stride_px, int pitc
     t.lv[k].xs = scales_host[2 * k];
     t.lv[k].ys = scales_host[2 * k + 1];
   }
-  pyramid_tail_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uchar4*>(plane_rgba), img_stride_px,
+  pyramid_tail_kernel<<<B * kTailCluster, 1024, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uchar4*>(plane_rgba), img_stride_px,
                                                                       pitch_px, t);
   g_pv_launches.fetch_add(1);
   PV_CUDA_CHECK(cudaGetLastError());
