@@ -217,6 +217,10 @@ int pv_tracker_create(int capacity, const float* hann64_host, const float* uu9_h
                       const float* tw_re32_host, const float* tw_im32_host, float padding, float lambda, float nu,
                       void** out_handle);
 int pv_tracker_destroy(void* handle);
+/* enable the 1-D scale filter of dlib's update(): 32 scales alpha^(k-16), 23x23 windows, FHOG cell 4.
+ * Tables are HOST float[32]: Hann over scales, alpha^(k-16), DFT twiddles exp(-2 pi i m/32). */
+int pv_tracker_enable_scale(void* handle, const float* hann32_host, const float* factor32_host, const float* tw_re32_host,
+                            const float* tw_im32_host, double alpha, float lambda, float nu);
 /* frame u8 [H,W,3]; ids i32 [n] bank slots; rects f32 [n,4] (l,t,r,b) */
 int pv_tracker_start(void* handle, const void* frame, int H, int W, const int* ids, const float* rects, int n,
                      void* stream);

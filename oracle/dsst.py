@@ -9,8 +9,10 @@ Restated: translation filter over the 31-channel FHOG (cell size 1) of a 64x64 c
 position rectangle grown by 1.4, cosine window, per-channel numerators A_i = conj(G) F_i and shared
 denominator B = sum |F_i|^2, response = ifft2(sum F_i conj(A_i) / (B + 0.001)), sub-pixel peak, PSR
 over everything outside the 8x8 peak window, running update with nu = 0.025.
-NOT restated (stated gap): the 1-D scale filter of `update` (32 scales, 23x23 windows)
-— `update` here is dlib's `update_noscale`; the rectangle keeps its size.
+Also restated: the 1-D scale filter of `update` — 32 scales alpha^(k-16) (alpha = 1.020) of the
+position rectangle, each resampled to 23x23, FHOG with cell size 4 (4x4 cells x 31 = 496 features),
+Hann window over scales, per-feature numerators As_j = conj(Gs) Fs_j and denominator Bs = sum |Fs_j|^2
+over a length-32 DFT, interpolated argmax, position *= alpha^(p-16), running update with nu = 0.025.
 Chip sampling and FHOG are float32/unfused like the CUDA path; the FFTs are numpy float64.
 """
 import numpy as np
@@ -122,7 +124,138 @@ def gaussian_target(px, py, n=FS):
     return np.exp(-(((x - f32(px)) ** 2) + ((y - f32(py)) ** 2)) / f32(3.0)).astype(f32)
 
 
+# ---------------------------------------------------------------------------------------------
+# scale filter
+# ---------------------------------------------------------------------------------------------
+N_SCALES = 32
+SCALE_WINDOW = 23
+SCALE_ALPHA = 1.020
+SCALE_LAMBDA = 0.001
+SCALE_NU = 0.025
+SCALE_CELL = 4
+
+
+def extract_chip_n(rgb, rect, n):
+    """bilinear n x n RGB chip of `rect` (no padding); corners map to corners; outside -> 0"""
+    H, W, _ = rgb.shape
+    l, t, r, b = [f32(v) for v in rect]
+    sx, sy = (r - l) / f32(n - 1), (b - t) / f32(n - 1)
+    xs = (l + np.arange(n, dtype=f32) * sx).astype(f32)
+    ys = (t + np.arange(n, dtype=f32) * sy).astype(f32)
+    left = np.floor(xs).astype(np.int64)
+    top = np.floor(ys).astype(np.int64)
+    lr = (xs - left.astype(f32)).astype(f32)[None, :, None]
+    tb = (ys - top.astype(f32)).astype(f32)[:, None, None]
+    ok = ((left >= 0) & (left + 1 < W))[None, :] & ((top >= 0) & (top + 1 < H))[:, None]
+    lc, tc = np.clip(left, 0, W - 2), np.clip(top, 0, H - 2)
+    s = rgb.astype(f32)
+    tl, tr, bl, br = s[tc][:, lc], s[tc][:, lc + 1], s[tc + 1][:, lc], s[tc + 1][:, lc + 1]
+    one = f32(1)
+    a = ((one - lr) * tl) + (lr * tr)
+    bb = ((one - lr) * bl) + (lr * br)
+    v = ((one - tb) * a) + (tb * bb)
+    v = np.clip(np.floor(v + f32(0.5)), 0, 255)
+    return np.where(ok[..., None], v, 0).astype(np.uint8)
+
+
+def fhog_cell4(chip):
+    """31-channel FHOG, cell size 4, of a uint8 [n,n,3] chip -> float32 [31, cells-2, cells-2]
+    (cells = round(n/4)); votes are bilinearly shared between the 4 nearest cells, in raster order."""
+    n = chip.shape[0]
+    cells = int(round(n / float(SCALE_CELL)))
+    c = chip.astype(f32)
+    hist = np.zeros((cells, cells, 18), f32)
+    for y in range(1, n - 1):
+        for x in range(1, n - 1):
+            best = f32(-1)
+            gx = gy = f32(0)
+            for ch in range(3):
+                dx = c[y, x + 1, ch] - c[y, x - 1, ch]
+                dy = c[y + 1, x, ch] - c[y - 1, x, ch]
+                v = (dx * dx) + (dy * dy)
+                if v > best:
+                    best, gx, gy = v, dx, dy
+            mag = np.sqrt(best)
+            bo, best_dot = 0, f32(0)
+            for o in range(9):
+                dot = (_UU[o] * gx) + (_VV[o] * gy)
+                if dot > best_dot:
+                    best_dot, bo = dot, o
+                elif -dot > best_dot:
+                    best_dot, bo = -dot, o + 9
+            xp = (f32(x) + f32(0.5)) / f32(SCALE_CELL) - f32(0.5)
+            yp = (f32(y) + f32(0.5)) / f32(SCALE_CELL) - f32(0.5)
+            ixp, iyp = int(np.floor(xp)), int(np.floor(yp))
+            vx0, vy0 = xp - f32(ixp), yp - f32(iyp)
+            vx1, vy1 = f32(1) - vx0, f32(1) - vy0
+            if ixp >= 0 and iyp >= 0:
+                hist[iyp, ixp, bo] += (vx1 * vy1) * mag
+            if ixp + 1 < cells and iyp >= 0:
+                hist[iyp, ixp + 1, bo] += (vx0 * vy1) * mag
+            if ixp >= 0 and iyp + 1 < cells:
+                hist[iyp + 1, ixp, bo] += (vx1 * vy0) * mag
+            if ixp + 1 < cells and iyp + 1 < cells:
+                hist[iyp + 1, ixp + 1, bo] += (vx0 * vy0) * mag
+    nrm = np.zeros((cells, cells), f32)
+    for o in range(9):
+        s_ = hist[:, :, o] + hist[:, :, o + 9]
+        nrm = nrm + (s_ * s_)
+    oc = cells - 2
+    out = np.zeros((31, oc, oc), f32)
+    for y in range(oc):
+        for x in range(oc):
+            Y, X = y + 1, x + 1
+            h = hist[Y, X]
+            ns = []
+            for (dy_, dx_) in ((-1, -1), (-1, 0), (0, -1), (0, 0)):
+                y0, x0 = Y + dy_, X + dx_
+                blk = ((nrm[y0, x0] + nrm[y0, x0 + 1]) + nrm[y0 + 1, x0]) + nrm[y0 + 1, x0 + 1]
+                ns.append(f32(1) / np.sqrt(blk + EPS))
+            t = [f32(0)] * 4
+            for o in range(18):
+                hk = [min(h[o] * ns[k], f32(0.2)) for k in range(4)]
+                out[o, y, x] = f32(0.5) * (((hk[0] + hk[1]) + hk[2]) + hk[3])
+                for k in range(4):
+                    t[k] = t[k] + hk[k]
+            for o in range(9):
+                s_ = h[o] + h[o + 9]
+                hk = [min(s_ * ns[k], f32(0.2)) for k in range(4)]
+                out[18 + o, y, x] = f32(0.5) * (((hk[0] + hk[1]) + hk[2]) + hk[3])
+            for k in range(4):
+                out[27 + k, y, x] = f32(0.2357) * t[k]
+    return out
+
+
+def scale_rect(rect, factor):
+    l, t, r, b = [float(v) for v in rect]
+    cx, cy = 0.5 * (l + r), 0.5 * (t + b)
+    hw, hh = 0.5 * (r - l) * factor, 0.5 * (b - t) * factor
+    return (cx - hw, cy - hh, cx + hw, cy + hh)
+
+
+def scale_space(rgb, position):
+    """float64 [496, 32]: feature j at scale k, windowed over scales"""
+    w = (f32(0.5) - f32(0.5) * np.cos(2 * np.pi * np.arange(N_SCALES) / (N_SCALES - 1))).astype(f32)
+    cols = []
+    for k in range(N_SCALES):
+        factor = f32(SCALE_ALPHA) ** f32(k - N_SCALES // 2)
+        l, t, r, b = [f32(v) for v in position]
+        cx, cy = (l + r) * f32(0.5), (t + b) * f32(0.5)
+        hw, hh = ((r - l) * f32(0.5)) * factor, ((b - t) * f32(0.5)) * factor
+        chip = extract_chip_n(rgb, (cx - hw, cy - hh, cx + hw, cy + hh), SCALE_WINDOW)
+        cols.append((fhog_cell4(chip).reshape(-1) * w[k]).astype(f32))
+    return np.stack(cols, axis=1).astype(np.float64)
+
+
+def scale_target(p):
+    k = np.arange(N_SCALES, dtype=f32)
+    return np.exp(-((k - f32(p)) ** 2) / f32(1.0)).astype(f32)
+
+
 class CorrelationTracker(object):
+    def __init__(self, use_scale=True):
+        self.use_scale = use_scale
+
     def _features(self, rgb, rect):
         chip, tf = extract_chip(rgb, rect)
         F = fhog_cell1(chip) * hann2d()[None]
@@ -135,8 +268,34 @@ class CorrelationTracker(object):
         G = np.conj(np.fft.fft2(gaussian_target(c, c).astype(np.float64)))
         self.A = G[None] * F
         self.B = (np.abs(F) ** 2).sum(0)
+        if self.use_scale:
+            Fs = np.fft.fft(scale_space(rgb, self.position), axis=1)
+            Gs = np.conj(np.fft.fft(scale_target(N_SCALES // 2).astype(np.float64)))
+            self.As = Gs[None] * Fs
+            self.Bs = (np.abs(Fs) ** 2).sum(0)
+
+    def update_scale(self, rgb):
+        Fs = np.fft.fft(scale_space(rgb, self.position), axis=1)
+        r = np.real(np.fft.ifft((Fs * np.conj(self.As)).sum(0) / (self.Bs + SCALE_LAMBDA)))
+        pk = int(np.argmax(r))
+        p = float(pk)
+        if 0 < pk < N_SCALES - 1:
+            d = r[pk - 1] - 2 * r[pk] + r[pk + 1]
+            if d != 0:
+                p += 0.5 * (r[pk - 1] - r[pk + 1]) / d
+        self.position = scale_rect(self.position, SCALE_ALPHA ** (p - N_SCALES // 2))
+        Gs = np.conj(np.fft.fft(scale_target(p).astype(np.float64)))
+        self.As = (1 - SCALE_NU) * self.As + SCALE_NU * (Gs[None] * Fs)
+        self.Bs = (1 - SCALE_NU) * self.Bs + SCALE_NU * (np.abs(Fs) ** 2).sum(0)
+        return p
 
     def update(self, rgb):
+        psr = self.update_noscale(rgb)
+        if self.use_scale:
+            self.update_scale(rgb)
+        return psr
+
+    def update_noscale(self, rgb):
         guess = self.position
         F, (rl, rt, sx, sy) = self._features(rgb, guess)
         R = np.real(np.fft.ifft2((F * np.conj(self.A)).sum(0) / (self.B + LAMBDA)))

@@ -7,7 +7,7 @@
 // window -> 31 2-D FFTs (shared memory, radix-2) -> response = ifft2(sum F_i conj(A_i)/(B+lambda))
 // -> argmax / sub-pixel / PSR (warp-shuffle + shared reductions) -> position -> filter update
 // (features are recomputed rather than spilled: 1 MB of state is read twice and written once).
-// Mirrors oracle/dsst.py step by step; scale filter not implemented (stated gap).
+// A second kernel runs the 1-D scale filter (32 scales, FHOG cell 4).  Mirrors oracle/dsst.py step by step.
 #include <atomic>
 #include "../../include/pv_b200.h"
 #include "pv_common.cuh"
@@ -383,8 +383,303 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
   for (int i = tid; i < NPIX; i += kThreads) B[i] = om * B[i] + nu * s.bsum[i];
 }
 
+
+// =============================================================================================
+// scale filter (second half of dlib correlation_tracker::update): 32 scales alpha^(k-16) of the
+// position rectangle -> 23x23 chips -> FHOG cell 4 (4x4x31 = 496 features) x Hann over scales ->
+// length-32 FFT per feature -> response over scales -> interpolated argmax -> position *= factor
+// -> running update of As[496][32], Bs[32].  One CTA per track; mirrors oracle/dsst.py.
+// =============================================================================================
+constexpr int NS = 32;
+constexpr int SW = 23;
+constexpr int SCELLS = 6;
+constexpr int SOUT = 4;
+constexpr int SF = 31 * SOUT * SOUT;   // 496
+constexpr int ZP = NS + 1;             // padded row length (bank conflicts)
+
+struct ScaleTables {
+  float hann[NS];
+  float factor[NS];          // alpha^(k-16) in float32, computed on the host like the oracle
+  float tw_re[NS], tw_im[NS];  // exp(-2 pi i m / 32)
+  float uu[9], vv[9];
+  float lambda, nu;
+  double alpha;
+};
+
+struct ScaleParams {
+  float2* As;      // [cap][496][32]
+  float* Bs;       // [cap][32]
+  float* pos;      // [cap][4]
+  const int* ids;
+  const uint8_t* frame;
+  int H, W;
+};
+
+__device__ __forceinline__ int rev5(int v) { return (int)(__brev((unsigned)v) >> 27); }
+
+template <bool START>
+__global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, const __grid_constant__ ScaleTables tb) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float2* Z = reinterpret_cast<float2*>(smem_raw);                 // [SF][ZP]
+  float* s_mag = reinterpret_cast<float*>(Z + SF * ZP);             // [SW*SW]
+  float* s_hist = s_mag + SW * SW;                                  // [36*18]
+  float* s_nrm = s_hist + SCELLS * SCELLS * 18;                     // [36]
+  float* s_red = s_nrm + SCELLS * SCELLS;                           // [8*64 + 64]
+  uint8_t* s_chip = reinterpret_cast<uint8_t*>(s_red + 8 * 64 + 64);  // [SW*SW*3]
+  uint8_t* s_ori = s_chip + SW * SW * 3 + 3;                        // [SW*SW]
+  __shared__ double s_gre[NS], s_gim[NS];   // conj(FFT(target))
+  __shared__ double s_rre[NS], s_rim[NS];
+  __shared__ float s_resp[NS];
+  __shared__ float s_peak;
+  const int tid = threadIdx.x;
+  const int slot = p.ids[blockIdx.x];
+  float2* As = p.As + (size_t)slot * SF * NS;
+  float* Bs = p.Bs + (size_t)slot * NS;
+  const float l = p.pos[slot * 4 + 0], t = p.pos[slot * 4 + 1], r = p.pos[slot * 4 + 2], b = p.pos[slot * 4 + 3];
+  const float cx = __fmul_rn(__fadd_rn(l, r), 0.5f), cy = __fmul_rn(__fadd_rn(t, b), 0.5f);
+  const float hw0 = __fmul_rn(__fsub_rn(r, l), 0.5f), hh0 = __fmul_rn(__fsub_rn(b, t), 0.5f);
+
+  for (int k = 0; k < NS; ++k) {
+    // ---- chip of scale k ----
+    const float hw = __fmul_rn(hw0, tb.factor[k]), hh = __fmul_rn(hh0, tb.factor[k]);
+    const float lk = __fsub_rn(cx, hw), rk = __fadd_rn(cx, hw), tk = __fsub_rn(cy, hh), bk = __fadd_rn(cy, hh);
+    const float sx = __fdiv_rn(__fsub_rn(rk, lk), (float)(SW - 1)), sy = __fdiv_rn(__fsub_rn(bk, tk), (float)(SW - 1));
+    for (int i = tid; i < SW * SW; i += kThreads) {
+      const int y = i / SW, x = i - y * SW;
+      const float fx = __fadd_rn(lk, __fmul_rn((float)x, sx)), fy = __fadd_rn(tk, __fmul_rn((float)y, sy));
+      const int left = (int)floorf(fx), top = (int)floorf(fy);
+      uint8_t o[3] = {0, 0, 0};
+      if (left >= 0 && left + 1 < p.W && top >= 0 && top + 1 < p.H) {
+        const float lr = __fsub_rn(fx, (float)left), tbv = __fsub_rn(fy, (float)top);
+        const float omlr = __fsub_rn(1.0f, lr), omtb = __fsub_rn(1.0f, tbv);
+        const uint8_t* ptl = p.frame + ((long long)top * p.W + left) * 3;
+        const uint8_t* pbl = ptl + (long long)p.W * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float a = __fadd_rn(__fmul_rn(omlr, (float)ptl[c]), __fmul_rn(lr, (float)ptl[3 + c]));
+          const float bb = __fadd_rn(__fmul_rn(omlr, (float)pbl[c]), __fmul_rn(lr, (float)pbl[3 + c]));
+          float v = __fadd_rn(__fmul_rn(omtb, a), __fmul_rn(tbv, bb));
+          o[c] = (uint8_t)fminf(fmaxf(floorf(__fadd_rn(v, 0.5f)), 0.f), 255.f);
+        }
+      }
+      s_chip[3 * i] = o[0]; s_chip[3 * i + 1] = o[1]; s_chip[3 * i + 2] = o[2];
+    }
+    __syncthreads();
+    // ---- gradient magnitude / snapped orientation ----
+    for (int i = tid; i < SW * SW; i += kThreads) {
+      const int y = i / SW, x = i - y * SW;
+      float m = 0.f;
+      int bo = 0;
+      if (y > 0 && y < SW - 1 && x > 0 && x < SW - 1) {
+        float gx = 0.f, gy = 0.f, best = -1.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float dx = __fsub_rn((float)s_chip[3 * (i + 1) + c], (float)s_chip[3 * (i - 1) + c]);
+          const float dy = __fsub_rn((float)s_chip[3 * (i + SW) + c], (float)s_chip[3 * (i - SW) + c]);
+          const float v = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+          if (v > best) { best = v; gx = dx; gy = dy; }
+        }
+        m = sqrtf(best);
+        float best_dot = 0.f;
+#pragma unroll
+        for (int o = 0; o < 9; ++o) {
+          const float dot = __fadd_rn(__fmul_rn(tb.uu[o], gx), __fmul_rn(tb.vv[o], gy));
+          if (dot > best_dot) { best_dot = dot; bo = o; }
+          else if (-dot > best_dot) { best_dot = -dot; bo = o + 9; }
+        }
+      }
+      s_mag[i] = m;
+      s_ori[i] = (uint8_t)bo;
+    }
+    __syncthreads();
+    // ---- cell histograms: every (cell, orientation) bin gathers its pixels in raster order ----
+    for (int bi = tid; bi < SCELLS * SCELLS * 18; bi += kThreads) {
+      const int o = bi % 18, cell = bi / 18;
+      const int cyi = cell / SCELLS, cxi = cell - cyi * SCELLS;
+      float acc = 0.f;
+      const int y0 = max(1, 4 * cyi - 2), y1 = min(SW - 2, 4 * cyi + 5);
+      const int x0 = max(1, 4 * cxi - 2), x1 = min(SW - 2, 4 * cxi + 5);
+      for (int y = y0; y <= y1; ++y) {
+        const float yp = __fsub_rn(__fdiv_rn(__fadd_rn((float)y, 0.5f), 4.0f), 0.5f);
+        const int iyp = (int)floorf(yp);
+        const float vy0 = __fsub_rn(yp, (float)iyp), vy1 = __fsub_rn(1.0f, vy0);
+        float wy;
+        if (iyp == cyi) wy = vy1; else if (iyp + 1 == cyi) wy = vy0; else continue;
+        for (int x = x0; x <= x1; ++x) {
+          if (s_ori[y * SW + x] != o) continue;
+          const float xp = __fsub_rn(__fdiv_rn(__fadd_rn((float)x, 0.5f), 4.0f), 0.5f);
+          const int ixp = (int)floorf(xp);
+          const float vx0 = __fsub_rn(xp, (float)ixp), vx1 = __fsub_rn(1.0f, vx0);
+          float wx;
+          if (ixp == cxi) wx = vx1; else if (ixp + 1 == cxi) wx = vx0; else continue;
+          acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wx, wy), s_mag[y * SW + x]));
+        }
+      }
+      s_hist[bi] = acc;   // layout [cell][o]
+    }
+    __syncthreads();
+    if (tid < SCELLS * SCELLS) {
+      float n = 0.f;
+      for (int o = 0; o < 9; ++o) {
+        const float sv = __fadd_rn(s_hist[tid * 18 + o], s_hist[tid * 18 + o + 9]);
+        n = __fadd_rn(n, __fmul_rn(sv, sv));
+      }
+      s_nrm[tid] = n;
+    }
+    __syncthreads();
+    // ---- 496 features of this scale ----
+    for (int j = tid; j < SF; j += kThreads) {
+      const int plane = j / (SOUT * SOUT), rem = j - plane * SOUT * SOUT;
+      const int y = rem / SOUT, x = rem - y * SOUT;
+      const int Y = y + 1, X = x + 1;
+      float ns[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int yy = Y - 1 + (q >> 1), xx = X - 1 + (q & 1);
+        const float blk = __fadd_rn(__fadd_rn(__fadd_rn(s_nrm[yy * SCELLS + xx], s_nrm[yy * SCELLS + xx + 1]),
+                                              s_nrm[(yy + 1) * SCELLS + xx]), s_nrm[(yy + 1) * SCELLS + xx + 1]);
+        ns[q] = __fdiv_rn(1.0f, sqrtf(__fadd_rn(blk, 0.0001f)));
+      }
+      const float* h = s_hist + (Y * SCELLS + X) * 18;
+      float v;
+      if (plane < 27) {
+        const float hv = plane < 18 ? h[plane] : __fadd_rn(h[plane - 18], h[plane - 18 + 9]);
+        const float h0 = fminf(__fmul_rn(hv, ns[0]), 0.2f), h1 = fminf(__fmul_rn(hv, ns[1]), 0.2f);
+        const float h2 = fminf(__fmul_rn(hv, ns[2]), 0.2f), h3 = fminf(__fmul_rn(hv, ns[3]), 0.2f);
+        v = __fmul_rn(0.5f, __fadd_rn(__fadd_rn(__fadd_rn(h0, h1), h2), h3));
+      } else {
+        const int q = plane - 27;
+        float tsum = 0.f;
+        for (int o = 0; o < 18; ++o) tsum = __fadd_rn(tsum, fminf(__fmul_rn(h[o], ns[q]), 0.2f));
+        v = __fmul_rn(0.2357f, tsum);
+      }
+      Z[j * ZP + rev5(k)] = make_float2(__fmul_rn(v, tb.hann[k]), 0.f);
+    }
+    __syncthreads();
+  }
+
+  // ---- length-32 FFT over scales for every feature row (input stored bit-reversed) ----
+  for (int j = tid; j < SF; j += kThreads) {
+    float2* z = Z + j * ZP;
+    for (int s = 1; s <= 5; ++s) {
+      const int half = 1 << (s - 1);
+      for (int bfly = 0; bfly < 16; ++bfly) {
+        const int grp = bfly / half, q = bfly - grp * half;
+        const int i0 = grp * (half << 1) + q, i1 = i0 + half;
+        const int m = q * (16 / half);
+        const float2 w = make_float2(tb.tw_re[m], tb.tw_im[m]);
+        const float2 u = z[i0], tv = cmul(w, z[i1]);
+        z[i0] = make_float2(u.x + tv.x, u.y + tv.y);
+        z[i1] = make_float2(u.x - tv.x, u.y - tv.y);
+      }
+    }
+  }
+  __syncthreads();
+
+  const int k = tid & 31, grp = tid >> 5;   // 8 row groups
+  float peak = 0.5f * NS;
+  if (!START) {
+    // response R^[k] = sum_j Z[j][k] conj(As[j][k]) / (Bs[k] + lambda)
+    float re = 0.f, im = 0.f;
+    for (int j = grp; j < SF; j += 8) {
+      const float2 f = Z[j * ZP + k];
+      const float2 a = As[(size_t)j * NS + k];
+      re += f.x * a.x + f.y * a.y;
+      im += f.y * a.x - f.x * a.y;
+    }
+    s_red[grp * 64 + k] = re;
+    s_red[grp * 64 + 32 + k] = im;
+    __syncthreads();
+    if (tid < NS) {
+      double sr = 0, si = 0;
+      for (int g = 0; g < 8; ++g) { sr += s_red[g * 64 + tid]; si += s_red[g * 64 + 32 + tid]; }
+      const double d = 1.0 / ((double)Bs[tid] + (double)tb.lambda);
+      s_rre[tid] = sr * d;
+      s_rim[tid] = si * d;
+    }
+    __syncthreads();
+    if (tid < NS) {   // inverse DFT, real part
+      double acc = 0;
+      for (int q = 0; q < NS; ++q) {
+        const int m = (q * tid) & 31;
+        acc += s_rre[q] * (double)tb.tw_re[m] + s_rim[q] * (double)tb.tw_im[m];   // Re(R * conj(w)) = Re(R e^{+i...})
+      }
+      s_resp[tid] = (float)(acc / NS);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int pk = 0;
+      float best = s_resp[0];
+      for (int q = 1; q < NS; ++q) if (s_resp[q] > best) { best = s_resp[q]; pk = q; }
+      double pp = pk;
+      if (pk > 0 && pk < NS - 1) {
+        const double c = s_resp[pk], a = s_resp[pk - 1], d2 = s_resp[pk + 1];
+        const double den = a - 2 * c + d2;
+        if (den != 0) pp += 0.5 * (a - d2) / den;
+      }
+      const double f = pow(tb.alpha, pp - NS / 2);
+      const double dl = l, dt = t, dr = r, db = b;
+      const double ccx = 0.5 * (dl + dr), ccy = 0.5 * (dt + db);
+      const double nhw = 0.5 * (dr - dl) * f, nhh = 0.5 * (db - dt) * f;
+      p.pos[slot * 4 + 0] = (float)(ccx - nhw);
+      p.pos[slot * 4 + 1] = (float)(ccy - nhh);
+      p.pos[slot * 4 + 2] = (float)(ccx + nhw);
+      p.pos[slot * 4 + 3] = (float)(ccy + nhh);
+      s_peak = (float)pp;
+    }
+    __syncthreads();
+    peak = s_peak;
+  }
+  // conj(DFT(target)) at `peak`
+  if (tid < NS) {
+    double re = 0, im = 0;
+    for (int q = 0; q < NS; ++q) {
+      const float dq = (float)q - peak;
+      const double g = (double)expf(-(dq * dq) / 1.0f);
+      const int m = (q * tid) & 31;
+      re += g * (double)tb.tw_re[m];
+      im += g * (double)tb.tw_im[m];
+    }
+    s_gre[tid] = re;
+    s_gim[tid] = -im;
+  }
+  __syncthreads();
+  // filter update / initialisation
+  {
+    const float gre = (float)s_gre[k], gim = (float)s_gim[k];
+    float bsum = 0.f;
+    for (int j = grp; j < SF; j += 8) {
+      const float2 f = Z[j * ZP + k];
+      const float2 gf = make_float2(gre * f.x - gim * f.y, gre * f.y + gim * f.x);
+      bsum += f.x * f.x + f.y * f.y;
+      if (START) {
+        As[(size_t)j * NS + k] = gf;
+      } else {
+        float2 a = As[(size_t)j * NS + k];
+        a.x = (1.0f - tb.nu) * a.x + tb.nu * gf.x;
+        a.y = (1.0f - tb.nu) * a.y + tb.nu * gf.y;
+        As[(size_t)j * NS + k] = a;
+      }
+    }
+    __syncthreads();
+    s_red[grp * 64 + k] = bsum;
+    __syncthreads();
+    if (tid < NS) {
+      float sb = 0.f;
+      for (int g = 0; g < 8; ++g) sb += s_red[g * 64 + tid];
+      Bs[tid] = START ? sb : (1.0f - tb.nu) * Bs[tid] + tb.nu * sb;
+    }
+  }
+}
+constexpr size_t kScaleSmem = (size_t)SF * ZP * 8 + (SW * SW) * 4 + (SCELLS * SCELLS * 18) * 4 + SCELLS * SCELLS * 4 +
+                              (8 * 64 + 64) * 4 + SW * SW * 3 + 3 + SW * SW + 64;
+
 struct Bank {
   int capacity;
+  float2* As = nullptr;
+  float* Bs = nullptr;
+  ScaleTables stb;
+  bool has_scale = false;
   float2* A;
   float* B;
   float* pos;
@@ -432,6 +727,8 @@ extern "C" int pv_tracker_destroy(void* handle) {
   cudaFree(b->B);
   cudaFree(b->pos);
   cudaFree(b->psr);
+  cudaFree(b->As);
+  cudaFree(b->Bs);
   delete b;
   return PV_OK;
 }
@@ -462,17 +759,70 @@ static int launch(Bank* b, bool start, const void* frame, int H, int W, const in
   return PV_OK;
 }
 
+/* enable the scale filter: tables are HOST float arrays of 32 entries (Hann over scales, alpha^(k-16), DFT twiddles) */
+extern "C" int pv_tracker_enable_scale(void* handle, const float* hann32_host, const float* factor32_host,
+                                       const float* tw_re32_host, const float* tw_im32_host, double alpha, float lambda,
+                                       float nu) {
+  PV_REQUIRE(handle && hann32_host && factor32_host && tw_re32_host && tw_im32_host, "pv_tracker_enable_scale: null argument");
+  Bank* b = static_cast<Bank*>(handle);
+  memcpy(b->stb.hann, hann32_host, sizeof(float) * NS);
+  memcpy(b->stb.factor, factor32_host, sizeof(float) * NS);
+  memcpy(b->stb.tw_re, tw_re32_host, sizeof(float) * NS);
+  memcpy(b->stb.tw_im, tw_im32_host, sizeof(float) * NS);
+  memcpy(b->stb.uu, b->tb.uu, sizeof(float) * 9);
+  memcpy(b->stb.vv, b->tb.vv, sizeof(float) * 9);
+  b->stb.alpha = alpha;
+  b->stb.lambda = lambda;
+  b->stb.nu = nu;
+  if (!b->As) {
+    cudaError_t e = cudaMalloc(&b->As, sizeof(float2) * (size_t)b->capacity * SF * NS);
+    if (e == cudaSuccess) e = cudaMalloc(&b->Bs, sizeof(float) * (size_t)b->capacity * NS);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tracker_scale_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScaleSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tracker_scale_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScaleSmem);
+    if (e != cudaSuccess) {
+      pv_set_error("pv_tracker_enable_scale: %s", cudaGetErrorString(e));
+      return PV_ERR_CUDA;
+    }
+  }
+  b->has_scale = true;
+  return PV_OK;
+}
+
+static int launch_scale(Bank* b, bool start, const void* frame, int H, int W, const int* ids, int n, void* stream) {
+  if (n == 0 || !b->has_scale) return PV_OK;
+  ScaleParams p;
+  p.As = b->As;
+  p.Bs = b->Bs;
+  p.pos = b->pos;
+  p.ids = ids;
+  p.frame = static_cast<const uint8_t*>(frame);
+  p.H = H;
+  p.W = W;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (start)
+    tracker_scale_kernel<true><<<n, kThreads, kScaleSmem, s>>>(p, b->stb);
+  else
+    tracker_scale_kernel<false><<<n, kThreads, kScaleSmem, s>>>(p, b->stb);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
 /* start trackers in slots ids[0..n) on `frame` (uint8 [H,W,3]) at rects [n,4] (l,t,r,b floats) */
 extern "C" int pv_tracker_start(void* handle, const void* frame, int H, int W, const int* ids, const float* rects, int n,
                                 void* stream) {
   PV_REQUIRE(handle && frame && ids && rects, "pv_tracker_start: null argument");
-  return launch(static_cast<Bank*>(handle), true, frame, H, W, ids, rects, n, stream);
+  int rc = launch(static_cast<Bank*>(handle), true, frame, H, W, ids, rects, n, stream);
+  if (rc != PV_OK) return rc;
+  return launch_scale(static_cast<Bank*>(handle), true, frame, H, W, ids, n, stream);
 }
 
 /* advance the trackers in slots ids[0..n) to `frame`; PSR and positions are left in the bank */
 extern "C" int pv_tracker_update(void* handle, const void* frame, int H, int W, const int* ids, int n, void* stream) {
   PV_REQUIRE(handle && frame && ids, "pv_tracker_update: null argument");
-  return launch(static_cast<Bank*>(handle), false, frame, H, W, ids, nullptr, n, stream);
+  int rc = launch(static_cast<Bank*>(handle), false, frame, H, W, ids, nullptr, n, stream);
+  if (rc != PV_OK) return rc;
+  return launch_scale(static_cast<Bank*>(handle), false, frame, H, W, ids, n, stream);
 }
 
 /* device pointers to the bank's state: positions float [capacity,4], psr float [capacity] */

@@ -19,6 +19,19 @@ FILTER_SIZE = 64
 PADDING = 1.4
 REGULARIZER_SPACE = 0.001
 NU_SPACE = 0.025
+N_SCALES = 32
+SCALE_ALPHA = 1.020
+REGULARIZER_SCALE = 0.001
+NU_SCALE = 0.025
+
+
+def _scale_tables():
+    f32 = np.float32
+    n = N_SCALES
+    hann = (f32(0.5) - f32(0.5) * np.cos(2 * np.pi * np.arange(n) / (n - 1))).astype(f32)
+    factor = np.asarray([f32(SCALE_ALPHA) ** f32(k - n // 2) for k in range(n)], f32)
+    m = np.arange(n)
+    return hann, factor, np.cos(-2 * np.pi * m / n).astype(f32), np.sin(-2 * np.pi * m / n).astype(f32)
 
 
 def _tables():
@@ -38,7 +51,7 @@ def _fp(a):
 
 
 class TrackerBank(object):
-    def __init__(self, capacity=256, device=None):
+    def __init__(self, capacity=256, device=None, use_scale=True):
         if not torch.cuda.is_available():
             raise RuntimeError("TrackerBank needs a CUDA device; there is no CPU fallback")
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -51,6 +64,13 @@ class TrackerBank(object):
                                                     C.c_float(PADDING), C.c_float(REGULARIZER_SPACE), C.c_float(NU_SPACE),
                                                     C.byref(h)), "pv_tracker_create")
         self.h = h
+        self.use_scale = bool(use_scale)
+        if self.use_scale:
+            sh, sf, sr, si = self._scale_tabs = _scale_tables()
+            with torch.cuda.device(self.dev):
+                _lib.check(_lib.lib().pv_tracker_enable_scale(self.h, _fp(sh), _fp(sf), _fp(sr), _fp(si),
+                                                              C.c_double(SCALE_ALPHA), C.c_float(REGULARIZER_SCALE),
+                                                              C.c_float(NU_SCALE)), "pv_tracker_enable_scale")
         pos, psr = C.POINTER(C.c_float)(), C.POINTER(C.c_float)()
         _lib.check(_lib.lib().pv_tracker_state(self.h, C.byref(pos), C.byref(psr)), "pv_tracker_state")
         self._pos_ptr, self._psr_ptr = pos, psr

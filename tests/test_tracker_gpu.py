@@ -43,6 +43,33 @@ def test_tracker_bank_matches_oracle(cuda):
     assert min(conf[:2]) > 10
 
 
+def test_scale_filter_recovers_known_zoom(cuda):
+    """known answer: the next frame is the first one magnified by 6 % about the box centre; the scale
+    filter must grow the box by ~6 % (oracle and CUDA agree on the factor)."""
+    import cv2
+    from oracle.dsst import CorrelationTracker as OracleTracker
+    from pyannote_video_b200.tracker import TrackerBank
+    f0 = make_frames(1, 360, 640, seed=3)[0].numpy()
+    z = 1.06
+    big = cv2.resize(f0, None, fx=z, fy=z, interpolation=cv2.INTER_LINEAR)
+    rect = (200.0, 100.0, 296.0, 196.0)
+    cx, cy = 248.0 * z, 148.0 * z
+    # crop the magnified frame so that the object centre stays where it was
+    ox, oy = int(round(cx - 248.0)), int(round(cy - 148.0))
+    f1 = np.ascontiguousarray(big[oy:oy + 360, ox:ox + 640])
+    bank = TrackerBank(capacity=2, device=cuda)
+    h = bank.start(bank.prepare_frame(torch.from_numpy(f0)), DRect(*rect))
+    bank.update(bank.prepare_frame(torch.from_numpy(f1)), [h])
+    got = bank.position(h)
+    ref = OracleTracker()
+    ref.start_track(f0, rect)
+    ref.update(f1)
+    rp = ref.get_position()
+    w_got, w_ref = got.right() - got.left(), rp[2] - rp[0]
+    assert abs(w_ref / 96.0 - z) < 0.02, w_ref
+    assert abs(w_got - w_ref) < 0.1, (w_got, w_ref)
+
+
 def test_tracking_by_detection_on_gpu_bank(cuda):
     """the control loop drives the CUDA bank exactly like a per-object tracker: same tracks as with the
     oracle tracker plugged in per object."""
