@@ -192,8 +192,15 @@ def main():
     # pyramid kernels leave free.
     side = torch.cuda.Stream(device=dev)
 
+    overlap = [True]
+
     def embed_branch(fr, bx, fi):
         main = torch.cuda.current_stream()
+        if not overlap[0]:      # instrumented (roofline) steps: everything on one stream, no co-running kernels
+            parts = face.shape_predictor_.predict(fr, bx, fi)
+            net = face.face_recognition_
+            face._chipper.extract(fr, parts, fi, net.chips)
+            return parts, net.forward_chips(bx.shape[0])
         side.wait_stream(main)
         with torch.cuda.stream(side):
             parts = face.shape_predictor_.predict(fr, bx, fi)
@@ -350,9 +357,11 @@ def main():
         saved = [(o, n, getattr(o, n)) for o, n, _ in patched]
         for o, n, label in patched:
             setattr(o, n, timed_stage(label, getattr(o, n)))
+        overlap[0] = False
         for s in range(args.profile_convs):
             step_resident(s)
         torch.cuda.synchronize(dev)
+        overlap[0] = True
         for o, n, f in saved:
             setattr(o, n, f)
         for op in conv_ops:
