@@ -142,6 +142,12 @@ int pv_pack_gathered(const void* rgba, void* out, int B, int H, int W, int kw, i
  * of the layout (pixel pairs), W even. */
 int pv_plane_to_pixrows(const void* rgba, void* out, int B, int H, int W, int64_t layout_plane_rows,
                         const float* mean_host, void* stream);
+/* first detector conv (5x5 stride 2, RGB -> 16) fused with input normalisation: reads the RGBA u8 plane
+ * [B,Hp,Wp,4] in place and builds the swizzled bf16 A tiles in shared memory (csrc/conv1_fused.cu).
+ * w_bf16 [5][16][16] (k = kw*3+c), scale/shift f32 [16], out rows via `dst`, err_flag: device int. */
+int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, const void* w_bf16, const float* scale,
+                   const float* shift, int relu, void* out, const PvRowMap* dst, int oh, int ow, const float* mean_host,
+                   int* err_flag, void* stream);
 /* dlib max_pool<3,3,2,2> (pad 0) on bf16 NHWC [B,H,W,C] -> rows of `dst` */
 int pv_maxpool3x3s2(const void* in, void* out, int B, int H, int W, int C, const PvRowMap* dst, void* stream);
 /* dlib avg_pool<2,2,2,2> skip path of ares_down: parity-layout input -> skip (zero-extended to Cout)

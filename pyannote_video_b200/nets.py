@@ -144,6 +144,38 @@ class EmbedNet:
                 a[0].check()
 
 
+class FusedConv1:
+    """First detector conv (5x5, stride 2, 3 -> 16) reading the RGBA u8 plane in place
+    (csrc/conv1_fused.cu); same `run(q_rows)` / `check()` protocol as Srgemm."""
+
+    def __init__(self, plane, Hp, Wp, conv, out, lout, device):
+        w = _t(conv["w"]).float()                                  # [16, 3, 5, 5]
+        assert tuple(w.shape) == (16, 3, 5, 5)
+        wk = torch.zeros(5, 16, 16)
+        wk[:, :, :15] = w.permute(2, 0, 3, 1).reshape(5, 16, 15)   # [kh][n][kw*3 + c]
+        self.w = wk.to(torch.bfloat16).contiguous().to(device)
+        sc, sh = _affine(conv)
+        self.scale, self.shift = sc.float().contiguous().to(device), sh.float().contiguous().to(device)
+        self.plane, self.Hp, self.Wp, self.out, self.lout = plane, Hp, Wp, out, lout
+        self.rm = lout.rowmap()
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.OH, self.OW = (Hp - 5) // 2 + 1, (Wp - 5) // 2 + 1
+        self.img = ((Hp + 1) // 2) * ((Wp + 1) // 2)
+
+    def run(self, q_rows=None):
+        M = (q_rows // self.img) if q_rows else self.plane.shape[0]
+        _lib.check(_lib.lib().pv_conv1_fused(_lib.ptr(self.plane), M, self.Hp, self.Wp, _lib.ptr(self.w), _lib.ptr(self.scale),
+                                             _lib.ptr(self.shift), 1, _lib.ptr(self.out), C.byref(self.rm), self.OH, self.OW,
+                                             _mean3(), _lib.ptr(self.err), _lib.stream_ptr()), "pv_conv1_fused")
+
+    def check(self):
+        torch.cuda.synchronize()
+        code = int(self.err.item())
+        if code:
+            self.err.zero_()
+            raise _lib.PvError("conv1_fused: device-side pipeline timeout (role code %d)" % code)
+
+
 class DetectorNet:
     """Batched CNN detector for frames of one size."""
 
@@ -162,8 +194,9 @@ class DetectorNet:
         Hp, Wp = geo.plane_h, geo.plane_w
         self.plane = torch.zeros(B, Hp, Wp, 4, dtype=torch.uint8, device=device)
         self.conv1_mode = config.DET_CONV1 if conv1_mode is None else conv1_mode
-        lg = RowLayout(self.conv1_mode, B, Hp, Wp, 3, kw=5)
-        self.lg, self.xg = lg, lg.alloc(device)
+        lg = RowLayout("gathered" if self.conv1_mode == "fused" else self.conv1_mode, B, Hp, Wp, 3, kw=5)
+        self.lg = lg
+        self.xg = lg.alloc(device) if self.conv1_mode != "fused" else None
         self.convs = []
         self.flops_per_frame = 0
         convs = model["convs"]
@@ -193,6 +226,16 @@ class DetectorNet:
                 self.scores = torch.zeros(B, OHs, OWs, dtype=torch.float32, device=device)
                 self.score_bias = float(sh[0])
                 op = Srgemm(cp, cur, self.partial, self.lpart, torch.ones(k), torch.zeros(k), relu=False, out_rows_f32=True)
+            elif i == 0 and self.conv1_mode == "fused":
+                OH1, OW1 = (Hp - k) // s + 1, (Wp - k) // s + 1
+                lo = RowLayout("parity", B, OH1, OW1, 16, pad=0)
+                o = lo.alloc(device)
+                op = FusedConv1(self.plane, Hp, Wp, c, o, lo, device)
+
+                class _CP(object):
+                    pass
+                cp = _CP()
+                cp.OH, cp.OW, cp.lin = OH1, OW1, lg
             else:
                 cp = ConvPlan(lcur, _t(c["w"]), s, pad, group=group)
                 _, _, nk, ns = W.DET_CONVS[i + 1]
@@ -265,7 +308,9 @@ class DetectorNet:
         L = _lib.lib()
         st = _lib.stream_ptr()
         geo = self.geo
-        if self.conv1_mode == "pixrows":
+        if self.conv1_mode == "fused":
+            pass   # conv1 reads the plane in place
+        elif self.conv1_mode == "pixrows":
             # NB: the pixel buffer is [2, Bcap, Hq, W]; a partial batch writes the first M images of
             # each parity plane, which is where rows n < M of the layout live.
             _lib.check(L.pv_plane_to_pixrows(_lib.ptr(self.plane), _lib.ptr(self.xg), M, geo.plane_h, geo.plane_w,

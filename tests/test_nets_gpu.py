@@ -50,7 +50,7 @@ def test_embed_net_matches_oracle(cuda):
     assert torch.equal(out2, out[:2])
 
 
-@pytest.mark.parametrize("upsample,conv1_mode", [(0, "gathered"), (1, "gathered"), (1, "pixrows"), (0, "pixrows")])
+@pytest.mark.parametrize("upsample,conv1_mode", [(0, "gathered"), (1, "gathered"), (1, "pixrows"), (0, "pixrows"), (1, "fused"), (0, "fused")])
 def test_detector_matches_oracle(cuda, upsample, conv1_mode):
     from oracle import nets as onets
     from oracle import pyramid as opyr
