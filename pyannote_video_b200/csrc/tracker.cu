@@ -19,7 +19,7 @@ namespace {
 constexpr int FS = 64;
 constexpr int NPIX = FS * FS;
 constexpr int NCH = 31;
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 
 struct TrackerTables {
   float hann[FS];
@@ -55,7 +55,10 @@ __device__ void fft2_64(float2* x, const TrackerTables& tb, bool inverse) {
     for (int s = 1; s <= 6; ++s) {
       const int half = 1 << (s - 1);
       for (int b = tid; b < FS * 32; b += kThreads) {
-        const int line = b >> 5, jj = b & 31;
+        // rows: a warp walks the butterflies of one line; columns: a warp walks 32 adjacent lines of one
+        // butterfly, so that its shared-memory accesses are consecutive float2 (no bank conflicts)
+        const int line = dim == 0 ? (b >> 5) : (b & 63);
+        const int jj = dim == 0 ? (b & 31) : (b >> 6);
         const int grp = jj / half, j = jj - grp * half;
         const int i0 = grp * (half << 1) + j, i1 = i0 + half;
         const int k = j * (32 / half);
@@ -183,25 +186,41 @@ __device__ void features_osum(Smem& s) {
   __syncthreads();
 }
 
-// windowed feature plane `ch`, stored bit-reversed for the FFT
-__device__ void build_plane(const Smem& s, const TrackerTables& tb, int ch) {
+__device__ __forceinline__ float feature_value(const Smem& s, const TrackerTables& tb, int ch, int i, int y, int x) {
+  const int o = s.ori[i];
+  float v;
+  if (ch < 18) v = (o == ch) ? s.osum[i] : 0.f;
+  else if (ch < 27) v = ((o % 9) == ch - 18) ? s.osum[i] : 0.f;
+  else {
+    const int k = ch - 27;
+    const float nk = inv_block(s, y - 1 + (k >> 1), x - 1 + (k & 1));
+    v = __fmul_rn(0.2357f, fminf(__fmul_rn(s.mag[i], nk), 0.2f));
+  }
+  return __fmul_rn(v, __fmul_rn(tb.hann[y], tb.hann[x]));
+}
+
+// two windowed REAL feature planes packed into one complex plane (cha -> re, chb -> im; chb < 0: zero),
+// stored bit-reversed for the FFT.  One complex FFT then yields both spectra:
+//   Fa[k] = (Z[k] + conj(Z[-k])) / 2,   Fb[k] = (Z[k] - conj(Z[-k])) / (2i)
+__device__ void build_plane2(const Smem& s, const TrackerTables& tb, int cha, int chb) {
   for (int i = threadIdx.x; i < NPIX; i += kThreads) {
     const int y = i >> 6, x = i & 63;
-    float v = 0.f;
+    float va = 0.f, vb = 0.f;
     if (y > 0 && y < FS - 1 && x > 0 && x < FS - 1) {
-      const int o = s.ori[i];
-      if (ch < 18) v = (o == ch) ? s.osum[i] : 0.f;
-      else if (ch < 27) v = ((o % 9) == ch - 18) ? s.osum[i] : 0.f;
-      else {
-        const int k = ch - 27;
-        const float nk = inv_block(s, y - 1 + (k >> 1), x - 1 + (k & 1));
-        v = __fmul_rn(0.2357f, fminf(__fmul_rn(s.mag[i], nk), 0.2f));
-      }
-      v = __fmul_rn(v, __fmul_rn(tb.hann[y], tb.hann[x]));
+      va = feature_value(s, tb, cha, i, y, x);
+      if (chb >= 0) vb = feature_value(s, tb, chb, i, y, x);
     }
-    s.plane[rev6(y) * FS + rev6(x)] = make_float2(v, 0.f);
+    s.plane[rev6(y) * FS + rev6(x)] = make_float2(va, vb);
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void split_spectra(const Smem& s, int i, float2& fa, float2& fb) {
+  const int y = i >> 6, x = i & 63;
+  const float2 z = s.plane[i];
+  const float2 zm = s.plane[((FS - y) & (FS - 1)) * FS + ((FS - x) & (FS - 1))];
+  fa = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
+  fb = make_float2(0.5f * (z.y + zm.y), 0.5f * (zm.x - z.x));
 }
 
 // FFT of the Gaussian target centred at (px,py); leaves conj(G^) in s.acc
@@ -242,13 +261,20 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
     target_hat(s, tb, 0.5f * (FS - 1), 0.5f * (FS - 1));
     for (int i = tid; i < NPIX; i += kThreads) s.bsum[i] = 0.f;
     __syncthreads();
-    for (int ch = 0; ch < NCH; ++ch) {
-      build_plane(s, tb, ch);
+    for (int ch = 0; ch < NCH; ch += 2) {
+      const bool two = ch + 1 < NCH;
+      build_plane2(s, tb, ch, two ? ch + 1 : -1);
       fft2_64(s.plane, tb, false);
       for (int i = tid; i < NPIX; i += kThreads) {
-        const float2 f = s.plane[i];
-        A[(size_t)ch * NPIX + i] = cmul(s.acc[i], f);
-        s.bsum[i] += f.x * f.x + f.y * f.y;
+        float2 fa, fb;
+        split_spectra(s, i, fa, fb);
+        A[(size_t)ch * NPIX + i] = cmul(s.acc[i], fa);
+        float bs = fa.x * fa.x + fa.y * fa.y;
+        if (two) {
+          A[(size_t)(ch + 1) * NPIX + i] = cmul(s.acc[i], fb);
+          bs += fb.x * fb.x + fb.y * fb.y;
+        }
+        s.bsum[i] += bs;
       }
       __syncthreads();
     }
@@ -264,17 +290,26 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
     s.bsum[i] = 0.f;
   }
   __syncthreads();
-  for (int ch = 0; ch < NCH; ++ch) {
-    build_plane(s, tb, ch);
+  for (int ch = 0; ch < NCH; ch += 2) {
+    const bool two = ch + 1 < NCH;
+    build_plane2(s, tb, ch, two ? ch + 1 : -1);
     fft2_64(s.plane, tb, false);
     for (int i = tid; i < NPIX; i += kThreads) {
-      const float2 f = s.plane[i];
+      float2 fa, fb;
+      split_spectra(s, i, fa, fb);
       const float2 a = A[(size_t)ch * NPIX + i];
       float2 acc = s.acc[i];
-      acc.x += f.x * a.x + f.y * a.y;   // f * conj(a)
-      acc.y += f.y * a.x - f.x * a.y;
+      acc.x += fa.x * a.x + fa.y * a.y;   // f * conj(a)
+      acc.y += fa.y * a.x - fa.x * a.y;
+      float bs = fa.x * fa.x + fa.y * fa.y;
+      if (two) {
+        const float2 b2 = A[(size_t)(ch + 1) * NPIX + i];
+        acc.x += fb.x * b2.x + fb.y * b2.y;
+        acc.y += fb.y * b2.x - fb.x * b2.y;
+        bs += fb.x * fb.x + fb.y * fb.y;
+      }
       s.acc[i] = acc;
-      s.bsum[i] += f.x * f.x + f.y * f.y;
+      s.bsum[i] += bs;
     }
     __syncthreads();
   }
@@ -334,8 +369,8 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
     sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
-  __shared__ double dsum[8], dsq[8];
-  __shared__ int dcnt[8];
+  __shared__ double dsum[kThreads / 32], dsq[kThreads / 32];
+  __shared__ int dcnt[kThreads / 32];
   if ((tid & 31) == 0) { dsum[tid >> 5] = sum; dsq[tid >> 5] = sumsq; dcnt[tid >> 5] = cnt; }
   __syncthreads();
   if (tid == 0) {
@@ -368,15 +403,26 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
   // ---- pass 2: filter update ----
   target_hat(s, tb, peak[0], peak[1]);
   const float nu = p.nu, om = 1.0f - p.nu;
-  for (int ch = 0; ch < NCH; ++ch) {
-    build_plane(s, tb, ch);
+  for (int ch = 0; ch < NCH; ch += 2) {
+    const bool two = ch + 1 < NCH;
+    build_plane2(s, tb, ch, two ? ch + 1 : -1);
     fft2_64(s.plane, tb, false);
     for (int i = tid; i < NPIX; i += kThreads) {
-      const float2 gf = cmul(s.acc[i], s.plane[i]);
+      float2 fa, fb;
+      split_spectra(s, i, fa, fb);
+      const float2 g = s.acc[i];
+      const float2 ga = cmul(g, fa);
       float2 a = A[(size_t)ch * NPIX + i];
-      a.x = om * a.x + nu * gf.x;
-      a.y = om * a.y + nu * gf.y;
+      a.x = om * a.x + nu * ga.x;
+      a.y = om * a.y + nu * ga.y;
       A[(size_t)ch * NPIX + i] = a;
+      if (two) {
+        const float2 gb = cmul(g, fb);
+        float2 b2 = A[(size_t)(ch + 1) * NPIX + i];
+        b2.x = om * b2.x + nu * gb.x;
+        b2.y = om * b2.y + nu * gb.y;
+        A[(size_t)(ch + 1) * NPIX + i] = b2;
+      }
     }
     __syncthreads();
   }
@@ -396,6 +442,7 @@ constexpr int SCELLS = 6;
 constexpr int SOUT = 4;
 constexpr int SF = 31 * SOUT * SOUT;   // 496
 constexpr int ZP = NS + 1;             // padded row length (bank conflicts)
+constexpr int kGroups = kThreads / 32; // row groups for the reductions over features
 
 struct ScaleTables {
   float hann[NS];
@@ -424,8 +471,8 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
   float* s_mag = reinterpret_cast<float*>(Z + SF * ZP);             // [SW*SW]
   float* s_hist = s_mag + SW * SW;                                  // [36*18]
   float* s_nrm = s_hist + SCELLS * SCELLS * 18;                     // [36]
-  float* s_red = s_nrm + SCELLS * SCELLS;                           // [8*64 + 64]
-  uint8_t* s_chip = reinterpret_cast<uint8_t*>(s_red + 8 * 64 + 64);  // [SW*SW*3]
+  float* s_red = s_nrm + SCELLS * SCELLS;                           // [kGroups*64 + 64]
+  uint8_t* s_chip = reinterpret_cast<uint8_t*>(s_red + kGroups * 64 + 64);  // [SW*SW*3]
   uint8_t* s_ori = s_chip + SW * SW * 3 + 3;                        // [SW*SW]
   __shared__ double s_gre[NS], s_gim[NS];   // conj(FFT(target))
   __shared__ double s_rre[NS], s_rim[NS];
@@ -576,12 +623,12 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
   }
   __syncthreads();
 
-  const int k = tid & 31, grp = tid >> 5;   // 8 row groups
+  const int k = tid & 31, grp = tid >> 5;   // kGroups row groups
   float peak = 0.5f * NS;
   if (!START) {
     // response R^[k] = sum_j Z[j][k] conj(As[j][k]) / (Bs[k] + lambda)
     float re = 0.f, im = 0.f;
-    for (int j = grp; j < SF; j += 8) {
+    for (int j = grp; j < SF; j += kGroups) {
       const float2 f = Z[j * ZP + k];
       const float2 a = As[(size_t)j * NS + k];
       re += f.x * a.x + f.y * a.y;
@@ -592,7 +639,7 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
     __syncthreads();
     if (tid < NS) {
       double sr = 0, si = 0;
-      for (int g = 0; g < 8; ++g) { sr += s_red[g * 64 + tid]; si += s_red[g * 64 + 32 + tid]; }
+      for (int g = 0; g < kGroups; ++g) { sr += s_red[g * 64 + tid]; si += s_red[g * 64 + 32 + tid]; }
       const double d = 1.0 / ((double)Bs[tid] + (double)tb.lambda);
       s_rre[tid] = sr * d;
       s_rim[tid] = si * d;
@@ -648,7 +695,7 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
   {
     const float gre = (float)s_gre[k], gim = (float)s_gim[k];
     float bsum = 0.f;
-    for (int j = grp; j < SF; j += 8) {
+    for (int j = grp; j < SF; j += kGroups) {
       const float2 f = Z[j * ZP + k];
       const float2 gf = make_float2(gre * f.x - gim * f.y, gre * f.y + gim * f.x);
       bsum += f.x * f.x + f.y * f.y;
@@ -666,13 +713,13 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
     __syncthreads();
     if (tid < NS) {
       float sb = 0.f;
-      for (int g = 0; g < 8; ++g) sb += s_red[g * 64 + tid];
+      for (int g = 0; g < kGroups; ++g) sb += s_red[g * 64 + tid];
       Bs[tid] = START ? sb : (1.0f - tb.nu) * Bs[tid] + tb.nu * sb;
     }
   }
 }
 constexpr size_t kScaleSmem = (size_t)SF * ZP * 8 + (SW * SW) * 4 + (SCELLS * SCELLS * 18) * 4 + SCELLS * SCELLS * 4 +
-                              (8 * 64 + 64) * 4 + SW * SW * 3 + 3 + SW * SW + 64;
+                              (kGroups * 64 + 64) * 4 + SW * SW * 3 + 3 + SW * SW + 64;
 
 struct Bank {
   int capacity;
