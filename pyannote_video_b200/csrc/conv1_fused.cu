@@ -19,12 +19,13 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kKH = 5, kKW = 5;
 constexpr int kN = 16;
-constexpr int kRing = 3;
+constexpr int kRing = 4;
 constexpr int kAcc = 2;
 constexpr int kSlabBytes = kTileM * 32;           // 128 rows x 16 bf16
 constexpr int kSlotBytes = kKH * kSlabBytes;      // 20 KB
 constexpr int kWBytes = kKH * kN * 32;            // 2.5 KB
-constexpr int kThreads = 32 * (4 + 1 + 4);        // 4 producer warps, 1 MMA warp, 4 epilogue warps
+constexpr int kProdWarps = 8;                     // rows x {filter rows 0-2 | 3-4}
+constexpr int kThreads = 32 * (kProdWarps + 1 + 4);  // producer warps, 1 MMA warp, 4 epilogue warps
 
 struct C1Params {
   const uchar4* plane;   // [B, Hp, Wp] RGBA
@@ -53,7 +54,51 @@ __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint3
 // 256-byte aligned: Swizzle<1,4,3> = address bit 4 ^= address bit 7
 __device__ __forceinline__ uint32_t sw32(uint32_t r, uint32_t c) { return r * 32u + ((c ^ ((r >> 2) & 1u)) << 4); }
 
-__global__ void __launch_bounds__(kThreads, 3) conv1_fused_kernel(const __grid_constant__ C1Params p) {
+// filter rows [KH0, KH1) of tile row m: pixel loads are issued up front with clamped coordinates (no
+// branches around them) so they are all in flight together; validity is applied afterwards
+template <int KH0, int KH1>
+__device__ __forceinline__ void produce_rows(const C1Params& p, bool in_range, uint32_t n, uint32_t oy, uint32_t ox,
+                                             uint32_t m, uint8_t* ring, uint64_t* bar_empty, uint32_t phase, int slot) {
+  uchar4 px[KH1 - KH0][kKW];
+  const int x0 = 2 * (int)ox;
+#pragma unroll
+  for (int kh = KH0; kh < KH1; ++kh) {
+    const int y = min(2 * (int)oy + kh, p.Hp - 1);
+    const uchar4* src = p.plane + ((long long)min(n, (uint32_t)(p.B - 1)) * p.Hp + y) * p.Wp;
+#pragma unroll
+    for (int kw = 0; kw < kKW; ++kw) px[kh - KH0][kw] = __ldg(src + min(x0 + kw, p.Wp - 1));
+  }
+  pv_mbar_wait(bar_empty, phase ^ 1u, p.err, 1);
+  uint8_t* base = ring + slot * kSlotBytes;
+#pragma unroll
+  for (int kh = KH0; kh < KH1; ++kh) {
+    const bool row_ok = in_range && (2 * (int)oy + kh < p.Hp);
+    float f[16];
+    f[15] = 0.f;
+#pragma unroll
+    for (int kw = 0; kw < kKW; ++kw) {
+      const uchar4 q4 = px[kh - KH0][kw];
+      const bool ok = row_ok && (x0 + kw < p.Wp) && (q4.w != 0);
+      f[kw * 3 + 0] = ok ? __fmul_rn(__fsub_rn((float)q4.x, p.m0), 0.00390625f) : 0.f;
+      f[kw * 3 + 1] = ok ? __fmul_rn(__fsub_rn((float)q4.y, p.m1), 0.00390625f) : 0.f;
+      f[kw * 3 + 2] = ok ? __fmul_rn(__fsub_rn((float)q4.z, p.m2), 0.00390625f) : 0.f;
+    }
+    uint4 c0, c1;
+    c0.x = pv_pack_bf16x2(f[0], f[1]);
+    c0.y = pv_pack_bf16x2(f[2], f[3]);
+    c0.z = pv_pack_bf16x2(f[4], f[5]);
+    c0.w = pv_pack_bf16x2(f[6], f[7]);
+    c1.x = pv_pack_bf16x2(f[8], f[9]);
+    c1.y = pv_pack_bf16x2(f[10], f[11]);
+    c1.z = pv_pack_bf16x2(f[12], f[13]);
+    c1.w = pv_pack_bf16x2(f[14], f[15]);
+    uint8_t* slab = base + kh * kSlabBytes;
+    *reinterpret_cast<uint4*>(slab + sw32(m, 0)) = c0;
+    *reinterpret_cast<uint4*>(slab + sw32(m, 1)) = c1;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_constant__ C1Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;                               // kRing slots of 5 slabs
@@ -82,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 3) conv1_fused_kernel(const __grid_c
   }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kRing; ++i) {
-      pv_mbar_init(&bar_full[i], 4);     // one arrival per producer warp
+      pv_mbar_init(&bar_full[i], kProdWarps);     // one arrival per producer warp
       pv_mbar_init(&bar_empty[i], 1);
     }
     for (int i = 0; i < kAcc; ++i) {
@@ -92,16 +137,16 @@ __global__ void __launch_bounds__(kThreads, 3) conv1_fused_kernel(const __grid_c
     pv_fence_mbar_init();
   }
   pv_fence_proxy_async();                  // weights written through the generic proxy, read by the tensor core
-  if (warp == 4) pv_tmem_alloc(s_tmem, 32);
+  if (warp == kProdWarps) pv_tmem_alloc(s_tmem, 32);
   pv_tc_fence_before();
   __syncthreads();
   pv_tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const uint32_t img = (uint32_t)p.hq * (uint32_t)p.wq;
 
-  if (warp < 4) {
+  if (warp < kProdWarps) {
     // ===================== producers: build the A slabs =====================
-    const uint32_t m = (uint32_t)threadIdx.x;   // row of the tile
+    const uint32_t m = (uint32_t)threadIdx.x & 127u;   // row of the tile
     int slot = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -111,47 +156,16 @@ __global__ void __launch_bounds__(kThreads, 3) conv1_fused_kernel(const __grid_c
       const uint32_t rem = q - n * img;
       const uint32_t oy = rem / (uint32_t)p.wq;
       const uint32_t ox = rem - oy * (uint32_t)p.wq;
-      pv_mbar_wait(&bar_empty[slot], phase ^ 1u, p.err, 1);
-      uint8_t* base = ring + slot * kSlotBytes;
-#pragma unroll
-      for (int kh = 0; kh < kKH; ++kh) {
-        const int y = 2 * (int)oy + kh;
-        float f[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) f[k] = 0.f;
-        if (in_range && y < p.Hp) {
-          const uchar4* src = p.plane + ((long long)n * p.Hp + y) * p.Wp + 2 * ox;
-#pragma unroll
-          for (int kw = 0; kw < kKW; ++kw) {
-            if (2 * (int)ox + kw < p.Wp) {
-              const uchar4 px = src[kw];
-              if (px.w) {
-                f[kw * 3 + 0] = __fmul_rn(__fsub_rn((float)px.x, p.m0), 0.00390625f);
-                f[kw * 3 + 1] = __fmul_rn(__fsub_rn((float)px.y, p.m1), 0.00390625f);
-                f[kw * 3 + 2] = __fmul_rn(__fsub_rn((float)px.z, p.m2), 0.00390625f);
-              }
-            }
-          }
-        }
-        uint4 c0, c1;
-        c0.x = pv_pack_bf16x2(f[0], f[1]);
-        c0.y = pv_pack_bf16x2(f[2], f[3]);
-        c0.z = pv_pack_bf16x2(f[4], f[5]);
-        c0.w = pv_pack_bf16x2(f[6], f[7]);
-        c1.x = pv_pack_bf16x2(f[8], f[9]);
-        c1.y = pv_pack_bf16x2(f[10], f[11]);
-        c1.z = pv_pack_bf16x2(f[12], f[13]);
-        c1.w = pv_pack_bf16x2(f[14], f[15]);
-        uint8_t* slab = base + kh * kSlabBytes;
-        *reinterpret_cast<uint4*>(slab + sw32(m, 0)) = c0;
-        *reinterpret_cast<uint4*>(slab + sw32(m, 1)) = c1;
-      }
+      if (threadIdx.x >> 7)
+        produce_rows<3, 5>(p, in_range, n, oy, ox, m, ring, &bar_empty[slot], phase, slot);
+      else
+        produce_rows<0, 3>(p, in_range, n, oy, ox, m, ring, &bar_empty[slot], phase, slot);
       pv_fence_proxy_async();        // make this thread's smem writes visible to the async (tensor-core) proxy
       __syncwarp();
       if (lane == 0) pv_mbar_arrive(&bar_full[slot]);
       if (++slot == kRing) { slot = 0; phase ^= 1u; }
     }
-  } else if (warp == 4) {
+  } else if (warp == kProdWarps) {
     // ===================== MMA issuer =====================
     const uint32_t lead = pv_elect_one() ? 1u : 0u;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
@@ -222,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 3) conv1_fused_kernel(const __grid_c
   }
   pv_tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kProdWarps) {
     __syncwarp();
     pv_tmem_dealloc(tmem_base, 32);
   }
@@ -266,7 +280,7 @@ extern "C" int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, con
     PV_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     PV_CUDA_CHECK(cudaFuncSetAttribute(conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   }
-  int grid = num_sms * 3;
+  int grid = num_sms * 2;
   if (grid > p.num_tiles) grid = p.num_tiles;
   conv1_fused_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
   g_pv_launches.fetch_add(1);

@@ -5,6 +5,6 @@ grep -E "passed|failed|error|Error|assert" gpurun_out/pytest_gpu.log | tail -25
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1.log 2>&1; echo "bench rc=$?"; tail -2 gpurun_out/bench_n1.log | cut -c1-2200
 PV_DET_CONV1=fused timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1_fused.log 2>&1; echo "bench fused rc=$?"; tail -2 gpurun_out/bench_n1_fused.log | cut -c1-1800
 rm -f gpurun_out/aux_bench.jsonl
-timeout 900 python scripts/gpu_bench_aux.py --frames 100 --n 20000 > gpurun_out/aux_bench.log 2>&1; tail -3 gpurun_out/aux_bench.log | cut -c1-600
+timeout 900 python scripts/gpu_bench_aux.py --frames 100 --n 100000 > gpurun_out/aux_bench.log 2>&1; tail -3 gpurun_out/aux_bench.log | cut -c1-600
 PV_DET_CONV1=fused timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 150 --csv --log-file gpurun_out/launches_fused.csv python bench.py --steps 3 --warmup 1 --no-cpu-baseline --profile-convs 0 > gpurun_out/bench_ncu.log 2>&1
 ls -la gpurun_out

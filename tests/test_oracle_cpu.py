@@ -182,3 +182,44 @@ def test_hac_known_cut_and_scipy_crosscheck():
     Z = fcluster(linkage(Y, "average"), t=0.6, criterion="distance")
     ref = ohac.partition_of({i: int(z) for i, z in enumerate(Z)})
     assert ours == ref
+
+
+# ---------------------------------------------------------------- correlation tracker (DSST)
+def test_dsst_oracle_follows_translation_and_zoom():
+    """known answers for the tracker restatement: a canvas moving by (-2,-1) px/frame is followed with
+    PSR >> 10; a 6 % magnification about the box centre is recovered by the scale filter."""
+    import cv2
+    from oracle.dsst import CorrelationTracker
+    from pyannote_video_b200.synth import make_frames
+    fr = make_frames(5, 240, 320, seed=3, shift_per_frame=(2.0, 1.0)).numpy()
+    tr = CorrelationTracker()
+    tr.start_track(fr[0], (100.0, 60.0, 180.0, 140.0))
+    psrs = [tr.update(fr[i]) for i in range(1, 5)]
+    p = tr.get_position()
+    assert min(psrs) > 10
+    assert abs((p[0] - 100.0) - (-2.0 * 4)) < 1.0 and abs((p[1] - 60.0) - (-1.0 * 4)) < 1.0
+    z = 1.06
+    big = cv2.resize(fr[0], None, fx=z, fy=z, interpolation=cv2.INTER_LINEAR)
+    cx, cy = 140.0 * z, 100.0 * z
+    ox, oy = int(round(cx - 140.0)), int(round(cy - 100.0))
+    f1 = np.ascontiguousarray(big[oy:oy + 240, ox:ox + 320])
+    t2 = CorrelationTracker()
+    t2.start_track(fr[0], (100.0, 60.0, 180.0, 140.0))
+    t2.update(f1)
+    q = t2.get_position()
+    assert abs((q[2] - q[0]) / 80.0 - z) < 0.02
+
+
+def test_fhog_known_answers():
+    from oracle.dsst import fhog_cell1, fhog_cell4
+    flat = np.full((64, 64, 3), 90, np.uint8)
+    assert np.abs(fhog_cell1(flat)).max() == 0          # no gradient -> no features
+    ramp = np.zeros((64, 64, 3), np.uint8)
+    ramp[:] = (np.arange(64) * 3)[None, :, None]         # horizontal ramp: gradient along +x only
+    f = fhog_cell1(ramp)
+    inner = f[:, 8:56, 8:56]
+    on = [c for c in range(18) if inner[c].max() > 0]
+    assert on == [0]                                     # orientation bin 0 (cos 0 = 1), contrast-sensitive
+    assert inner[18].max() > 0 and inner[19:27].max() == 0
+    f4 = fhog_cell4(ramp[:23, :23])
+    assert f4.shape == (31, 4, 4) and f4[0].min() > 0 and f4[1:18].max() == 0
