@@ -143,8 +143,9 @@ int pv_pack_gathered(const void* rgba, void* out, int B, int H, int W, int kw, i
 int pv_plane_to_pixrows(const void* rgba, void* out, int B, int H, int W, int64_t layout_plane_rows,
                         const float* mean_host, void* stream);
 /* first detector conv (5x5 stride 2, RGB -> 16) fused with input normalisation: reads the RGBA u8 plane
- * [B,Hp,Wp,4] in place and builds the swizzled bf16 A tiles in shared memory (csrc/conv1_fused.cu).
- * w_bf16 [5][16][16] (k = kw*3+c), scale/shift f32 [16], out rows via `dst`, err_flag: device int. */
+ * [B,Hp,Wp,4] in place (TMA, Wp % 4 == 0) and feeds tcgen05.mma from a normalised pixel-row buffer in
+ * shared memory (csrc/conv1_fused.cu).  w_bf16 [16][3][5][5] (dlib order), scale/shift f32 [16],
+ * oh = (Hp-5)/2+1, ow = (Wp-5)/2+1, out rows via `dst`, err_flag: device int. */
 int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, const void* w_bf16, const float* scale,
                    const float* shift, int relu, void* out, const PvRowMap* dst, int oh, int ow, const float* mean_host,
                    int* err_flag, void* stream);

@@ -8,7 +8,12 @@ SRGEMM_GROUP = "row"   # validated on B200 (gpurun #1): descriptors at arbitrary
 # (gpurun #1 also settled the UMMA descriptor question: base_offset stays 0; the tensor core applies the
 # swizzle XOR to absolute shared-memory address bits, exactly like TMA does when it writes the slab.)
 
-# first detector conv input: "gathered" (pack kernel writes kw*3-wide rows, 16 B/pixel) or
-# "pixrows" (conv reads 8-pixel runs of a bf16 RGBX plane in place through an overlapping-row
-# tensor map, 8 B/pixel; needs cuTensorMapEncodeTiled to accept a 16-byte row stride)
-DET_CONV1 = os.environ.get("PV_DET_CONV1", "gathered")
+# first detector conv input:
+#   "fused"    conv1_fused.cu reads the RGBA u8 plane by TMA, normalises every pixel once into a
+#              shared-memory pixel-row buffer and lets tcgen05.mma read OVERLAPPING A rows from it
+#              (no im2col in HBM or in shared memory).  8 frames 1080p: 1.36 ms            [default]
+#   "gathered" pack kernel writes kw*3-wide bf16 rows (16 B/pixel), generic srgemm reads them back:
+#              1.15 + 1.73 ms
+#   "pixrows"  pack kernel writes a bf16 RGBX plane (8 B/pixel), srgemm reads 8-pixel runs through an
+#              overlapping-row tensor map (row stride 16 B): slower than "gathered" (L2-bound re-reads)
+DET_CONV1 = os.environ.get("PV_DET_CONV1", "fused")

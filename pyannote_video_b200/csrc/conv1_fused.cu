@@ -4,11 +4,22 @@
 //
 // The generic path first writes a "gathered" bf16 matrix (16 B per plane pixel) and reads it back
 // through TMA; with ~32 M plane pixels per 1080p frame that round trip is the largest HBM stream of
-// the whole detector.  Here four producer warps build the 128 x 16 A tile of every filter row in
-// shared memory themselves — normalise (v - mean)/256, convert to bf16, store in the 32-byte-swizzled
-// K-major layout tcgen05.mma expects — so the plane is read once (4 B/pixel) and nothing is written.
-// MMA issue, TMEM accumulators and the fused affine + ReLU epilogue are as in srgemm.cu.
+// the whole detector.  Here the plane is read once, as raw pixels, by TMA (asynchronous, deep ring);
+// eight converter warps normalise every raw pixel ONCE — (v - mean)/256 as bf16 RGB0, 8 bytes — into
+// a pixel-row buffer in shared memory, and tcgen05.mma reads its A operand straight out of that
+// buffer: in the un-swizzled K-major layout the 8 rows of a core matrix are 16 bytes apart, which is
+// exactly the 2-pixel step between neighbouring outputs of a stride-2 convolution, so the A rows
+// (the 5-pixel windows) simply OVERLAP in shared memory and no im2col gather is ever materialised.
+//   A row m, filter row kh  = pixels 2m .. 2m+5 of buffer row kh   (3 chunks of 2 pixels = 8 bf16)
+//   MMA j = 0..4 : chunks 0,1 of filter row j               (LBO = 16 B)
+//   MMA 5, 6     : chunk 2 of filter rows (0,1) and (2,3)   (LBO = one buffer row)
+//   MMA 7        : chunk 2 of filter row 4 (+ a zero-weight chunk)
+// A tile is 126 consecutive outputs of ONE output row (2*125 + 5 = 255 input pixels fit one 256-pixel
+// TMA box; rows 126/127 of the MMA are padding), so TMA's out-of-bounds zero fill is the plane's zero
+// padding and tile coordinates advance without divisions.
+#include <cuda.h>
 #include <atomic>
+#include <cstdlib>
 #include "../../include/pv_b200.h"
 #include "pv_common.cuh"
 
@@ -17,29 +28,37 @@ extern std::atomic<long long> g_pv_launches;
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kKH = 5, kKW = 5;
+constexpr int kTileOut = 126;                     // valid outputs per tile
+constexpr int kKH = 5;
 constexpr int kN = 16;
-constexpr int kRing = 4;
+constexpr int kRawW = 256;                        // pixels per raw row (TMA box)
+constexpr int kRawBytes = kKH * kRawW * 4;        // 5 KB
+constexpr int kRawRing = 6;
+constexpr int kPxRowBytes = (kRawW + 8) * 8;      // 264 pixels x 8 B; the 8 trailing pixels stay zero
+constexpr int kPxSlotBytes = 10752;               // 5 rows (10560 B) rounded up to 128
+constexpr int kPxRing = 4;
 constexpr int kAcc = 2;
-constexpr int kSlabBytes = kTileM * 32;           // 128 rows x 16 bf16
-constexpr int kSlotBytes = kKH * kSlabBytes;      // 20 KB
-constexpr int kWBytes = kKH * kN * 32;            // 2.5 KB
-constexpr int kProdWarps = 8;                     // rows x {filter rows 0-2 | 3-4}
-constexpr int kThreads = 32 * (kProdWarps + 1 + 4);  // producer warps, 1 MMA warp, 4 epilogue warps
+constexpr int kNumMma = 8;
+constexpr int kWBytes = kNumMma * 512;            // 8 B operands of 16 x 16 bf16
+constexpr int kConvWarps = 8;
+// warps: 0 = TMA, 1 = MMA, 2..9 = converters, 10..13 = epilogue
+constexpr int kThreads = 32 * (2 + kConvWarps + 4);
+static_assert(kPxSlotBytes >= kKH * kPxRowBytes, "slot too small");
 
 struct C1Params {
-  const uchar4* plane;   // [B, Hp, Wp] RGBA
+  CUtensorMap raw;       // uint32 [B*Hp rows, Wp cols], box 256 x 5
   int B, Hp, Wp;
-  int hq, wq, oh, ow;    // output grid (ceil(Hp/2), ceil(Wp/2)) and valid extent
-  const __nv_bfloat16* w;  // [5][16][16] (k = kw*3 + c, k = 15 is zero)
+  int oh, ow;            // valid output extent
+  int tiles_per_row;
+  const __nv_bfloat16* w;  // [16][3][5][5]
   const float* scale;
   const float* shift;
   int relu;
   __nv_bfloat16* out;
   PvRowMap dst;
-  float m0, m1, m2;
-  long long q_rows;
+  float c0, c1, c2;      // -mean/256
   int num_tiles;
+  int swap_ls;
   int* err;
 };
 
@@ -50,62 +69,52 @@ __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint3
   return (long long)plane * m.plane_rows + (long long)n * m.img + (long long)(Y >> 1) * m.w + (X >> 1);
 }
 
-// byte offset of 16-byte chunk `c` (0/1) of row `r` in a 32-byte-swizzled K-major tile whose base is
-// 256-byte aligned: Swizzle<1,4,3> = address bit 4 ^= address bit 7
-__device__ __forceinline__ uint32_t sw32(uint32_t r, uint32_t c) { return r * 32u + ((c ^ ((r >> 2) & 1u)) << 4); }
+// tile -> (image, output row, first output column), advanced by gridDim.x tiles without divisions
+struct TileWalk {
+  uint32_t n, oy, ct;
+  uint32_t step_n, step_oy, step_ct;
+  __device__ __forceinline__ void init(const C1Params& p, uint32_t tile, uint32_t step) {
+    const uint32_t tpr = (uint32_t)p.tiles_per_row, oh = (uint32_t)p.oh;
+    uint32_t r = tile / tpr;
+    ct = tile - r * tpr;
+    n = r / oh;
+    oy = r - n * oh;
+    r = step / tpr;
+    step_ct = step - r * tpr;
+    step_n = r / oh;
+    step_oy = r - step_n * oh;
+  }
+  __device__ __forceinline__ void next(const C1Params& p) {
+    ct += step_ct;
+    oy += step_oy;
+    n += step_n;
+    if (ct >= (uint32_t)p.tiles_per_row) { ct -= (uint32_t)p.tiles_per_row; ++oy; }
+    if (oy >= (uint32_t)p.oh) { oy -= (uint32_t)p.oh; ++n; }
+  }
+};
 
-// filter rows [KH0, KH1) of tile row m: pixel loads are issued up front with clamped coordinates (no
-// branches around them) so they are all in flight together; validity is applied afterwards
-template <int KH0, int KH1>
-__device__ __forceinline__ void produce_rows(const C1Params& p, bool in_range, uint32_t n, uint32_t oy, uint32_t ox,
-                                             uint32_t m, uint8_t* ring, uint64_t* bar_empty, uint32_t phase, int slot) {
-  uchar4 px[KH1 - KH0][kKW];
-  const int x0 = 2 * (int)ox;
-#pragma unroll
-  for (int kh = KH0; kh < KH1; ++kh) {
-    const int y = min(2 * (int)oy + kh, p.Hp - 1);
-    const uchar4* src = p.plane + ((long long)min(n, (uint32_t)(p.B - 1)) * p.Hp + y) * p.Wp;
-#pragma unroll
-    for (int kw = 0; kw < kKW; ++kw) px[kh - KH0][kw] = __ldg(src + min(x0 + kw, p.Wp - 1));
-  }
-  pv_mbar_wait(bar_empty, phase ^ 1u, p.err, 1);
-  uint8_t* base = ring + slot * kSlotBytes;
-#pragma unroll
-  for (int kh = KH0; kh < KH1; ++kh) {
-    const bool row_ok = in_range && (2 * (int)oy + kh < p.Hp);
-    float f[16];
-    f[15] = 0.f;
-#pragma unroll
-    for (int kw = 0; kw < kKW; ++kw) {
-      const uchar4 q4 = px[kh - KH0][kw];
-      const bool ok = row_ok && (x0 + kw < p.Wp) && (q4.w != 0);
-      f[kw * 3 + 0] = ok ? __fmul_rn(__fsub_rn((float)q4.x, p.m0), 0.00390625f) : 0.f;
-      f[kw * 3 + 1] = ok ? __fmul_rn(__fsub_rn((float)q4.y, p.m1), 0.00390625f) : 0.f;
-      f[kw * 3 + 2] = ok ? __fmul_rn(__fsub_rn((float)q4.z, p.m2), 0.00390625f) : 0.f;
-    }
-    uint4 c0, c1;
-    c0.x = pv_pack_bf16x2(f[0], f[1]);
-    c0.y = pv_pack_bf16x2(f[2], f[3]);
-    c0.z = pv_pack_bf16x2(f[4], f[5]);
-    c0.w = pv_pack_bf16x2(f[6], f[7]);
-    c1.x = pv_pack_bf16x2(f[8], f[9]);
-    c1.y = pv_pack_bf16x2(f[10], f[11]);
-    c1.z = pv_pack_bf16x2(f[12], f[13]);
-    c1.w = pv_pack_bf16x2(f[14], f[15]);
-    uint8_t* slab = base + kh * kSlabBytes;
-    *reinterpret_cast<uint4*>(slab + sw32(m, 0)) = c0;
-    *reinterpret_cast<uint4*>(slab + sw32(m, 1)) = c1;
-  }
+// un-swizzled K-major operand: start address, LBO = byte step between the two 8-element K chunks,
+// SBO = byte step between 8-row groups (cute::UMMA::SmemDescriptor, LayoutType::INTERLEAVE; version 1)
+__device__ __forceinline__ uint64_t desc_kmajor_plain(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
 }
 
 __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_constant__ C1Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = smem;                               // kRing slots of 5 slabs
-  uint8_t* wsm = ring + kRing * kSlotBytes;           // swizzled weights (1024-aligned: 20 KB slots)
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(wsm + ((kWBytes + 1023) & ~1023));
-  uint64_t* bar_empty = bar_full + kRing;
-  uint64_t* bar_tfull = bar_empty + kRing;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* pxb = smem;                                // kPxRing slots of 5 bf16 pixel rows
+  uint8_t* raw = pxb + kPxRing * kPxSlotBytes;        // kRawRing raw pixel blocks
+  uint8_t* wsm = raw + kRawRing * kRawBytes;          // 8 B operands
+  uint64_t* bar_rfull = reinterpret_cast<uint64_t*>(wsm + kWBytes);
+  uint64_t* bar_rempty = bar_rfull + kRawRing;
+  uint64_t* bar_full = bar_rempty + kRawRing;
+  uint64_t* bar_empty = bar_full + kPxRing;
+  uint64_t* bar_tfull = bar_empty + kPxRing;
   uint64_t* bar_tempty = bar_tfull + kAcc;
   float* s_scale = reinterpret_cast<float*>(bar_tempty + kAcc);
   float* s_shift = s_scale + kN;
@@ -115,19 +124,40 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
   const int lane = threadIdx.x & 31;
 
   // ---- setup ----
-  for (int i = threadIdx.x; i < kKH * kN * 2; i += kThreads) {   // one 16-byte chunk per iteration
-    const int kh = i / (kN * 2), rem = i - kh * kN * 2;
-    const int n = rem >> 1, c = rem & 1;
-    const uint4 v = *reinterpret_cast<const uint4*>(p.w + ((kh * kN + n) * 16 + c * 8));
-    *reinterpret_cast<uint4*>(wsm + kh * (kN * 32) + sw32((uint32_t)n, (uint32_t)c)) = v;
+  // B operand j: element (n, k) at j*512 + (k>>3)*256 + (n>>3)*128 + (n&7)*16 + (k&7)*2
+  for (int i = threadIdx.x; i < kNumMma * kN * 16; i += kThreads) {
+    const int j = i >> 8, n = (i >> 4) & 15, k = i & 15;
+    const int ch = k & 3;
+    int kh, kw;
+    if (j < 5) {
+      kh = j;
+      kw = k >> 2;
+    } else {
+      kh = (j - 5) * 2 + (k >> 3);
+      kw = 4 + ((k >> 2) & 1);
+    }
+    const bool ok = ch < 3 && kw < 5 && kh < 5;
+    const __nv_bfloat16 v = ok ? p.w[((n * 3 + ch) * 5 + kh) * 5 + kw] : __float2bfloat16(0.f);
+    *reinterpret_cast<__nv_bfloat16*>(wsm + j * 512 + (k >> 3) * 256 + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = v;
+  }
+  // trailing 8 pixels of every buffer row: read by the padding rows of the MMA, must be finite
+  for (int i = threadIdx.x; i < kPxRing * kKH * 8; i += kThreads) {
+    const int s = i / (kKH * 8), rem = i - s * (kKH * 8);
+    const int kh = rem >> 3, q = rem & 7;
+    *reinterpret_cast<uint2*>(pxb + s * kPxSlotBytes + kh * kPxRowBytes + (kRawW + q) * 8) = make_uint2(0u, 0u);
   }
   if (threadIdx.x < kN) {
     s_scale[threadIdx.x] = p.scale[threadIdx.x];
     s_shift[threadIdx.x] = p.shift[threadIdx.x];
   }
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < kRing; ++i) {
-      pv_mbar_init(&bar_full[i], kProdWarps);     // one arrival per producer warp
+    pv_tma_prefetch_desc(&p.raw);
+    for (int i = 0; i < kRawRing; ++i) {
+      pv_mbar_init(&bar_rfull[i], 1);
+      pv_mbar_init(&bar_rempty[i], kConvWarps);
+    }
+    for (int i = 0; i < kPxRing; ++i) {
+      pv_mbar_init(&bar_full[i], kConvWarps);     // one arrival per converter warp
       pv_mbar_init(&bar_empty[i], 1);
     }
     for (int i = 0; i < kAcc; ++i) {
@@ -136,78 +166,113 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
     }
     pv_fence_mbar_init();
   }
-  pv_fence_proxy_async();                  // weights written through the generic proxy, read by the tensor core
-  if (warp == kProdWarps) pv_tmem_alloc(s_tmem, 32);
+  pv_fence_proxy_async();                  // weights / zero pads written through the generic proxy, read by the tensor core
+  if (warp == 1) pv_tmem_alloc(s_tmem, 32);
   pv_tc_fence_before();
   __syncthreads();
   pv_tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const uint32_t img = (uint32_t)p.hq * (uint32_t)p.wq;
 
-  if (warp < kProdWarps) {
-    // ===================== producers: build the A slabs =====================
-    const uint32_t m = (uint32_t)threadIdx.x & 127u;   // row of the tile
-    int slot = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const uint32_t q = (uint32_t)tile * kTileM + m;
-      const bool in_range = (long long)q < p.q_rows;
-      const uint32_t n = q / img;
-      const uint32_t rem = q - n * img;
-      const uint32_t oy = rem / (uint32_t)p.wq;
-      const uint32_t ox = rem - oy * (uint32_t)p.wq;
-      if (threadIdx.x >> 7)
-        produce_rows<3, 5>(p, in_range, n, oy, ox, m, ring, &bar_empty[slot], phase, slot);
-      else
-        produce_rows<0, 3>(p, in_range, n, oy, ox, m, ring, &bar_empty[slot], phase, slot);
-      pv_fence_proxy_async();        // make this thread's smem writes visible to the async (tensor-core) proxy
-      __syncwarp();
-      if (lane == 0) pv_mbar_arrive(&bar_full[slot]);
-      if (++slot == kRing) { slot = 0; phase ^= 1u; }
+  if (warp == 0) {
+    // ===================== TMA: raw pixel blocks =====================
+    if (pv_elect_one()) {
+      TileWalk t;
+      t.init(p, blockIdx.x, gridDim.x);
+      int rs = 0;
+      uint32_t rphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        pv_mbar_wait_backoff(&bar_rempty[rs], rphase ^ 1u, p.err, 1, 64);
+        pv_mbar_arrive_expect_tx(&bar_rfull[rs], kRawBytes);
+        pv_tma_load_2d(raw + rs * kRawBytes, &p.raw, &bar_rfull[rs], (int32_t)(2 * kTileOut * t.ct),
+                       (int32_t)(t.n * (uint32_t)p.Hp + 2 * t.oy));
+        if (++rs == kRawRing) { rs = 0; rphase ^= 1u; }
+        t.next(p);
+      }
     }
-  } else if (warp == kProdWarps) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t lead = pv_elect_one() ? 1u : 0u;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    const uint32_t hi = ((256u >> 4)) | (1u << 14) | (6u << 29);   // SBO = 256 B, version 1, SWIZZLE_32B
-    const uint32_t w_lo = ((pv_smem_u32(wsm) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t a_sbo = 128u, b_lbo = 256u, b_sbo = 128u;
+    uint64_t bdesc[kNumMma];
+#pragma unroll
+    for (int j = 0; j < kNumMma; ++j)
+      bdesc[j] = p.swap_ls ? desc_kmajor_plain(pv_smem_u32(wsm + j * 512), b_sbo, b_lbo)
+                           : desc_kmajor_plain(pv_smem_u32(wsm + j * 512), b_lbo, b_sbo);
     int slot = 0, buf = 0;
     uint32_t phase = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       pv_mbar_wait(&bar_tempty[buf], aphase ^ 1u, p.err, 2);
       pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
       pv_tc_fence_after();
-      const uint32_t a_lo = ((pv_smem_u32(ring + slot * kSlotBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a0 = pv_smem_u32(pxb + slot * kPxSlotBytes);
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kN);
 #pragma unroll
-      for (int kh = 0; kh < kKH; ++kh)
-        pv_umma_bf16_pred(tmem_d, ((uint64_t)hi << 32) | (a_lo + kh * (kSlabBytes >> 4)),
-                          ((uint64_t)hi << 32) | (w_lo + kh * ((kN * 32) >> 4)), idesc, kh > 0 ? 1u : 0u, lead);
+      for (int j = 0; j < kNumMma; ++j) {
+        const uint32_t addr = j < 5 ? a0 + j * kPxRowBytes : a0 + (j - 5) * 2 * kPxRowBytes + 32;
+        const uint32_t lbo = (j == 5 || j == 6) ? (uint32_t)kPxRowBytes : 16u;
+        const uint64_t ad = p.swap_ls ? desc_kmajor_plain(addr, a_sbo, lbo) : desc_kmajor_plain(addr, lbo, a_sbo);
+        pv_umma_bf16_pred(tmem_d, ad, bdesc[j], idesc, j > 0 ? 1u : 0u, lead);
+      }
       pv_umma_commit_pred(&bar_empty[slot], lead);
       pv_umma_commit_pred(&bar_tfull[buf], lead);
-      if (++slot == kRing) { slot = 0; phase ^= 1u; }
+      if (++slot == kPxRing) { slot = 0; phase ^= 1u; }
       if (++buf == kAcc) { buf = 0; aphase ^= 1u; }
+    }
+  } else if (warp < 2 + kConvWarps) {
+    // ===================== converters: every raw pixel -> bf16 RGB0, once =====================
+    const int ct = threadIdx.x - 64;               // pixel column 0..255 of the block
+    int rs = 0, slot = 0;
+    uint32_t rphase = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      pv_mbar_wait(&bar_rfull[rs], rphase, p.err, 5);
+      const uint32_t* rb = reinterpret_cast<const uint32_t*>(raw + rs * kRawBytes) + ct;
+      uint32_t v[kKH];
+#pragma unroll
+      for (int kh = 0; kh < kKH; ++kh) v[kh] = rb[kh * kRawW];
+      pv_mbar_wait(&bar_empty[slot], phase ^ 1u, p.err, 6);
+      uint8_t* dstp = pxb + slot * kPxSlotBytes + ct * 8;
+#pragma unroll
+      for (int kh = 0; kh < kKH; ++kh) {
+        // (v - mean)/256 == fma(v, 2^-8, -mean*2^-8) bit for bit (power-of-two scaling commutes with rounding)
+        const float r = fmaf((float)(v[kh] & 255u), 0.00390625f, p.c0);
+        const float g = fmaf((float)((v[kh] >> 8) & 255u), 0.00390625f, p.c1);
+        const float b = fmaf((float)((v[kh] >> 16) & 255u), 0.00390625f, p.c2);
+        const bool a = (v[kh] >> 24) != 0u;          // alpha 0 = pyramid padding / TMA zero fill -> exact 0
+        uint2 o;
+        o.x = a ? pv_pack_bf16x2(r, g) : 0u;
+        o.y = a ? pv_pack_bf16x2(b, 0.f) : 0u;
+        *reinterpret_cast<uint2*>(dstp + kh * kPxRowBytes) = o;
+      }
+      pv_fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        pv_mbar_arrive(&bar_full[slot]);
+        pv_mbar_arrive(&bar_rempty[rs]);
+      }
+      if (++rs == kRawRing) { rs = 0; rphase ^= 1u; }
+      if (++slot == kPxRing) { slot = 0; phase ^= 1u; }
     }
   } else {
     // ===================== epilogue =====================
     const int quarter = warp & 3;
     const uint32_t m = (uint32_t)(quarter * 32 + lane);
+    TileWalk t;
+    t.init(p, blockIdx.x, gridDim.x);
     int buf = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const uint32_t q = (uint32_t)tile * kTileM + m;
-      bool valid = (long long)q < p.q_rows;
-      const uint32_t n = q / img;
-      const uint32_t rem = q - n * img;
-      const uint32_t y = rem / (uint32_t)p.wq;
-      const uint32_t x = rem - y * (uint32_t)p.wq;
-      valid = valid && (y < (uint32_t)p.oh) && (x < (uint32_t)p.ow);
-      const long long drow = row_of(p.dst, n, y, x);
-      pv_mbar_wait(&bar_tfull[buf], aphase, p.err, 4);
+      const uint32_t x = t.ct * kTileOut + m;
+      const bool valid = (m < (uint32_t)kTileOut) && (x < (uint32_t)p.ow);
+      const long long drow = row_of(p.dst, t.n, t.oy, x);
+      pv_mbar_wait_backoff(&bar_tfull[buf], aphase, p.err, 4, 32);
       pv_tc_fence_after();
       uint32_t v[16];
       pv_tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kN), v);
       pv_tmem_ld_wait();
+      pv_tc_fence_before();
+      __syncwarp();
+      if (lane == 0) pv_mbar_arrive(&bar_tempty[buf]);   // accumulator is in registers: release it early
       if (valid) {
         float f[16];
 #pragma unroll
@@ -228,21 +293,24 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
         dp[0] = o0;
         dp[1] = o1;
       }
-      pv_tc_fence_before();
-      __syncwarp();
-      if (lane == 0) pv_mbar_arrive(&bar_tempty[buf]);
       if (++buf == kAcc) { buf = 0; aphase ^= 1u; }
+      t.next(p);
     }
   }
   pv_tc_fence_before();
   __syncthreads();
-  if (warp == kProdWarps) {
+  if (warp == 1) {
     __syncwarp();
     pv_tmem_dealloc(tmem_base, 32);
   }
 }
 
-constexpr size_t kSmemBytes = 1024 + kRing * kSlotBytes + ((kWBytes + 1023) & ~1023) + (2 * kRing + 2 * kAcc) * 8 + 2 * kN * 4 + 64;
+constexpr size_t kSmemBytes = 128 + kPxRing * kPxSlotBytes + kRawRing * kRawBytes + kWBytes +
+                              (2 * kRawRing + 2 * kPxRing + 2 * kAcc) * 8 + 2 * kN * 4 + 64;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 }  // namespace
 
@@ -251,35 +319,60 @@ extern "C" int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, con
                               const float* mean_host, int* err_flag, void* stream) {
   PV_REQUIRE(plane_rgba && w_bf16 && scale && shift && out && dst && mean_host && err_flag, "pv_conv1_fused: null argument");
   PV_REQUIRE(dst->cols >= kN && dst->cols % 8 == 0, "pv_conv1_fused: dst.cols=%d", dst->cols);
+  PV_REQUIRE(B > 0 && Hp >= kKH && Wp >= 5 && oh > 0 && ow > 0, "pv_conv1_fused: bad extent B=%d Hp=%d Wp=%d", B, Hp, Wp);
+  PV_REQUIRE(2 * (oh - 1) + kKH <= Hp && 2 * (ow - 1) + 5 <= Wp, "pv_conv1_fused: output %dx%d does not fit plane %dx%d", oh, ow, Hp, Wp);
+  PV_REQUIRE(Wp % 4 == 0, "pv_conv1_fused: plane width %d must be a multiple of 4 pixels (16-byte TMA row pitch)", Wp);
+  PV_REQUIRE((reinterpret_cast<uintptr_t>(plane_rgba) & 15) == 0, "pv_conv1_fused: plane must be 16-byte aligned");
+  static EncodeTiledFn encode = nullptr;
+  static int num_sms = 0;
+  static int swap_ls = 0;
+  if (!encode) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PV_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres));
+    PV_REQUIRE(qres == cudaDriverEntryPointSuccess && fp, "pv_conv1_fused: cuTensorMapEncodeTiled unavailable");
+    int dev = 0;
+    PV_CUDA_CHECK(cudaGetDevice(&dev));
+    PV_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    PV_CUDA_CHECK(cudaFuncSetAttribute(conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    const char* e = getenv("PV_C1_SWAP");
+    swap_ls = (e && e[0] == '1') ? 1 : 0;
+    encode = reinterpret_cast<EncodeTiledFn>(fp);
+  }
   C1Params p;
-  p.plane = static_cast<const uchar4*>(plane_rgba);
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)Wp, (cuuint64_t)B * (cuuint64_t)Hp};
+    cuuint64_t gstride[1] = {(cuuint64_t)Wp * 4};
+    cuuint32_t box[2] = {kRawW, kKH};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&p.raw, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(plane_rgba), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      pv_set_error("pv_conv1_fused: cuTensorMapEncodeTiled failed (CUresult %d, Wp=%d rows=%lld)", (int)r, Wp, (long long)B * Hp);
+      return PV_ERR_CUDA;
+    }
+  }
   p.B = B;
   p.Hp = Hp;
   p.Wp = Wp;
-  p.hq = (Hp + 1) / 2;
-  p.wq = (Wp + 1) / 2;
   p.oh = oh;
   p.ow = ow;
+  p.tiles_per_row = (ow + kTileOut - 1) / kTileOut;
   p.w = static_cast<const __nv_bfloat16*>(w_bf16);
   p.scale = scale;
   p.shift = shift;
   p.relu = relu;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.dst = *dst;
-  p.m0 = mean_host[0];
-  p.m1 = mean_host[1];
-  p.m2 = mean_host[2];
-  p.q_rows = (long long)B * p.hq * p.wq;
-  PV_REQUIRE(p.q_rows < (1ll << 31), "pv_conv1_fused: too many rows");
-  p.num_tiles = (int)((p.q_rows + kTileM - 1) / kTileM);
+  p.c0 = -mean_host[0] * 0.00390625f;
+  p.c1 = -mean_host[1] * 0.00390625f;
+  p.c2 = -mean_host[2] * 0.00390625f;
+  const long long nt = (long long)B * oh * p.tiles_per_row;
+  PV_REQUIRE(nt < (1ll << 31), "pv_conv1_fused: too many tiles");
+  p.num_tiles = (int)nt;
+  p.swap_ls = swap_ls;
   p.err = err_flag;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    PV_CUDA_CHECK(cudaGetDevice(&dev));
-    PV_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    PV_CUDA_CHECK(cudaFuncSetAttribute(conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  }
   int grid = num_sms * 2;
   if (grid > p.num_tiles) grid = p.num_tiles;
   conv1_fused_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);

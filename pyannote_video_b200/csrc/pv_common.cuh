@@ -112,6 +112,23 @@ __device__ __forceinline__ void pv_mbar_wait(uint64_t* bar, uint32_t parity, int
   }
 }
 
+// Same, for roles that are not on the critical path (deep rings ahead of them): sleep between polls so
+// the spin loop does not compete for issue slots with the warps doing the work.
+__device__ __forceinline__ void pv_mbar_wait_backoff(uint64_t* bar, uint32_t parity, int* err_flag, int code,
+                                                     unsigned ns) {
+  if (pv_mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  unsigned polls = 0;
+  while (!pv_mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if ((++polls & 63u) == 0u && clock64() - t0 > 4000000000LL) {
+      if (err_flag) atomicExch(err_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
 // ---- TMA ---------------------------------------------------------------------
 __device__ __forceinline__ void pv_tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

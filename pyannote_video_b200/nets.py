@@ -151,9 +151,7 @@ class FusedConv1:
     def __init__(self, plane, Hp, Wp, conv, out, lout, device):
         w = _t(conv["w"]).float()                                  # [16, 3, 5, 5]
         assert tuple(w.shape) == (16, 3, 5, 5)
-        wk = torch.zeros(5, 16, 16)
-        wk[:, :, :15] = w.permute(2, 0, 3, 1).reshape(5, 16, 15)   # [kh][n][kw*3 + c]
-        self.w = wk.to(torch.bfloat16).contiguous().to(device)
+        self.w = w.to(torch.bfloat16).contiguous().to(device)     # the kernel lays out its own MMA operands
         sc, sh = _affine(conv)
         self.scale, self.shift = sc.float().contiguous().to(device), sh.float().contiguous().to(device)
         self.plane, self.Hp, self.Wp, self.out, self.lout = plane, Hp, Wp, out, lout

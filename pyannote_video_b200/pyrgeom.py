@@ -54,7 +54,7 @@ class PyramidGeometry:
                 x_cursor += w + PYR_PAD
         self.rects = rects                                    # (x0, y0, w, h) per level
         self.plane_w = x_cursor - PYR_PAD + PYR_OUTER_PAD
-        self.plane_w += self.plane_w & 1          # even width: the first conv reads pixel PAIRS in place
+        self.plane_w = (self.plane_w + 3) & ~3    # 16-byte row pitch: the first conv reads raw pixel rows by TMA
         self.plane_h = col_h + 2 * PYR_OUTER_PAD
         # ---- float32 factors mapping level-local coordinates to original-image coordinates ----
         f32 = np.float32

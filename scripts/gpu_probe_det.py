@@ -1,0 +1,71 @@
+"""GPU probe: per-layer times of the CNN detector on 1080p frames (CUDA events around every launch
+group), for one first-conv mode (env PV_DET_CONV1).  With --once it runs a single forward so that
+an ncu capture of one kernel stays cheap.  Usage: python scripts/gpu_probe_det.py [--frames 8] [--once]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+
+from pyannote_video_b200 import config, weights
+from pyannote_video_b200.nets import DetectorNet
+from pyannote_video_b200.synth import make_frames
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--once", action="store_true")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    B = args.frames
+    det = DetectorNet(weights.make_detector(), 1080, 1920, 1, B, dev)
+    frames = make_frames(B, 1080, 1920, seed=1, device=dev)
+    det.detect(frames)
+    det.check()
+    if args.once:
+        torch.cuda.synchronize()
+        return
+    names = ["conv%d" % (i + 1) for i in range(len(det.convs))]
+    acc = {n: 0.0 for n in names}
+    acc["pyramid"] = 0.0
+    acc["forward_scores"] = 0.0
+    for r in range(args.reps):
+        evs = []
+        for (op, img), n in zip(det.convs, names):
+            def timed(q_rows=None, _run=op.run, _n=n):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _run(q_rows)
+                b.record()
+                evs.append((_n, a, b))
+            op._saved_run = op.run
+            op.run = timed
+        a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a0.record()
+        det.build_plane(frames, B)
+        a1.record()
+        det.forward_scores(B)
+        a2.record()
+        torch.cuda.synchronize()
+        for (op, img) in det.convs:
+            op.run = op._saved_run
+        for n, a, b in evs:
+            acc[n] += a.elapsed_time(b)
+        acc["pyramid"] += a0.elapsed_time(a1)
+        acc["forward_scores"] += a1.elapsed_time(a2)
+    out = {k: round(v / args.reps * 1000.0, 1) for k, v in acc.items()}
+    out["mode"] = det.conv1_mode
+    out["frames"] = B
+    out["unit"] = "us"
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
