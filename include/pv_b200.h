@@ -130,6 +130,42 @@ int pv_srgemm_info(void* handle, int* n_ring, int* slot_bytes, int* resident, in
 int pv_srgemm_check(void* handle, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * detconv: the detector's conv layers 2..7 as 2-D tiled implicit GEMMs (csrc/detconv.cu) — the `con`
+ * layers of dlib's MMOD CNN behind face_detector_(rgb, 1), pyannote/video/face/face.py:66.
+ *
+ *   out[b, oy, ox, n] = act( scale[n] * sum_{kh,kw,c} x[b, oy*s + kh - pad_y, ox*s + kw - pad_x, c] * w[n,c,kh,kw] + shift[n] )
+ *
+ * x is a plain NHWC bf16 tensor [B, H, pitch, c_in] (pitch >= W, even; columns W..pitch-1 must be zero),
+ * zero padding comes from TMA out-of-bounds fill (stride 1: pad = k/2, stride 2: pad 0 — dlib's con_
+ * defaults).  One tile = 8 x 16 output pixels = one 128 x N TMEM accumulator; the input patch is loaded
+ * once per tile by a 4-D TMA box and every tap's A operand is a UMMA descriptor into that patch.
+ * Compiled instances (c_in, n_out, kh, kw, stride, out_f32): (16,32,5,5,2,0) (32,32,5,5,2,0) (32,48,5,5,1,0)
+ * (48,48,5,5,1,0) (48,16,9,1,1,1).
+ * w_img: device image of the weights exactly as they sit in shared memory — for tap t = kh*KW+kw and
+ * 16-channel chunk j an N x 16 tile at byte (t*(c_in/16)+j)*N*32, element (n,k) at
+ * (k>>3)*(N*16) + (n>>3)*128 + (n&7)*16 + (k&7)*2   (un-swizzled K-major core matrices).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct PvDetconvDesc {
+  const void* x;         /* bf16 [B, H, pitch, c_in]                                            */
+  int32_t B, H, W, pitch;
+  int32_t c_in, n_out, kh, kw, stride, out_f32;
+  const void* w_img;
+  int64_t w_bytes;       /* kh*kw*(c_in/16)*n_out*32                                            */
+  const float* scale;    /* [n_out] */
+  const float* shift;    /* [n_out] */
+  int32_t relu;
+  void* out;             /* bf16 (or f32 when out_f32) [B, OH, out_pitch, out_cs]               */
+  int32_t out_pitch, out_cs;
+} PvDetconvDesc;
+
+int pv_detconv_create(const PvDetconvDesc* desc, void** out_handle);
+int pv_detconv_run(void* handle, int B, void* stream);     /* first B images (B <= desc->B)      */
+int pv_detconv_destroy(void* handle);
+int pv_detconv_info(void* handle, int* n_stages, int* smem_bytes, int* tiles_x, int* tiles_y);
+/* reads (and clears) the device-side error flag; 0 = none. Synchronises the stream. */
+int pv_detconv_check(void* handle, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * first-layer packing and the small layers of the embedder (csrc/layers.cu)
  * ------------------------------------------------------------------------------------------ */
 /* RGBA u8 [B,H,W,4] (A==0: pyramid padding) -> "gathered" bf16 rows for a kw x kw stride-2 first conv:
@@ -176,6 +212,10 @@ int pv_pyramid_tail(void* plane_rgba, int64_t img_stride_px, int pitch_px, int B
  * score[n,y,x] = bias + sum_kw D[(n*Hq+y)*Wq + x+kw][kw] re-assembles it (D fp32 [rows, cols]) */
 int pv_det_shift_sum(const float* D, int B, int Hq, int Wq, int cols, int OH, int OW, int KW, float bias, float* scores,
                      void* stream);
+/* same re-assembly over the un-padded NHWC partials of detconv: P fp32 [B, H, pitch, cols] computed at the
+ * un-padded positions; score[n,y,x] = bias + sum_kw P[n, y, x+kw-KW/2][kw], out-of-range columns contribute 0 */
+int pv_det_shift_sum_nhwc(const float* P, int B, int H, int W, int pitch, int cols, int KW, float bias, float* scores,
+                          void* stream);
 /* cells of the score map above `thr` -> per-frame candidate lists (counts are zeroed first) */
 int pv_det_candidates(const float* scores, int B, int cells, float thr, int* counts, float* cand_score, int* cand_cell,
                       int cap, void* stream);

@@ -79,6 +79,22 @@ class PvSrgemmDesc(C.Structure):
     ]
 
 
+class PvDetconvDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("pitch", C.c_int32),
+        ("c_in", C.c_int32), ("n_out", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+        ("stride", C.c_int32), ("out_f32", C.c_int32),
+        ("w_img", C.c_void_p),
+        ("w_bytes", C.c_int64),
+        ("scale", C.c_void_p),
+        ("shift", C.c_void_p),
+        ("relu", C.c_int32),
+        ("out", C.c_void_p),
+        ("out_pitch", C.c_int32), ("out_cs", C.c_int32),
+    ]
+
+
 _lib = None
 
 

@@ -17,3 +17,9 @@ SRGEMM_GROUP = "row"   # validated on B200 (gpurun #1): descriptors at arbitrary
 #   "pixrows"  pack kernel writes a bf16 RGBX plane (8 B/pixel), srgemm reads 8-pixel runs through an
 #              overlapping-row tensor map (row stride 16 B): slower than "gathered" (L2-bound re-reads)
 DET_CONV1 = os.environ.get("PV_DET_CONV1", "fused")
+
+# detector conv layers 2..7:
+#   "detconv"  csrc/detconv.cu: 2-D tiles (8 x 16 outputs), one 4-D TMA patch per tile, every tap's A operand is a
+#              UMMA descriptor into the patch (1.9 input pixels read per output), compile-time MMA sequence  [default]
+#   "srgemm"   the generic 1-D shifted-row GEMM (5.3 input rows read per output, table-driven issue loop)
+DET_CONVS = os.environ.get("PV_DET_CONVS", "detconv")

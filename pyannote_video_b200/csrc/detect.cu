@@ -143,6 +143,23 @@ __global__ void det_shift_sum_kernel(const float* __restrict__ D, int B, int Hq,
   scores[idx] = s;
 }
 
+// un-padded NHWC partials (detconv): out-of-range columns are the conv's zero padding
+__global__ void det_shift_sum_nhwc_kernel(const float* __restrict__ P, int B, int H, int W, int pitch, int cols, int KW,
+                                          float bias, float* __restrict__ scores) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W) return;
+  const int x = (int)(idx % W);
+  const long long r = idx / W;   // n*H + y
+  const float* row = P + r * pitch * cols;
+  float s = bias;
+  const int half = KW / 2;
+  for (int kw = 0; kw < KW; ++kw) {
+    const int xx = x + kw - half;
+    if (xx >= 0 && xx < W) s += row[(long long)xx * cols + kw];
+  }
+  scores[idx] = s;
+}
+
 // ---- candidates -----------------------------------------------------------------------------
 __global__ void det_candidates_kernel(const float* __restrict__ scores, int B, int cells, float thr,
                                       int* __restrict__ counts, float* __restrict__ cand_score,
@@ -343,6 +360,19 @@ extern "C" int pv_det_shift_sum(const float* D, int B, int Hq, int Wq, int cols,
   const int threads = 256;
   det_shift_sum_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       D, B, Hq, Wq, cols, OH, OW, KW, bias, scores);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_det_shift_sum_nhwc(const float* P, int B, int H, int W, int pitch, int cols, int KW, float bias,
+                                     float* scores, void* stream) {
+  PV_REQUIRE(P && scores, "pv_det_shift_sum_nhwc: null argument");
+  PV_REQUIRE(KW <= cols && pitch >= W && B > 0 && H > 0 && W > 0, "pv_det_shift_sum_nhwc: geometry");
+  const long long total = (long long)B * H * W;
+  const int threads = 256;
+  det_shift_sum_nhwc_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      P, B, H, W, pitch, cols, KW, bias, scores);
   g_pv_launches.fetch_add(1);
   PV_CUDA_CHECK(cudaGetLastError());
   return PV_OK;

@@ -1,0 +1,115 @@
+"""Host side of csrc/detconv.cu: the detector's conv layers 2..7 as 2-D tiled implicit GEMMs.
+
+Activations are plain NHWC bf16 tensors [B, H, pitch, C] (pitch = W rounded up to even; the extra
+column stays zero), weights are packed on the host into the exact shared-memory image the kernel's
+UMMA descriptors read (include/pv_b200.h, PvDetconvDesc).  Replaces the `con` layers of dlib's MMOD
+CNN behind face_detector_(rgb, 1), pyannote/video/face/face.py:66.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+INSTANCES = {  # (c_in, n_out, kh, kw, stride, out_f32)
+    (16, 32, 5, 5, 2, 0), (32, 32, 5, 5, 2, 0), (32, 48, 5, 5, 1, 0), (48, 48, 5, 5, 1, 0), (48, 16, 9, 1, 1, 1)}
+
+
+def even(n):
+    return (n + 1) // 2 * 2
+
+
+def pack_weight_image(w, c_in, n_out):
+    """w float [Cout, Cin, KH, KW] -> uint8 image: for tap t = kh*KW+kw and 16-channel chunk j an
+    n_out x 16 bf16 tile at byte (t*(c_in/16)+j)*n_out*32, element (n,k) at
+    (k>>3)*(n_out*16) + (n>>3)*128 + (n&7)*16 + (k&7)*2."""
+    w = torch.as_tensor(w).float()
+    Cout, Cin, KH, KW = w.shape
+    assert Cout <= n_out and Cin <= c_in and c_in % 16 == 0 and n_out % 16 == 0
+    kch = c_in // 16
+    full = torch.zeros(KH, KW, kch, n_out, 16)
+    wp = torch.zeros(n_out, c_in, KH, KW)
+    wp[:Cout, :Cin] = w
+    full[:] = wp.permute(2, 3, 1, 0).reshape(KH, KW, kch, 16, n_out).permute(0, 1, 2, 4, 3)   # [kh,kw,j,n,k]
+    # tile layout: [k>>3][n>>3][n&7][k&7]
+    t = full.reshape(KH * KW * kch, n_out // 8, 8, 2, 8).permute(0, 3, 1, 2, 4).contiguous()
+    img = t.to(torch.bfloat16).view(torch.uint8).reshape(-1)
+    assert img.numel() == KH * KW * kch * n_out * 32
+    return img
+
+
+def unpack_weight_image(img, c_in, n_out, KH, KW):
+    """inverse of pack_weight_image (element-address formula written out; used by the CPU test)."""
+    kch = c_in // 16
+    v = img.view(torch.bfloat16).float().numpy()
+    out = np.zeros((n_out, c_in, KH, KW), np.float32)
+    for t in range(KH * KW):
+        for j in range(kch):
+            base = (t * kch + j) * n_out * 32
+            for n in range(n_out):
+                for k in range(16):
+                    off = base + (k >> 3) * (n_out * 16) + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2
+                    out[n, j * 16 + k, t // KW, t % KW] = v[off // 2]
+    return out
+
+
+class DetConv:
+    """One bound conv layer: x [Bmax,H,pitch,c_in] bf16 -> out [Bmax,OH,out_pitch,out_cs] (bf16, or f32
+    when out_f32).  Same `run(B)` / `check()` protocol as plan.Srgemm."""
+
+    def __init__(self, x, H, W, weight, stride, scale, shift, relu, c_in, n_out, out_f32=False, out_cs=None):
+        dev = x.device
+        Cout, Cin, KH, KW = weight.shape
+        key = (c_in, n_out, KH, KW, stride, int(out_f32))
+        if key not in INSTANCES:
+            raise _lib.PvError("detconv: no kernel instance for %r" % (key,))
+        B, Hx, pitch, Cx = x.shape
+        assert x.dtype == torch.bfloat16 and x.is_contiguous() and (Hx, Cx) == (H, c_in) and pitch == even(W)
+        pad_y, pad_x = (KH // 2, KW // 2) if stride == 1 else (0, 0)
+        self.OH = (H + 2 * pad_y - KH) // stride + 1
+        self.OW = (W + 2 * pad_x - KW) // stride + 1
+        self.out_pitch = even(self.OW)
+        self.out_cs = out_cs or n_out
+        self.out = torch.zeros(B, self.OH, self.out_pitch, self.out_cs, dtype=torch.float32 if out_f32 else torch.bfloat16,
+                               device=dev)
+        self.w_img = pack_weight_image(weight, c_in, n_out).to(dev)
+        sc = torch.zeros(n_out, dtype=torch.float32)
+        sh = torch.zeros(n_out, dtype=torch.float32)
+        sc[:Cout] = torch.as_tensor(scale).float()
+        sh[:Cout] = torch.as_tensor(shift).float()
+        self.scale, self.shift = sc.to(dev), sh.to(dev)
+        self.x = x
+        self.Bmax = B
+        d = _lib.PvDetconvDesc()
+        d.x = x.data_ptr()
+        d.B, d.H, d.W, d.pitch = B, H, W, pitch
+        d.c_in, d.n_out, d.kh, d.kw, d.stride, d.out_f32 = c_in, n_out, KH, KW, stride, int(out_f32)
+        d.w_img, d.w_bytes = self.w_img.data_ptr(), self.w_img.numel()
+        d.scale, d.shift = self.scale.data_ptr(), self.shift.data_ptr()
+        d.relu = int(relu)
+        d.out = self.out.data_ptr()
+        d.out_pitch, d.out_cs = self.out_pitch, self.out_cs
+        h = C.c_void_p()
+        _lib.check(_lib.lib().pv_detconv_create(C.byref(d), C.byref(h)), "pv_detconv_create")
+        self.h = h
+        self.flops_per_image = 2 * self.OH * self.OW * Cout * Cin * KH * KW
+
+    def info(self):
+        a, b, c, e = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.check(_lib.lib().pv_detconv_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(e)), "pv_detconv_info")
+        return dict(n_stages=a.value, smem_bytes=b.value, tiles_x=c.value, tiles_y=e.value)
+
+    def run(self, B=None):
+        _lib.check(_lib.lib().pv_detconv_run(self.h, int(B or self.Bmax), _lib.stream_ptr()), "pv_detconv_run")
+
+    def check(self):
+        _lib.check(_lib.lib().pv_detconv_check(self.h, _lib.stream_ptr()), "pv_detconv_check")
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.lib().pv_detconv_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

@@ -18,6 +18,7 @@ import torch
 from . import _lib, config
 from . import weights as W
 from .plan import ConvPlan, RowLayout, Srgemm
+from .detconv import DetConv, even
 from .pyrgeom import pyramid_geometry, det_cell_to_plane
 
 
@@ -181,7 +182,7 @@ class DetectorNet:
     MAX_DET = 256
     TAIL_PIXELS = 250000      # pyramid levels at most this large are built by the one-launch tail kernel
 
-    def __init__(self, model, H, W_, upsample, max_batch, device, group=None, conv1_mode=None):
+    def __init__(self, model, H, W_, upsample, max_batch, device, group=None, conv1_mode=None, conv_impl=None):
         if model.get("kind") != "mmod_detector":
             raise RuntimeError("DetectorNet: not a detector model")
         group = config.SRGEMM_GROUP if group is None else group
@@ -192,6 +193,67 @@ class DetectorNet:
         Hp, Wp = geo.plane_h, geo.plane_w
         self.plane = torch.zeros(B, Hp, Wp, 4, dtype=torch.uint8, device=device)
         self.conv1_mode = config.DET_CONV1 if conv1_mode is None else conv1_mode
+        self.conv_impl = config.DET_CONVS if conv_impl is None else conv_impl
+        if self.conv_impl == "detconv":
+            self._init_detconv(model, device)
+        else:
+            self._init_srgemm(model, device, group)
+        self._init_tail(model, device)
+
+    def _init_detconv(self, model, device):
+        """layers 2..7 on csrc/detconv.cu: plain NHWC activations [B, H, even(W), C], no padding in HBM"""
+        B, geo = self.B, self.geo
+        Hp, Wp = geo.plane_h, geo.plane_w
+        convs = model["convs"]
+        self.convs = []
+        self.flops_per_frame = 0
+        # conv1 (5x5 s2, RGB -> 16) writes straight into the NHWC tensor through a row map
+        cout, cin, k, s = W.DET_CONVS[0]
+        OH1, OW1 = (Hp - k) // s + 1, (Wp - k) // s + 1
+        l1 = RowLayout("padded", B, OH1, even(OW1), 16, pad=0)
+        a1 = l1.alloc(device)
+        if self.conv1_mode == "fused":
+            self.lg, self.xg = None, None
+            op = FusedConv1(self.plane, Hp, Wp, convs[0], a1, l1, device)
+            img1 = op.img
+        else:
+            lg = RowLayout(self.conv1_mode, B, Hp, Wp, 3, kw=5)
+            self.lg, self.xg = lg, lg.alloc(device)
+            cp = ConvPlan(lg, _t(convs[0]["w"]), s, 0, group=config.SRGEMM_GROUP)
+            sc, sh = _affine(convs[0])
+            op = Srgemm(cp, self.xg, a1, l1, sc, sh, relu=True)
+            img1 = lg.img
+        self.convs.append((op, img1))
+        self.flops_per_frame += 2 * OH1 * OW1 * cout * cin * k * k
+        x, h, w = a1.view(B, OH1, even(OW1), 16), OH1, OW1
+        n = len(convs)
+        for i in range(1, n):
+            cout, cin, k, s = W.DET_CONVS[i]
+            c = convs[i]
+            last = i == n - 1
+            c_in = x.shape[3]
+            if last:
+                # 9x9, one output channel: the 9 filter columns become 9 output channels of a 9x1 conv;
+                # pv_det_shift_sum_nhwc adds the kw-shifted channels back together.
+                wt = _t(c["w"]).float()                                   # [1, cin, 9, 9]
+                w9 = wt[0].permute(2, 0, 1).unsqueeze(-1).contiguous()    # [kw, cin, kh, 1]
+                op = DetConv(x, h, w, w9, 1, torch.ones(k), torch.zeros(k), False, c_in, 16, out_f32=True)
+                self.partial = op.out
+                self.OH, self.OW = op.OH, w
+                self.scores = torch.zeros(B, self.OH, self.OW, dtype=torch.float32, device=device)
+                self.score_bias = float(_affine(c, affine=False)[1][0])
+                self.flops_per_frame += 2 * self.OH * self.OW * cout * cin * k * k
+            else:
+                sc, sh = _affine(c)
+                n_out = (cout + 15) // 16 * 16
+                op = DetConv(x, h, w, _t(c["w"]), s, sc, sh, True, c_in, n_out)
+                self.flops_per_frame += 2 * op.OH * op.OW * cout * cin * k * k
+                x, h, w = op.out, op.OH, op.OW
+            self.convs.append((op, 1))
+
+    def _init_srgemm(self, model, device, group):
+        B, geo = self.B, self.geo
+        Hp, Wp = geo.plane_h, geo.plane_w
         lg = RowLayout("gathered" if self.conv1_mode == "fused" else self.conv1_mode, B, Hp, Wp, 3, kw=5)
         self.lg = lg
         self.xg = lg.alloc(device) if self.conv1_mode != "fused" else None
@@ -247,6 +309,9 @@ class DetectorNet:
             self.flops_per_frame += 2 * (self.OH * self.OW if last else cp.OH * cp.OW) * cout * cin * k * k
             if not last:
                 lcur, cur = lo, o
+
+    def _init_tail(self, model, device):
+        B, geo = self.B, self.geo
         # pyramid: big levels one launch each, the small tail (<= TAIL_PIXELS per level) in one launch
         f32 = np.float32
         tail_from = next((i for i, (w, h) in enumerate(geo.sizes) if i >= 1 and w * h <= self.TAIL_PIXELS), geo.n_levels)
@@ -318,6 +383,11 @@ class DetectorNet:
                                           C.c_int64(self.lg.plane_rows), _mean3(), st), "pv_pack_gathered")
         for op, img in self.convs:
             op.run(M * img)
+        if self.conv_impl == "detconv":
+            _lib.check(L.pv_det_shift_sum_nhwc(_lib.ptr(self.partial), M, self.OH, self.OW, self.partial.shape[2], 16, 9,
+                                               C.c_float(self.score_bias), _lib.ptr(self.scores), st),
+                       "pv_det_shift_sum_nhwc")
+            return self.scores[:M]
         lp = self.lpart
         _lib.check(L.pv_det_shift_sum(_lib.ptr(self.partial), M, lp.Hq, lp.Wq, 16, self.OH, self.OW, 9,
                                       C.c_float(self.score_bias), _lib.ptr(self.scores), st), "pv_det_shift_sum")

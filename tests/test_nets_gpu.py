@@ -50,15 +50,18 @@ def test_embed_net_matches_oracle(cuda):
     assert torch.equal(out2, out[:2])
 
 
-@pytest.mark.parametrize("upsample,conv1_mode", [(0, "gathered"), (1, "gathered"), (1, "pixrows"), (0, "pixrows"), (1, "fused"), (0, "fused")])
-def test_detector_matches_oracle(cuda, upsample, conv1_mode):
+@pytest.mark.parametrize("upsample,conv1_mode,conv_impl", [
+    (1, "fused", "detconv"), (0, "fused", "detconv"), (1, "gathered", "detconv"),
+    (0, "gathered", "srgemm"), (1, "gathered", "srgemm"), (1, "pixrows", "srgemm"), (0, "pixrows", "srgemm"),
+    (1, "fused", "srgemm"), (0, "fused", "srgemm")])
+def test_detector_matches_oracle(cuda, upsample, conv1_mode, conv_impl):
     from oracle import nets as onets
     from oracle import pyramid as opyr
     from pyannote_video_b200.nets import DetectorNet
     H, Wd = 120, 168
     model = W.make_detector(seed=2, score_bias=0.0)
     frames = make_frames(2, H, Wd, seed=4)
-    net = DetectorNet(model, H, Wd, upsample, max_batch=2, device=cuda, conv1_mode=conv1_mode)
+    net = DetectorNet(model, H, Wd, upsample, max_batch=2, device=cuda, conv1_mode=conv1_mode, conv_impl=conv_impl)
     fd = frames.to(cuda)
     net.build_plane(fd, 2)
     plane = net.plane[:2].cpu().numpy()

@@ -142,3 +142,16 @@ def test_stride2_first_layer_read_in_place():
     emulate(cp, lin.to_rows(x), out, lout, torch.ones(cout), torch.zeros(cout), relu=False)
     ref = F.conv2d(x.permute(0, 3, 1, 2), w, stride=2).permute(0, 2, 3, 1)
     assert torch.allclose(lout.from_rows(out, C=cout), ref, atol=3e-2, rtol=3e-2)
+
+
+def test_detconv_weight_image_roundtrip():
+    """the shared-memory weight image of csrc/detconv.cu: pack (vectorised) == element-address formula"""
+    from pyannote_video_b200.detconv import pack_weight_image, unpack_weight_image
+    w = torch.randn(45, 45, 5, 5).to(torch.bfloat16).float()
+    img = pack_weight_image(w, 48, 48)
+    assert img.numel() == 25 * 3 * 48 * 32
+    u = unpack_weight_image(img, 48, 48, 5, 5)
+    assert (u[:45, :45] == w.numpy()).all() and (u[45:] == 0).all() and (u[:, 45:] == 0).all()
+    w9 = torch.randn(9, 45, 9, 1).to(torch.bfloat16).float()
+    u9 = unpack_weight_image(pack_weight_image(w9, 48, 16), 48, 16, 9, 1)
+    assert (u9[:9, :45] == w9.numpy()).all()
