@@ -14,9 +14,11 @@
 //   MMA j = 0..4 : chunks 0,1 of filter row j               (LBO = 16 B)
 //   MMA 5, 6     : chunk 2 of filter rows (0,1) and (2,3)   (LBO = one buffer row)
 //   MMA 7        : chunk 2 of filter row 4 (+ a zero-weight chunk)
-// A tile is 126 consecutive outputs of ONE output row (2*125 + 5 = 255 input pixels fit one 256-pixel
-// TMA box; rows 126/127 of the MMA are padding), so TMA's out-of-bounds zero fill is the plane's zero
-// padding and tile coordinates advance without divisions.
+// A tile is 126 consecutive outputs of FOUR consecutive output rows (2*125 + 5 = 255 input pixels fit one
+// 256-pixel TMA box; rows 126/127 of each MMA are padding; 2*4 + 3 = 11 input rows).  Four rows per tile
+// mean every input pixel is fetched and converted 11/8 = 1.4 times instead of 2.5 times, and the per-tile
+// hand-offs (two mbarrier waits, one fence.proxy.async per converter warp) are paid once per 504 outputs.
+// TMA's out-of-bounds zero fill is the plane's zero padding; tile coordinates advance without divisions.
 #include <cuda.h>
 #include <atomic>
 #include <cstdlib>
@@ -31,24 +33,27 @@ constexpr int kTileM = 128;
 constexpr int kTileOut = 126;                     // valid outputs per tile
 constexpr int kKH = 5;
 constexpr int kN = 16;
+constexpr int kRows = 4;                          // output rows per tile
+constexpr int kInRows = 2 * kRows + 3;            // 11 input rows
 constexpr int kRawW = 256;                        // pixels per raw row (TMA box)
-constexpr int kRawBytes = kKH * kRawW * 4;        // 5 KB
-constexpr int kRawRing = 6;
+constexpr int kRawBytes = kInRows * kRawW * 4;    // 11 KB
+constexpr int kRawRing = 3;
 constexpr int kPxRowBytes = (kRawW + 8) * 8;      // 264 pixels x 8 B; the 8 trailing pixels stay zero
-constexpr int kPxSlotBytes = 10752;               // 5 rows (10560 B) rounded up to 128
-constexpr int kPxRing = 4;
-constexpr int kAcc = 2;
-constexpr int kNumMma = 8;
+constexpr int kPxSlotBytes = 23296;               // 11 rows (23232 B) rounded up to 128
+constexpr int kPxRing = 2;
+constexpr int kAcc = 2;                           // tiles in flight in TMEM (kRows accumulators each)
+constexpr int kNumMma = 8;                        // per output row
 constexpr int kWBytes = kNumMma * 512;            // 8 B operands of 16 x 16 bf16
 constexpr int kConvWarps = 8;
 // warps: 0 = TMA, 1 = MMA, 2..9 = converters, 10..13 = epilogue
 constexpr int kThreads = 32 * (2 + kConvWarps + 4);
-static_assert(kPxSlotBytes >= kKH * kPxRowBytes, "slot too small");
+static_assert(kPxSlotBytes >= kInRows * kPxRowBytes, "slot too small");
 
 struct C1Params {
-  CUtensorMap raw;       // uint32 [B*Hp rows, Wp cols], box 256 x 5
+  CUtensorMap raw;       // uint32 [B*Hp rows, Wp cols], box 256 x 11
   int B, Hp, Wp;
   int oh, ow;            // valid output extent
+  int oh_tiles;          // ceil(oh / kRows)
   int tiles_per_row;
   const __nv_bfloat16* w;  // [16][3][5][5]
   const float* scale;
@@ -69,12 +74,12 @@ __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint3
   return (long long)plane * m.plane_rows + (long long)n * m.img + (long long)(Y >> 1) * m.w + (X >> 1);
 }
 
-// tile -> (image, output row, first output column), advanced by gridDim.x tiles without divisions
+// tile -> (image, tile row (kRows output rows), first output column), advanced by gridDim.x tiles without divisions
 struct TileWalk {
   uint32_t n, oy, ct;
   uint32_t step_n, step_oy, step_ct;
   __device__ __forceinline__ void init(const C1Params& p, uint32_t tile, uint32_t step) {
-    const uint32_t tpr = (uint32_t)p.tiles_per_row, oh = (uint32_t)p.oh;
+    const uint32_t tpr = (uint32_t)p.tiles_per_row, oh = (uint32_t)p.oh_tiles;
     uint32_t r = tile / tpr;
     ct = tile - r * tpr;
     n = r / oh;
@@ -89,7 +94,7 @@ struct TileWalk {
     oy += step_oy;
     n += step_n;
     if (ct >= (uint32_t)p.tiles_per_row) { ct -= (uint32_t)p.tiles_per_row; ++oy; }
-    if (oy >= (uint32_t)p.oh) { oy -= (uint32_t)p.oh; ++n; }
+    if (oy >= (uint32_t)p.oh_tiles) { oy -= (uint32_t)p.oh_tiles; ++n; }
   }
 };
 
@@ -141,8 +146,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
     *reinterpret_cast<__nv_bfloat16*>(wsm + j * 512 + (k >> 3) * 256 + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = v;
   }
   // trailing 8 pixels of every buffer row: read by the padding rows of the MMA, must be finite
-  for (int i = threadIdx.x; i < kPxRing * kKH * 8; i += kThreads) {
-    const int s = i / (kKH * 8), rem = i - s * (kKH * 8);
+  for (int i = threadIdx.x; i < kPxRing * kInRows * 8; i += kThreads) {
+    const int s = i / (kInRows * 8), rem = i - s * (kInRows * 8);
     const int kh = rem >> 3, q = rem & 7;
     *reinterpret_cast<uint2*>(pxb + s * kPxSlotBytes + kh * kPxRowBytes + (kRawW + q) * 8) = make_uint2(0u, 0u);
   }
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
     pv_fence_mbar_init();
   }
   pv_fence_proxy_async();                  // weights / zero pads written through the generic proxy, read by the tensor core
-  if (warp == 1) pv_tmem_alloc(s_tmem, 32);
+  if (warp == 1) pv_tmem_alloc(s_tmem, kAcc * kRows * kN);
   pv_tc_fence_before();
   __syncthreads();
   pv_tc_fence_after();
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
         pv_mbar_wait_backoff(&bar_rempty[rs], rphase ^ 1u, p.err, 1, 64);
         pv_mbar_arrive_expect_tx(&bar_rfull[rs], kRawBytes);
         pv_tma_load_2d(raw + rs * kRawBytes, &p.raw, &bar_rfull[rs], (int32_t)(2 * kTileOut * t.ct),
-                       (int32_t)(t.n * (uint32_t)p.Hp + 2 * t.oy));
+                       (int32_t)(t.n * (uint32_t)p.Hp + 2 * kRows * t.oy));
         if (++rs == kRawRing) { rs = 0; rphase ^= 1u; }
         t.next(p);
       }
@@ -206,13 +211,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
       pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
       pv_tc_fence_after();
       const uint32_t a0 = pv_smem_u32(pxb + slot * kPxSlotBytes);
-      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kN);
 #pragma unroll
-      for (int j = 0; j < kNumMma; ++j) {
-        const uint32_t addr = j < 5 ? a0 + j * kPxRowBytes : a0 + (j - 5) * 2 * kPxRowBytes + 32;
-        const uint32_t lbo = (j == 5 || j == 6) ? (uint32_t)kPxRowBytes : 16u;
-        const uint64_t ad = p.swap_ls ? desc_kmajor_plain(addr, a_sbo, lbo) : desc_kmajor_plain(addr, lbo, a_sbo);
-        pv_umma_bf16_pred(tmem_d, ad, bdesc[j], idesc, j > 0 ? 1u : 0u, lead);
+      for (int r = 0; r < kRows; ++r) {
+        const uint32_t tmem_d = tmem_base + (uint32_t)((buf * kRows + r) * kN);
+        const uint32_t ar = a0 + (uint32_t)(2 * r * kPxRowBytes);
+#pragma unroll
+        for (int j = 0; j < kNumMma; ++j) {
+          const uint32_t addr = j < 5 ? ar + j * kPxRowBytes : ar + (j - 5) * 2 * kPxRowBytes + 32;
+          const uint32_t lbo = (j == 5 || j == 6) ? (uint32_t)kPxRowBytes : 16u;
+          const uint64_t ad = p.swap_ls ? desc_kmajor_plain(addr, a_sbo, lbo) : desc_kmajor_plain(addr, lbo, a_sbo);
+          pv_umma_bf16_pred(tmem_d, ad, bdesc[j], idesc, j > 0 ? 1u : 0u, lead);
+        }
       }
       pv_umma_commit_pred(&bar_empty[slot], lead);
       pv_umma_commit_pred(&bar_tfull[buf], lead);
@@ -227,13 +236,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       pv_mbar_wait(&bar_rfull[rs], rphase, p.err, 5);
       const uint32_t* rb = reinterpret_cast<const uint32_t*>(raw + rs * kRawBytes) + ct;
-      uint32_t v[kKH];
+      uint32_t v[kInRows];
 #pragma unroll
-      for (int kh = 0; kh < kKH; ++kh) v[kh] = rb[kh * kRawW];
+      for (int kh = 0; kh < kInRows; ++kh) v[kh] = rb[kh * kRawW];
       pv_mbar_wait(&bar_empty[slot], phase ^ 1u, p.err, 6);
       uint8_t* dstp = pxb + slot * kPxSlotBytes + ct * 8;
 #pragma unroll
-      for (int kh = 0; kh < kKH; ++kh) {
+      for (int kh = 0; kh < kInRows; ++kh) {
         // (v - mean)/256 == fma(v, 2^-8, -mean*2^-8) bit for bit (power-of-two scaling commutes with rounding)
         const float r = fmaf((float)(v[kh] & 255u), 0.00390625f, p.c0);
         const float g = fmaf((float)((v[kh] >> 8) & 255u), 0.00390625f, p.c1);
@@ -263,35 +272,41 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const uint32_t x = t.ct * kTileOut + m;
-      const bool valid = (m < (uint32_t)kTileOut) && (x < (uint32_t)p.ow);
-      const long long drow = row_of(p.dst, t.n, t.oy, x);
+      const bool xvalid = (m < (uint32_t)kTileOut) && (x < (uint32_t)p.ow);
+      const uint32_t oy0 = t.oy * kRows;
       pv_mbar_wait_backoff(&bar_tfull[buf], aphase, p.err, 4, 32);
       pv_tc_fence_after();
-      uint32_t v[16];
-      pv_tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kN), v);
-      pv_tmem_ld_wait();
-      pv_tc_fence_before();
-      __syncwarp();
-      if (lane == 0) pv_mbar_arrive(&bar_tempty[buf]);   // accumulator is in registers: release it early
-      if (valid) {
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          f[j] = fmaf(__uint_as_float(v[j]), s_scale[j], s_shift[j]);
-          if (p.relu) f[j] = fmaxf(f[j], 0.f);
+#pragma unroll 1
+      for (int r = 0; r < kRows; ++r) {
+        uint32_t v[16];
+        pv_tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * kRows + r) * kN), v);
+        pv_tmem_ld_wait();
+        if (r == kRows - 1) {
+          pv_tc_fence_before();
+          __syncwarp();
+          if (lane == 0) pv_mbar_arrive(&bar_tempty[buf]);   // last accumulator is in registers: release the buffer
         }
-        uint4 o0, o1;
-        o0.x = pv_pack_bf16x2(f[0], f[1]);
-        o0.y = pv_pack_bf16x2(f[2], f[3]);
-        o0.z = pv_pack_bf16x2(f[4], f[5]);
-        o0.w = pv_pack_bf16x2(f[6], f[7]);
-        o1.x = pv_pack_bf16x2(f[8], f[9]);
-        o1.y = pv_pack_bf16x2(f[10], f[11]);
-        o1.z = pv_pack_bf16x2(f[12], f[13]);
-        o1.w = pv_pack_bf16x2(f[14], f[15]);
-        uint4* dp = reinterpret_cast<uint4*>(p.out + drow * p.dst.cols);
-        dp[0] = o0;
-        dp[1] = o1;
+        if (xvalid && oy0 + r < (uint32_t)p.oh) {
+          const long long drow = row_of(p.dst, t.n, oy0 + r, x);
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[j] = fmaf(__uint_as_float(v[j]), s_scale[j], s_shift[j]);
+            if (p.relu) f[j] = fmaxf(f[j], 0.f);
+          }
+          uint4 o0, o1;
+          o0.x = pv_pack_bf16x2(f[0], f[1]);
+          o0.y = pv_pack_bf16x2(f[2], f[3]);
+          o0.z = pv_pack_bf16x2(f[4], f[5]);
+          o0.w = pv_pack_bf16x2(f[6], f[7]);
+          o1.x = pv_pack_bf16x2(f[8], f[9]);
+          o1.y = pv_pack_bf16x2(f[10], f[11]);
+          o1.z = pv_pack_bf16x2(f[12], f[13]);
+          o1.w = pv_pack_bf16x2(f[14], f[15]);
+          uint4* dp = reinterpret_cast<uint4*>(p.out + drow * p.dst.cols);
+          dp[0] = o0;
+          dp[1] = o1;
+        }
       }
       if (++buf == kAcc) { buf = 0; aphase ^= 1u; }
       t.next(p);
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    pv_tmem_dealloc(tmem_base, 32);
+    pv_tmem_dealloc(tmem_base, kAcc * kRows * kN);
   }
 }
 
@@ -343,7 +358,7 @@ extern "C" int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, con
   {
     cuuint64_t gdim[2] = {(cuuint64_t)Wp, (cuuint64_t)B * (cuuint64_t)Hp};
     cuuint64_t gstride[1] = {(cuuint64_t)Wp * 4};
-    cuuint32_t box[2] = {kRawW, kKH};
+    cuuint32_t box[2] = {kRawW, kInRows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&p.raw, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(plane_rgba), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -368,7 +383,8 @@ extern "C" int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, con
   p.c0 = -mean_host[0] * 0.00390625f;
   p.c1 = -mean_host[1] * 0.00390625f;
   p.c2 = -mean_host[2] * 0.00390625f;
-  const long long nt = (long long)B * oh * p.tiles_per_row;
+  p.oh_tiles = (oh + kRows - 1) / kRows;
+  const long long nt = (long long)B * p.oh_tiles * p.tiles_per_row;
   PV_REQUIRE(nt < (1ll << 31), "pv_conv1_fused: too many tiles");
   p.num_tiles = (int)nt;
   p.swap_ls = swap_ls;

@@ -63,6 +63,115 @@ __device__ __forceinline__ uchar4 bilinear_px(const uint8_t* __restrict__ s, int
   return o;
 }
 
+// ---- column-walking resize (the big pyramid levels) -------------------------------------------------
+// Same arithmetic as bilinear_px, bit for bit, organised so that the conversion unit (I2F / F2I / FRND run at
+// a quarter of the FP32 rate and bounded the per-pixel kernel: ncu, profiles/README.md) is never used and the
+// horizontal interpolation of a source row is shared by the output rows that read it:
+//   * u8 -> f32 as (2^23 | b) - 2^23, floor(t) for 0 <= t < 2^22 as the mantissa of t (+) 2^23 rounded down;
+//   * a thread owns ONE output column (left/right/lr are constants) and walks kResizeRows output rows; the
+//     horizontally interpolated source rows h[top], h[bot] (3 floats each) are kept between rows.
+constexpr int kResizeRows = 16;
+constexpr int kResizeCols = 2;      // columns per thread, 256 apart (coalesced rows, shared row arithmetic)
+
+// byte `SEL` (0..2) of v as an exact float: prmt builds 0x4B0000vv = 2^23 + vv, minus 2^23
+template <int SEL>
+__device__ __forceinline__ float pv_u8f_sel(uint32_t v, uint32_t magic) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(magic), "n"(0x7540 | SEL));
+  return __fsub_rn(__uint_as_float(r), 8388608.0f);
+}
+__device__ __forceinline__ float pv_u8f(uint32_t b) { return __fsub_rn(__uint_as_float(0x4B000000u | b), 8388608.0f); }
+// floor of 0 <= t < 2^22, as float bits with the integer in the mantissa
+__device__ __forceinline__ uint32_t pv_floor_bits(float t) { return __float_as_uint(__fadd_rd(t, 8388608.0f)); }
+
+// horizontally interpolated source row: h[ch] = omlr * S[il][ch] + lr * S[ir][ch]  (il, ir: pixel indices in the image)
+template <int SRC_CH>
+__device__ __forceinline__ void hrow(const uint8_t* __restrict__ s, uint32_t il, uint32_t ir, float lr, float omlr,
+                                     uint32_t magic, float (&h)[3]) {
+  if (SRC_CH == 4) {
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(s);
+    const uint32_t a = __ldg(s4 + il);
+    const uint32_t b = __ldg(s4 + ir);
+    h[0] = __fadd_rn(__fmul_rn(omlr, pv_u8f_sel<0>(a, magic)), __fmul_rn(lr, pv_u8f_sel<0>(b, magic)));
+    h[1] = __fadd_rn(__fmul_rn(omlr, pv_u8f_sel<1>(a, magic)), __fmul_rn(lr, pv_u8f_sel<1>(b, magic)));
+    h[2] = __fadd_rn(__fmul_rn(omlr, pv_u8f_sel<2>(a, magic)), __fmul_rn(lr, pv_u8f_sel<2>(b, magic)));
+  } else {
+    const uint8_t* pl = s + il * 3u;
+    const uint8_t* pr = s + ir * 3u;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      h[ch] = __fadd_rn(__fmul_rn(omlr, pv_u8f((uint32_t)__ldg(pl + ch))), __fmul_rn(lr, pv_u8f((uint32_t)__ldg(pr + ch))));
+  }
+}
+
+template <int SRC_CH>
+__global__ void __launch_bounds__(256) resize_cols_kernel(const uint8_t* __restrict__ src, long long src_img_stride,
+                                                          int src_pitch_px, int sx0, int sy0, int sw, int sh,
+                                                          uchar4* __restrict__ dst, long long dst_img_stride, int dst_pitch_px,
+                                                          int dx0, int dy0, int dw, int dh, float xs, float ys, uint32_t magic) {
+  // magic = 0x4B000000 arrives as a kernel argument so that prmt keeps it as a constant-bank operand and the
+  // selector as its one immediate
+  const int c0 = blockIdx.x * (256 * kResizeCols) + threadIdx.x;
+  if (c0 >= dw) return;
+  const int r0 = blockIdx.y * kResizeRows;
+  const int r1 = min(r0 + kResizeRows, dh);
+  const uint8_t* s = src + (long long)blockIdx.z * src_img_stride;
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst) + (long long)blockIdx.z * dst_img_stride + (long long)(dy0 + r0) * dst_pitch_px + dx0 + c0;
+  uint32_t il[kResizeCols], ir[kResizeCols];      // pixel index of the left/right tap in source row sy0
+  float lr[kResizeCols], omlr[kResizeCols];
+  bool on[kResizeCols];
+#pragma unroll
+  for (int j = 0; j < kResizeCols; ++j) {
+    const int c = c0 + 256 * j;
+    on[j] = c < dw;
+    const float x = __fmul_rn((float)min(c, dw - 1), xs);
+    const int left = min((int)(pv_floor_bits(x) & 0x7FFFFFu), sw - 1);
+    const int right = min(left + 1, sw - 1);
+    lr[j] = __fsub_rn(x, (float)left);
+    omlr[j] = __fsub_rn(1.0f, lr[j]);
+    il[j] = (uint32_t)(sy0 * src_pitch_px + sx0 + left);
+    ir[j] = (uint32_t)(sy0 * src_pitch_px + sx0 + right);
+  }
+  int cur = -2;                                  // source row held in hc (hn holds min(cur + 1, sh - 1))
+  float hc[kResizeCols][3], hn[kResizeCols][3];
+#pragma unroll
+  for (int j = 0; j < kResizeCols; ++j)
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) hc[j][ch] = hn[j][ch] = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float y = __fmul_rn((float)r, ys);
+    const int top = min((int)(pv_floor_bits(y) & 0x7FFFFFu), sh - 1);
+    const int bot = min(top + 1, sh - 1);
+    const float tb = __fsub_rn(y, (float)top), omtb = __fsub_rn(1.0f, tb);
+    if (top != cur) {                            // warp-uniform: rows depend on r only
+      const uint32_t o_top = (uint32_t)(top * src_pitch_px), o_bot = (uint32_t)(bot * src_pitch_px);
+#pragma unroll
+      for (int j = 0; j < kResizeCols; ++j) {
+        if (top == cur + 1) { hc[j][0] = hn[j][0]; hc[j][1] = hn[j][1]; hc[j][2] = hn[j][2]; }
+        else hrow<SRC_CH>(s, il[j] + o_top, ir[j] + o_top, lr[j], omlr[j], magic, hc[j]);
+        if (bot == top) { hn[j][0] = hc[j][0]; hn[j][1] = hc[j][1]; hn[j][2] = hc[j][2]; }
+        else hrow<SRC_CH>(s, il[j] + o_bot, ir[j] + o_bot, lr[j], omlr[j], magic, hn[j]);
+      }
+      cur = top;
+    }
+#pragma unroll
+    for (int j = 0; j < kResizeCols; ++j) {
+      uint32_t q[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float v = __fadd_rn(__fmul_rn(omtb, hc[j][ch]), __fmul_rn(tb, hn[j][ch]));
+        // floor(v + 0.5) clamped to [0, 255]: v >= 0, so only the upper clamp can bind
+        q[ch] = pv_floor_bits(fminf(__fadd_rn(v, 0.5f), 255.5f));
+      }
+      // q[ch] = 0x4B0000vv: byte0 = q0, byte1 = q1, byte2 = q2, byte3 = 255
+      const uint32_t t01 = __byte_perm(q[0], q[1], 0x0040u);            // [q0.b0, q1.b0, -, -]
+      const uint32_t t2a = __byte_perm(q[2], 0xFF000000u, 0x0070u);     // [q2.b0, 0xFF, -, -]
+      if (on[j]) d[256 * j] = __byte_perm(t01, t2a, 0x5410u);
+    }
+    d += dst_pitch_px;
+  }
+}
+
 // 2-D launch: blockIdx.z = image; a CTA covers 8 rows x 128 columns, each thread 4 consecutive columns
 // (independent bilinear samples in flight, 16 contiguous bytes written per thread)
 template <int SRC_CH>
@@ -315,7 +424,17 @@ extern "C" int pv_resize_bilinear(const void* src, int src_channels, int64_t src
   const int threads = 256;
   const dim3 blocks((unsigned)((dw + 127) / 128), (unsigned)((dh + 7) / 8), (unsigned)B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (src_channels == 3)
+  if (!copy_only) {
+    const dim3 cb((unsigned)((dw + 256 * kResizeCols - 1) / (256 * kResizeCols)), (unsigned)((dh + kResizeRows - 1) / kResizeRows), (unsigned)B);
+    if (src_channels == 3)
+      resize_cols_kernel<3><<<cb, 256, 0, s>>>(static_cast<const uint8_t*>(src), src_img_stride, src_pitch_px, sx0, sy0, sw,
+                                               sh, static_cast<uchar4*>(dst_rgba), dst_img_stride_px, dst_pitch_px, dx0, dy0,
+                                               dw, dh, xs, ys, 0x4B000000u);
+    else
+      resize_cols_kernel<4><<<cb, 256, 0, s>>>(static_cast<const uint8_t*>(src), src_img_stride, src_pitch_px, sx0, sy0, sw,
+                                               sh, static_cast<uchar4*>(dst_rgba), dst_img_stride_px, dst_pitch_px, dx0, dy0,
+                                               dw, dh, xs, ys, 0x4B000000u);
+  } else if (src_channels == 3)
     resize_bilinear_kernel<3><<<blocks, threads, 0, s>>>(static_cast<const uint8_t*>(src), src_img_stride, src_pitch_px,
                                                          sx0, sy0, sw, sh, static_cast<uchar4*>(dst_rgba),
                                                          dst_img_stride_px, dst_pitch_px, dx0, dy0, dw, dh, xs, ys, B,

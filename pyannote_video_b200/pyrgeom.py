@@ -3,7 +3,7 @@
 dlib's `input_rgb_image_pyramid<pyramid_down<6>>` tiles every pyramid level into ONE image so a
 single pass of the conv stack scans all scales (reference call site: face_detector_(rgb, 1),
 pyannote/video/face/face.py:66).  dlib's exact packing is not recalled, so the
-packing below is our own shelf layout; it is pure integer host logic shared by the CUDA path and
+packing below is our own guillotine layout; it is pure integer host logic shared by the CUDA path and
 the oracle, which therefore see the same plane.
 """
 import numpy as np
@@ -25,6 +25,32 @@ def det_cell_to_plane(c, r):
     return back(c), back(r)
 
 
+def _guillotine(sizes, pw, ph):
+    """place the tiles (each followed by PYR_PAD zero pixels to its right and below) into a pw x ph area;
+    returns [(x, y, w, h)] or None if they do not fit"""
+    free = [(0, 0, pw + PYR_PAD, ph + PYR_PAD)]
+    out = []
+    for (w, h) in sizes:
+        ww, hh = w + PYR_PAD, h + PYR_PAD
+        best = None
+        for i, (fx, fy, fw, fh) in enumerate(free):
+            if ww <= fw and hh <= fh:
+                score = min(fw - ww, fh - hh)
+                if best is None or score < best[0]:
+                    best = (score, i)
+        if best is None:
+            return None
+        fx, fy, fw, fh = free.pop(best[1])
+        out.append((fx, fy, w, h))
+        r1, b1 = (fx + ww, fy, fw - ww, hh), (fx, fy + hh, fw, fh - hh)      # split along the tile's bottom edge
+        r2, b2 = (fx + ww, fy, fw - ww, fh), (fx, fy + hh, ww, fh - hh)      # split along the tile's right edge
+        cand = (r1, b1) if max(r1[2] * r1[3], b1[2] * b1[3]) > max(r2[2] * r2[3], b2[2] * b2[3]) else (r2, b2)
+        for c in cand:
+            if c[2] > PYR_PAD + PYR_MIN_SIDE - 1 and c[3] > PYR_PAD + PYR_MIN_SIDE - 1:
+                free.append(c)
+    return out
+
+
 class PyramidGeometry:
     def __init__(self, H, W, upsample):
         self.H, self.W, self.upsample = H, W, int(upsample)
@@ -34,28 +60,26 @@ class PyramidGeometry:
             sizes.append((w, h))
             h, w = ((PYR_N - 1) * h) // PYR_N, ((PYR_N - 1) * w) // PYR_N
         self.sizes = sizes
-        # ---- shelf packing: columns of tiles, each column as tall as level 0 ----
+        # ---- guillotine packing (our own): the conv stack scans the whole plane, so every
+        # padding pixel costs as much as an image pixel.  Levels go, largest first, into the free rectangle
+        # with the best short-side fit; a few plane heights are tried and the smallest plane wins
+        # (1080p, upsample 1: 27.1 M level pixels in a 28.9 M-pixel plane, 93.8 %).
         w0, h0 = sizes[0]
-        col_h = h0
-        cols = []      # [x0, width, y_cursor]
-        rects = []
-        x_cursor = PYR_OUTER_PAD
-        for (w, h) in sizes:
-            placed = False
-            for col in cols:
-                if w <= col[1] and col[2] + h <= PYR_OUTER_PAD + col_h:
-                    rects.append((col[0], col[2], w, h))
-                    col[2] += h + PYR_PAD
-                    placed = True
+        best = None
+        heights = [h0] + [h0 + sizes[i][1] + PYR_PAD for i in (5, 3, 2, 1) if i < len(sizes)]
+        for ph in heights:
+            for pw in range(w0, 8 * w0 + 8, 8):
+                rects = _guillotine(sizes, pw, ph)
+                if rects is not None:
+                    pw_al = (pw + 2 * PYR_OUTER_PAD + 3) & ~3
+                    tot = pw_al * (ph + 2 * PYR_OUTER_PAD)
+                    if best is None or tot < best[0]:
+                        best = (tot, pw_al, ph + 2 * PYR_OUTER_PAD, rects)
                     break
-            if not placed:
-                cols.append([x_cursor, w, PYR_OUTER_PAD + h + PYR_PAD])
-                rects.append((x_cursor, PYR_OUTER_PAD, w, h))
-                x_cursor += w + PYR_PAD
-        self.rects = rects                                    # (x0, y0, w, h) per level
-        self.plane_w = x_cursor - PYR_PAD + PYR_OUTER_PAD
-        self.plane_w = (self.plane_w + 3) & ~3    # 16-byte row pitch: the first conv reads raw pixel rows by TMA
-        self.plane_h = col_h + 2 * PYR_OUTER_PAD
+        assert best is not None
+        self.rects = [(x + PYR_OUTER_PAD, y + PYR_OUTER_PAD, w, h) for (x, y, w, h) in best[3]]   # (x0, y0, w, h) per level
+        self.plane_w = best[1]    # multiple of 4 pixels = 16-byte row pitch: the first conv reads raw pixel rows by TMA
+        self.plane_h = best[2]
         # ---- float32 factors mapping level-local coordinates to original-image coordinates ----
         f32 = np.float32
         fx, fy = [], []

@@ -114,3 +114,21 @@ def test_landmarks_and_chips_bit_exact(cuda):
         ref_chips = olm.extract_chips(frames[f].numpy(), ref)
         assert np.array_equal(chips[sel][..., :3], ref_chips), "chips differ in frame %d" % f
         assert (chips[sel][..., 3] == 255).all()
+
+
+@pytest.mark.parametrize("upsample", [0, 1])
+def test_pyramid_plane_bit_exact_all_levels_column_kernel(cuda, upsample, monkeypatch):
+    """every level through the column-walking resize kernel (no one-launch tail), odd sizes, 3 frames"""
+    from oracle import pyramid as opyr
+    from pyannote_video_b200.nets import DetectorNet
+    monkeypatch.setattr(DetectorNet, "TAIL_PIXELS", 0)
+    H, Wd = 203, 331
+    model = W.make_detector(seed=2)
+    frames = make_frames(3, H, Wd, seed=9)
+    net = DetectorNet(model, H, Wd, upsample, max_batch=3, device=cuda)
+    assert net._tail_n == 0
+    net.build_plane(frames.to(cuda), 3)
+    plane = net.plane.cpu().numpy()
+    for i in range(3):
+        ref_plane, _ = opyr.build_plane(frames[i].numpy(), upsample)
+        assert np.array_equal(plane[i], ref_plane), "pyramid plane differs (frame %d)" % i
