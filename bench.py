@@ -332,23 +332,28 @@ def main():
         sampler.stop_flag = True
         sampler.join(timeout=3)
 
-    # ---------------- roofline leg: CUDA events around every srgemm launch ----------------
+    # ---------------- roofline leg: CUDA events around every tensor-core conv launch ----------------
+    # Dominant kernel family = detconv_kernel (detector convs 2..7, csrc/detconv.cu): achieved = algorithmic
+    # FLOPs of those six layers / their summed launch time.  conv1_fused and the embedder's srgemm launches
+    # are reported beside it ("layers", "all_convs").  `traffic` = dram bytes read+written by the six detconv
+    # launches from the committed `ncu --set full` capture (profiles/ncu_traffic.json, bytes per frame x B).
     roof = None
     if rank == 0 and args.profile_convs > 0:
         det = face._detector_for(H, W)
         net = face.face_recognition_
-        conv_ops = [op for op, _ in det.convs] + [a[0] for k, a in net.ops if k == "conv"]
+        det_names = ["conv%d" % (i + 1) for i in range(len(det.convs))]
+        conv_ops = [(n, op) for n, (op, _) in zip(det_names, det.convs)] + [("embed", a[0]) for k, a in net.ops if k == "conv"]
         evs = []
         orig = {}
-        for op in conv_ops:
+        for name, op in conv_ops:
             orig[id(op)] = op.run
 
-            def timed_run(q_rows=None, _op=op, _run=op.run):
+            def timed_run(q_rows=None, _name=name, _run=op.run):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 _run(q_rows)
                 b.record()
-                evs.append((a, b))
+                evs.append((_name, a, b))
             op.run = timed_run
         # coarse stage timing of the same instrumented steps (CUDA events on the launch stream)
         stage_ev = {}
@@ -363,7 +368,7 @@ def main():
                 return r
             return wrapped
 
-        patched = [(det, "build_plane", "pyramid"), (det, "forward_scores", "pack+convs+shift_sum"), (det, "decode", "decode+nms"),
+        patched = [(det, "build_plane", "pyramid"), (det, "forward_scores", "convs+shift_sum"), (det, "decode", "decode+nms"),
                    (face.shape_predictor_, "predict", "landmarks"), (face._chipper, "extract", "chips"),
                    (net, "forward_chips", "embed")]
         saved = [(o, n, getattr(o, n)) for o, n, _ in patched]
@@ -376,18 +381,40 @@ def main():
         overlap[0] = True
         for o, n, f in saved:
             setattr(o, n, f)
-        for op in conv_ops:
+        for name, op in conv_ops:
             op.run = orig[id(op)]
-        stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / max(1, args.profile_convs) for k, v in stage_ev.items()}
-        conv_ms = sum(a.elapsed_time(b) for a, b in evs)
-        flops = args.profile_convs * (B * det.flops_per_frame + B * FACES_PER_FRAME * net.flops_per_face)
+        P = args.profile_convs
+        stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / max(1, P) for k, v in stage_ev.items()}
+        layer_ms = {}
+        for name, a, b in evs:
+            layer_ms[name] = layer_ms.get(name, 0.0) + a.elapsed_time(b) / P
+        layer_flops = {n: B * f for n, f in zip(det_names, det.algorithmic_flops_per_layer)}   # per pyramid pixel, padding excluded
+        layer_flops["embed"] = B * FACES_PER_FRAME * net.flops_per_face
         peaks = load_peaks()
-        achieved = flops / (conv_ms * 1e-3) / 1e12
-        roof = dict(bound="tensor", achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
-                    frac=achieved / peaks["tf_sustained"], traffic=None, peak_source=peaks["source"],
-                    kernel="srgemm_kernel (all %d conv launches/step)" % len(conv_ops),
-                    conv_ms_per_step=conv_ms / args.profile_convs, launches_timed=len(evs),
-                    stage_ms_per_step={k: round(v, 3) for k, v in stage_ms.items()})
+        peak = peaks["tf_sustained"]
+        layers = {n: dict(ms=round(layer_ms[n], 4), tflops=round(layer_flops[n] / (layer_ms[n] * 1e-3) / 1e12, 1),
+                          frac=round(layer_flops[n] / (layer_ms[n] * 1e-3) / 1e12 / peak, 4)) for n in layer_ms}
+        dom = [n for n in det_names[1:]] if det.conv_impl in ("detconv", "rsconv") else det_names
+        dom_ms = sum(layer_ms[n] for n in dom)
+        dom_fl = sum(layer_flops[n] for n in dom)
+        all_ms = sum(layer_ms.values())
+        all_fl = sum(layer_flops.values())
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if det.conv_impl in ("detconv", "rsconv") and os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("plane") == [det.geo.plane_h, det.geo.plane_w]:
+                traffic = tj["detconv_dram_bytes_per_frame"] * B
+        achieved = dom_fl / (dom_ms * 1e-3) / 1e12
+        roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
+                    peak_source=peaks["source"],
+                    kernel=("%s_kernel (detector convs 2..7, %d launches/step)" % (det.conv_impl, len(dom)))
+                    if det.conv_impl in ("detconv", "rsconv") else "srgemm_kernel (detector convs)",
+                    kernel_ms_per_step=round(dom_ms, 4), algorithmic_flops_per_step=dom_fl,
+                    all_convs=dict(ms_per_step=round(all_ms, 4), tflops=round(all_fl / (all_ms * 1e-3) / 1e12, 1),
+                                   frac=round(all_fl / (all_ms * 1e-3) / 1e12 / peak, 4), launches_per_step=len(evs) // P),
+                    layers=layers, stage_ms_per_step={k: round(v, 3) for k, v in stage_ms.items()})
 
     if rank != 0:
         if world > 1:

@@ -166,6 +166,22 @@ int pv_detconv_info(void* handle, int* n_stages, int* smem_bytes, int* tiles_x, 
 int pv_detconv_check(void* handle, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * rsconv: the same layers as detconv, "row-streaming" decomposition (csrc/rsconv.cu) — default.
+ * A work item is 128 output columns x seg_rows output rows; every input row is loaded once (one TMA box)
+ * and multiplied, per filter column kw and 16-channel chunk, against ALL filter rows that use it side by
+ * side ([W_kh(r_lo) | ... | W_kh(r_hi)], N up to 5*48 = 240), accumulating into a ring of TMEM row slots
+ * (one 128 x n_out accumulator per output row).  Same PvDetconvDesc, same instances, different weight image:
+ * for parity class q = kh mod stride (stride 1: only q = 0), filter column kw and chunk j one tile of
+ * nq*n_out rows x 16 k, rows ordered by DECREASING kh (block b holds kh = q + stride*(nq-1-b)); element (nn,k)
+ * at (k>>3)*(nq*n_out*16) + (nn>>3)*128 + (nn&7)*16 + (k&7)*2; tiles ordered [q][kw][j].
+ * ------------------------------------------------------------------------------------------ */
+int pv_rsconv_create(const PvDetconvDesc* desc, void** out_handle);
+int pv_rsconv_run(void* handle, int B, void* stream);
+int pv_rsconv_destroy(void* handle);
+int pv_rsconv_info(void* handle, int* n_stages, int* smem_bytes, int* strips, int* segs, int* seg_rows);
+int pv_rsconv_check(void* handle, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * first-layer packing and the small layers of the embedder (csrc/layers.cu)
  * ------------------------------------------------------------------------------------------ */
 /* RGBA u8 [B,H,W,4] (A==0: pyramid padding) -> "gathered" bf16 rows for a kw x kw stride-2 first conv:

@@ -19,7 +19,10 @@ SRGEMM_GROUP = "row"   # validated on B200 (gpurun #1): descriptors at arbitrary
 DET_CONV1 = os.environ.get("PV_DET_CONV1", "fused")
 
 # detector conv layers 2..7:
+#   "rsconv"   csrc/rsconv.cu: row streaming — every input row is loaded once and multiplied against all filter rows
+#              that use it side by side (N up to 5 x 48 = 240 per MMA, accumulators = a ring of TMEM row slots):
+#              tensor-bound instead of shared-memory-bound                                                  [default]
 #   "detconv"  csrc/detconv.cu: 2-D tiles (8 x 16 outputs), one 4-D TMA patch per tile, every tap's A operand is a
-#              UMMA descriptor into the patch (1.9 input pixels read per output), compile-time MMA sequence  [default]
+#              UMMA descriptor into the patch (1.9 input pixels read per output), compile-time MMA sequence
 #   "srgemm"   the generic 1-D shifted-row GEMM (5.3 input rows read per output, table-driven issue loop)
-DET_CONVS = os.environ.get("PV_DET_CONVS", "detconv")
+DET_CONVS = os.environ.get("PV_DET_CONVS", "rsconv")

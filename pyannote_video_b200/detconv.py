@@ -58,6 +58,12 @@ class DetConv:
     """One bound conv layer: x [Bmax,H,pitch,c_in] bf16 -> out [Bmax,OH,out_pitch,out_cs] (bf16, or f32
     when out_f32).  Same `run(B)` / `check()` protocol as plan.Srgemm."""
 
+    _create, _run, _check, _destroy = "pv_detconv_create", "pv_detconv_run", "pv_detconv_check", "pv_detconv_destroy"
+
+    @staticmethod
+    def _pack(weight, c_in, n_out, stride):
+        return pack_weight_image(weight, c_in, n_out)
+
     def __init__(self, x, H, W, weight, stride, scale, shift, relu, c_in, n_out, out_f32=False, out_cs=None):
         dev = x.device
         Cout, Cin, KH, KW = weight.shape
@@ -73,7 +79,7 @@ class DetConv:
         self.out_cs = out_cs or n_out
         self.out = torch.zeros(B, self.OH, self.out_pitch, self.out_cs, dtype=torch.float32 if out_f32 else torch.bfloat16,
                                device=dev)
-        self.w_img = pack_weight_image(weight, c_in, n_out).to(dev)
+        self.w_img = self._pack(weight, c_in, n_out, stride).to(dev)
         sc = torch.zeros(n_out, dtype=torch.float32)
         sh = torch.zeros(n_out, dtype=torch.float32)
         sc[:Cout] = torch.as_tensor(scale).float()
@@ -91,7 +97,7 @@ class DetConv:
         d.out = self.out.data_ptr()
         d.out_pitch, d.out_cs = self.out_pitch, self.out_cs
         h = C.c_void_p()
-        _lib.check(_lib.lib().pv_detconv_create(C.byref(d), C.byref(h)), "pv_detconv_create")
+        _lib.check(getattr(_lib.lib(), self._create)(C.byref(d), C.byref(h)), self._create)
         self.h = h
         self.flops_per_image = 2 * self.OH * self.OW * Cout * Cin * KH * KW
 
@@ -101,15 +107,77 @@ class DetConv:
         return dict(n_stages=a.value, smem_bytes=b.value, tiles_x=c.value, tiles_y=e.value)
 
     def run(self, B=None):
-        _lib.check(_lib.lib().pv_detconv_run(self.h, int(B or self.Bmax), _lib.stream_ptr()), "pv_detconv_run")
+        _lib.check(getattr(_lib.lib(), self._run)(self.h, int(B or self.Bmax), _lib.stream_ptr()), self._run)
 
     def check(self):
-        _lib.check(_lib.lib().pv_detconv_check(self.h, _lib.stream_ptr()), "pv_detconv_check")
+        _lib.check(getattr(_lib.lib(), self._check)(self.h, _lib.stream_ptr()), self._check)
 
     def __del__(self):
         try:
             if getattr(self, "h", None):
-                _lib.lib().pv_detconv_destroy(self.h)
+                getattr(_lib.lib(), self._destroy)(self.h)
                 self.h = None
         except Exception:
             pass
+
+
+def pack_weight_image_rs(w, c_in, n_out, stride):
+    """weight image of csrc/rsconv.cu (include/pv_b200.h): tiles ordered [q][kw][j]; tile (q,kw,j) has nq*n_out
+    rows (block b = filter row kh = q + stride*(nq-1-b)) x 16 channels of chunk j, un-swizzled K-major core
+    matrices: element (nn,k) at (k>>3)*(nq*n_out*16) + (nn>>3)*128 + (nn&7)*16 + (k&7)*2."""
+    w = torch.as_tensor(w).float()
+    Cout, Cin, KH, KW = w.shape
+    assert Cout <= n_out and Cin <= c_in and c_in % 16 == 0 and n_out % 16 == 0 and stride in (1, 2)
+    kch = c_in // 16
+    wp = torch.zeros(n_out, c_in, KH, KW)
+    wp[:Cout, :Cin] = w
+    parts = []
+    for q in range(stride):
+        khs = list(range(q, KH, stride))[::-1]            # decreasing kh
+        nq = len(khs)
+        if nq == 0:
+            continue
+        for kw in range(KW):
+            for j in range(kch):
+                # [nq*n_out, 16]: row nn = b*n_out + n
+                tile = torch.stack([wp[:, j * 16:(j + 1) * 16, kh, kw] for kh in khs], dim=0).reshape(nq * n_out, 16)
+                t = tile.reshape(nq * n_out // 8, 8, 2, 8).permute(2, 0, 1, 3).contiguous()   # [k>>3][nn>>3][nn&7][k&7]
+                parts.append(t.reshape(-1))
+    img = torch.cat(parts).to(torch.bfloat16).view(torch.uint8).reshape(-1)
+    return img
+
+
+def unpack_weight_image_rs(img, c_in, n_out, KH, KW, stride):
+    """inverse of pack_weight_image_rs, element-address formula written out (CPU test)"""
+    kch = c_in // 16
+    v = img.view(torch.bfloat16).float().numpy()
+    out = np.zeros((n_out, c_in, KH, KW), np.float32)
+    base = 0
+    for q in range(stride):
+        khs = list(range(q, KH, stride))[::-1]
+        nq = len(khs)
+        for kw in range(KW):
+            for j in range(kch):
+                for b, kh in enumerate(khs):
+                    for n in range(n_out):
+                        nn = b * n_out + n
+                        for k in range(16):
+                            off = base + (k >> 3) * (nq * n_out * 16) + (nn >> 3) * 128 + (nn & 7) * 16 + (k & 7) * 2
+                            out[n, j * 16 + k, kh, kw] = v[off // 2]
+                base += nq * n_out * 32
+    return out
+
+
+class RsConv(DetConv):
+    """Same layer contract as DetConv on the row-streaming kernel (csrc/rsconv.cu)."""
+
+    _create, _run, _check, _destroy = "pv_rsconv_create", "pv_rsconv_run", "pv_rsconv_check", "pv_rsconv_destroy"
+
+    @staticmethod
+    def _pack(weight, c_in, n_out, stride):
+        return pack_weight_image_rs(weight, c_in, n_out, stride)
+
+    def info(self):
+        a, b, c, e, f = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.check(_lib.lib().pv_rsconv_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(e), C.byref(f)), "pv_rsconv_info")
+        return dict(n_stages=a.value, smem_bytes=b.value, strips=c.value, segs=e.value, seg_rows=f.value)

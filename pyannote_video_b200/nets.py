@@ -18,7 +18,7 @@ import torch
 from . import _lib, config
 from . import weights as W
 from .plan import ConvPlan, RowLayout, Srgemm
-from .detconv import DetConv, even
+from .detconv import DetConv, RsConv, even
 from .pyrgeom import pyramid_geometry, det_cell_to_plane
 
 
@@ -194,19 +194,31 @@ class DetectorNet:
         self.plane = torch.zeros(B, Hp, Wp, 4, dtype=torch.uint8, device=device)
         self.conv1_mode = config.DET_CONV1 if conv1_mode is None else conv1_mode
         self.conv_impl = config.DET_CONVS if conv_impl is None else conv_impl
-        if self.conv_impl == "detconv":
+        if self.conv_impl in ("detconv", "rsconv"):
             self._init_detconv(model, device)
         else:
             self._init_srgemm(model, device, group)
         self._init_tail(model, device)
+        # algorithmic work: MACs per PYRAMID pixel (not per plane pixel: computing on the
+        # padding between tiles is overhead, not work) -> 3701.48 MAC/pixel for the MMOD face net
+        P = float(geo.total_level_pixels())
+        cum = 1
+        self.algorithmic_flops_per_layer = []
+        for (cout, cin, k, s) in W.DET_CONVS:
+            cum *= s
+            self.algorithmic_flops_per_layer.append(2.0 * P / (cum * cum) * cout * cin * k * k)
+        self.algorithmic_flops_per_frame = sum(self.algorithmic_flops_per_layer)
 
     def _init_detconv(self, model, device):
-        """layers 2..7 on csrc/detconv.cu: plain NHWC activations [B, H, even(W), C], no padding in HBM"""
+        """layers 2..7 on csrc/rsconv.cu (row streaming) or csrc/detconv.cu (2-D tiles): plain NHWC activations
+        [B, H, even(W), C], no padding in HBM"""
+        Conv = RsConv if self.conv_impl == "rsconv" else DetConv
         B, geo = self.B, self.geo
         Hp, Wp = geo.plane_h, geo.plane_w
         convs = model["convs"]
         self.convs = []
         self.flops_per_frame = 0
+        self.flops_per_layer = []
         # conv1 (5x5 s2, RGB -> 16) writes straight into the NHWC tensor through a row map
         cout, cin, k, s = W.DET_CONVS[0]
         OH1, OW1 = (Hp - k) // s + 1, (Wp - k) // s + 1
@@ -224,7 +236,7 @@ class DetectorNet:
             op = Srgemm(cp, self.xg, a1, l1, sc, sh, relu=True)
             img1 = lg.img
         self.convs.append((op, img1))
-        self.flops_per_frame += 2 * OH1 * OW1 * cout * cin * k * k
+        self.flops_per_layer.append(2 * OH1 * OW1 * cout * cin * k * k)
         x, h, w = a1.view(B, OH1, even(OW1), 16), OH1, OW1
         n = len(convs)
         for i in range(1, n):
@@ -237,19 +249,20 @@ class DetectorNet:
                 # pv_det_shift_sum_nhwc adds the kw-shifted channels back together.
                 wt = _t(c["w"]).float()                                   # [1, cin, 9, 9]
                 w9 = wt[0].permute(2, 0, 1).unsqueeze(-1).contiguous()    # [kw, cin, kh, 1]
-                op = DetConv(x, h, w, w9, 1, torch.ones(k), torch.zeros(k), False, c_in, 16, out_f32=True)
+                op = Conv(x, h, w, w9, 1, torch.ones(k), torch.zeros(k), False, c_in, 16, out_f32=True)
                 self.partial = op.out
                 self.OH, self.OW = op.OH, w
                 self.scores = torch.zeros(B, self.OH, self.OW, dtype=torch.float32, device=device)
                 self.score_bias = float(_affine(c, affine=False)[1][0])
-                self.flops_per_frame += 2 * self.OH * self.OW * cout * cin * k * k
+                self.flops_per_layer.append(2 * self.OH * self.OW * cout * cin * k * k)
             else:
                 sc, sh = _affine(c)
                 n_out = (cout + 15) // 16 * 16
-                op = DetConv(x, h, w, _t(c["w"]), s, sc, sh, True, c_in, n_out)
-                self.flops_per_frame += 2 * op.OH * op.OW * cout * cin * k * k
+                op = Conv(x, h, w, _t(c["w"]), s, sc, sh, True, c_in, n_out)
+                self.flops_per_layer.append(2 * op.OH * op.OW * cout * cin * k * k)
                 x, h, w = op.out, op.OH, op.OW
             self.convs.append((op, 1))
+        self.flops_per_frame = sum(self.flops_per_layer)
 
     def _init_srgemm(self, model, device, group):
         B, geo = self.B, self.geo
@@ -259,6 +272,7 @@ class DetectorNet:
         self.xg = lg.alloc(device) if self.conv1_mode != "fused" else None
         self.convs = []
         self.flops_per_frame = 0
+        self.flops_per_layer = []
         convs = model["convs"]
         lcur, cur = lg, self.xg
         n = len(convs)
@@ -306,7 +320,8 @@ class DetectorNet:
                 o = lo.alloc(device)
                 op = Srgemm(cp, cur, o, lo, sc, sh, relu=True)
             self.convs.append((op, cp.lin.img))
-            self.flops_per_frame += 2 * (self.OH * self.OW if last else cp.OH * cp.OW) * cout * cin * k * k
+            self.flops_per_layer.append(2 * (self.OH * self.OW if last else cp.OH * cp.OW) * cout * cin * k * k)
+            self.flops_per_frame += self.flops_per_layer[-1]
             if not last:
                 lcur, cur = lo, o
 
@@ -383,7 +398,7 @@ class DetectorNet:
                                           C.c_int64(self.lg.plane_rows), _mean3(), st), "pv_pack_gathered")
         for op, img in self.convs:
             op.run(M * img)
-        if self.conv_impl == "detconv":
+        if self.conv_impl in ("detconv", "rsconv"):
             _lib.check(L.pv_det_shift_sum_nhwc(_lib.ptr(self.partial), M, self.OH, self.OW, self.partial.shape[2], 16, 9,
                                                C.c_float(self.score_bias), _lib.ptr(self.scores), st),
                        "pv_det_shift_sum_nhwc")

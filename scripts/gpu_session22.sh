@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_detconv_gpu.py -m gpu -q -x > gpurun_out/pytest_rs.log 2>&1; echo "rsconv pytest rc=$?"
+grep -E "passed|failed|Error|assert|rc=" gpurun_out/pytest_rs.log | tail -12
+timeout 600 python -m pytest tests/test_nets_gpu.py tests/test_fullsize_gpu.py -m gpu -q -x -k "detector" > gpurun_out/pytest_det.log 2>&1; echo "detector pytest rc=$?"
+grep -E "passed|failed|Error|assert" gpurun_out/pytest_det.log | tail -8
+timeout 300 python scripts/gpu_probe_det.py --frames 8 2>&1 | tail -1
+PV_DET_CONVS=detconv timeout 300 python scripts/gpu_probe_det.py --frames 8 2>&1 | tail -1

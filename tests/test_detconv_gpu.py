@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from pyannote_video_b200.detconv import DetConv, even
+from pyannote_video_b200.detconv import DetConv, RsConv, even
 
 pytestmark = pytest.mark.gpu
 
@@ -21,15 +21,24 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("c_in,cin,n_out,cout,kh,kw,stride,f32,B,H,W", CASES)
-def test_detconv_matches_conv2d(cuda, c_in, cin, n_out, cout, kh, kw, stride, f32, B, H, W):
+CASES_RS = CASES + [
+    (48, 45, 48, 45, 5, 5, 1, False, 1, 70, 150),      # two strips, several row segments, slot-ring wraps
+    (16, 16, 32, 32, 5, 5, 2, False, 2, 131, 300),
+    (48, 45, 16, 9, 9, 1, 1, True, 2, 90, 140),
+]
+
+
+@pytest.mark.parametrize("impl", ["rsconv", "detconv"])
+@pytest.mark.parametrize("c_in,cin,n_out,cout,kh,kw,stride,f32,B,H,W", CASES_RS)
+def test_detconv_matches_conv2d(cuda, impl, c_in, cin, n_out, cout, kh, kw, stride, f32, B, H, W):
+    Conv = RsConv if impl == "rsconv" else DetConv
     torch.manual_seed(3)
     x = torch.randn(B, H, W, cin).to(torch.bfloat16)
     w = (torch.randn(cout, cin, kh, kw) / (cin * kh * kw) ** 0.5).to(torch.bfloat16).float()
     scale, shift = torch.rand(cout) + 0.5, torch.randn(cout) * 0.1
     xd = torch.zeros(B, H, even(W), c_in, dtype=torch.bfloat16, device=cuda)
     xd[:, :, :W, :cin] = x.to(cuda)
-    op = DetConv(xd, H, W, w, stride, scale, shift, not f32, c_in, n_out, out_f32=f32)
+    op = Conv(xd, H, W, w, stride, scale, shift, not f32, c_in, n_out, out_f32=f32)
     op.out.fill_(7.0)     # positions outside the valid extent must stay untouched
     op.run()
     op.check()

@@ -51,7 +51,8 @@ def test_embed_net_matches_oracle(cuda):
 
 
 @pytest.mark.parametrize("upsample,conv1_mode,conv_impl", [
-    (1, "fused", "detconv"), (0, "fused", "detconv"), (1, "gathered", "detconv"),
+    (1, "fused", "rsconv"), (0, "fused", "rsconv"), (1, "gathered", "rsconv"),
+    (1, "fused", "detconv"), (0, "fused", "detconv"),
     (0, "gathered", "srgemm"), (1, "gathered", "srgemm"), (1, "pixrows", "srgemm"), (0, "pixrows", "srgemm"),
     (1, "fused", "srgemm"), (0, "fused", "srgemm")])
 def test_detector_matches_oracle(cuda, upsample, conv1_mode, conv_impl):

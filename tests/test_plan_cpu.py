@@ -155,3 +155,14 @@ def test_detconv_weight_image_roundtrip():
     w9 = torch.randn(9, 45, 9, 1).to(torch.bfloat16).float()
     u9 = unpack_weight_image(pack_weight_image(w9, 48, 16), 48, 16, 9, 1)
     assert (u9[:9, :45] == w9.numpy()).all()
+
+
+def test_rsconv_weight_image_roundtrip():
+    """the shared-memory weight image of csrc/rsconv.cu (filter rows of one parity class side by side)"""
+    from pyannote_video_b200.detconv import pack_weight_image_rs, unpack_weight_image_rs
+    for (cout, cin, kh, kw, c_in, n_out, s) in [(45, 45, 5, 5, 48, 48, 1), (32, 16, 5, 5, 16, 32, 2), (9, 45, 9, 1, 48, 16, 1)]:
+        w = torch.randn(cout, cin, kh, kw).to(torch.bfloat16).float()
+        img = pack_weight_image_rs(w, c_in, n_out, s)
+        assert img.numel() == kh * kw * (c_in // 16) * n_out * 32
+        u = unpack_weight_image_rs(img, c_in, n_out, kh, kw, s)
+        assert (u[:cout, :cin] == w.numpy()).all() and (u[cout:] == 0).all() and (u[:, cin:] == 0).all()
