@@ -172,14 +172,18 @@ int pv_detconv_check(void* handle, void* stream);
  * side ([W_kh(r_lo) | ... | W_kh(r_hi)], N up to 5*48 = 240), accumulating into a ring of TMEM row slots
  * (one 128 x n_out accumulator per output row).  Same PvDetconvDesc, same instances, different weight image:
  * for parity class q = kh mod stride (stride 1: only q = 0), filter column kw and chunk j one tile of
- * nq*n_out rows x 16 k, rows ordered by DECREASING kh (block b holds kh = q + stride*(nq-1-b)); element (nn,k)
- * at (k>>3)*(nq*n_out*16) + (nn>>3)*128 + (nn&7)*16 + (k&7)*2; tiles ordered [q][kw][j].
+ * nq*n_out rows x 16 k (32 bytes per row), rows ordered by DECREASING kh (block b holds kh = q + stride*(nq-1-b));
+ * K-major with the 32-byte swizzle: element (nn,k) at nn*32 + (((k>>3) ^ ((nn>>2)&1)) * 16) + (k&7)*2;
+ * tiles ordered [q][kw][j].
  * ------------------------------------------------------------------------------------------ */
 int pv_rsconv_create(const PvDetconvDesc* desc, void** out_handle);
 int pv_rsconv_run(void* handle, int B, void* stream);
 int pv_rsconv_destroy(void* handle);
 int pv_rsconv_info(void* handle, int* n_stages, int* smem_bytes, int* strips, int* segs, int* seg_rows);
 int pv_rsconv_check(void* handle, void* stream);
+/* role timing of the last launch when the plan was created with PV_RS_DEBUG set: out8 (HOST) = cycles summed over
+ * CTAs {MMA: wait slot, wait data, issue, input rows; epilogue: wait row, work, total; 0} */
+int pv_rsconv_debug(void* handle, long long* out8);
 
 /* ------------------------------------------------------------------------------------------
  * first-layer packing and the small layers of the embedder (csrc/layers.cu)

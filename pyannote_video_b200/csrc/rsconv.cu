@@ -27,6 +27,8 @@
 // memory; stride 2 uses pixel-PAIR operand rows (2C channels), the tap's column parity selects the K offset.
 #include <cuda.h>
 #include <atomic>
+#include <cstdlib>
+#include <vector>
 #include "../../include/pv_b200.h"
 #include "pv_common.cuh"
 
@@ -53,6 +55,7 @@ struct RsParams {
   int relu;
   int n_stages;
   int* err;
+  long long* dbg;   // optional [grid][8] cycle counters (role timing), nullptr = off
 };
 
 __host__ __device__ constexpr int rs_align1k(int v) { return (v + 1023) & ~1023; }
@@ -105,7 +108,11 @@ struct RsGeo {
   static constexpr int kPadY = S == 1 ? KH / 2 : 0, kPadX = S == 1 ? KW / 2 : 0;
   static constexpr int kNQ0 = (KH + S - 1) / S;            // filter rows of parity class 0 (kh = 0, S, 2S, ...)
   static constexpr int kNQ1 = S == 2 ? KH / 2 : 0;          // parity class 1 (kh = 1, 3, ...)
-  static constexpr int kSlots = (512 / NC) < kMaxSlots ? (512 / NC) : kMaxSlots;
+  // layers with <= 32 output channels run two CTAs per SM (each half of TMEM and of shared memory): their rows
+  // carry few MMAs, so a second issuing thread hides the per-row hand-offs of the first
+  static constexpr int kCtas = NC <= 32 ? 2 : 1;
+  static constexpr int kTmemBudget = 512 / kCtas;
+  static constexpr int kSlots = (kTmemBudget / NC) < kMaxSlots ? (kTmemBudget / NC) : kMaxSlots;
   static constexpr uint32_t kTmemCols = kSlots * NC > 256 ? 512u : (kSlots * NC > 128 ? 256u : 128u);
   static constexpr int kTile0Bytes = kNQ0 * NC * 32;        // one (kw, chunk) weight tile of class 0
   static constexpr int kTile1Bytes = kNQ1 * NC * 32;
@@ -116,7 +123,7 @@ struct RsGeo {
 // C: channels per input pixel in memory (16/32/48), NC: padded output channels, KH x KW filter, S stride
 // (1: pad = K/2 on both axes, 2: pad 0), F32: fp32 output rows (last layer)
 template <int C, int NC, int KH, int KW, int S, bool F32>
-__global__ void __launch_bounds__(kThreads, 1) rsconv_kernel(const __grid_constant__ RsParams p) {
+__global__ void __launch_bounds__(kThreads, (NC <= 32 ? 2 : 1)) rsconv_kernel(const __grid_constant__ RsParams p) {
   using G = RsGeo<C, NC, KH, KW, S>;
   constexpr int NSLOT = G::kSlots;
   static_assert(NC % 16 == 0 && NC >= 16 && NC <= 64, "NC");
@@ -198,51 +205,69 @@ __global__ void __launch_bounds__(kThreads, 1) rsconv_kernel(const __grid_consta
       constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);   // + (N >> 3) << 17
       constexpr uint32_t AHI0 = rs_a_desc_hi(G::kRowB0);
       constexpr uint32_t AHI1 = rs_a_desc_hi(G::kRowB1 > 0 ? G::kRowB1 : 32);
-      constexpr uint32_t BHI = (uint32_t)(128 >> 4) | (1u << 14);    // SBO = 128 B between 8-row groups, version 1
+      // B tiles are K-major rows of 32 bytes (16 channels) in the 32-byte swizzle (the un-swizzled core-matrix layout is
+      // fetched at half the shared-memory rate: measured, profiles/README.md): SBO = 8 rows = 256 B, version 1
+      constexpr uint32_t BHI = (uint32_t)(256 >> 4) | (1u << 14) | (6u << 29);
+      constexpr uint32_t BLK16 = (uint32_t)(NC * 32 >> 4);          // one output row's block of a B tile: NC rows x 32 B
+      constexpr int DC = (KH - 1) / S;                                // rows between the newest row and the one that completes
       pv_mbar_wait(bar_w, 0, p.err, 5);
       pv_tc_fence_after();
       const uint32_t w_addr16 = (pv_smem_u32(wsm) & 0x3FFFFu) >> 4;
-      const uint32_t ring_lo = (pv_smem_u32(ring) & 0x3FFFFu) >> 4;
+      const uint32_t ring_lo = ((pv_smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t cnt = 0;                       // output rows started so far (slot = cnt % NSLOT)
+      int slot_base = 0;                      // slot / ring parity of the item's first output row
+      uint32_t par_base = 0;
+      long long c_rempty = 0, c_full = 0, c_issue = 0, c_rows = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int r_img = item % items_per_img;
         const int seg = r_img / p.strips;
         const int ra = seg * p.seg_rows;
         const int rb = min(ra + p.seg_rows, p.OH);
         const int t0 = S * ra, t1 = S * (rb - 1) + KH - 1;       // t = y + pad
+        int slot_top = slot_base;             // slot / parity of row r_top(t) (tracked past rb - 1 as if rows went on)
+        uint32_t par_top = par_base;
+        // barriers of the item's first input row (later rows are checked while the previous row's MMAs run)
+        long long c0 = p.dbg ? clock64() : 0;
+        pv_mbar_wait(&bar_rempty[slot_top], par_top ^ 1u, p.err, 2);
+        long long c1 = p.dbg ? clock64() : 0;
+        pv_mbar_wait(&bar_full[stage], phase, p.err, 3);
+        long long c2 = p.dbg ? clock64() : 0;
         for (int t = t0; t <= t1; ++t) {
+          pv_tc_fence_after();
           const int q = S == 2 ? (t & 1) : 0;
-          const int nq = (S == 2 && q == 1) ? G::kNQ1 : G::kNQ0;
+          const bool odd = S == 2 && q == 1;
+          const int nq = odd ? G::kNQ1 : G::kNQ0;
           const int r_top = S == 2 ? (t >> 1) : t;               // row reading this input row with kh = q
           const int r_first = r_top - (nq - 1);                  // row reading it with the largest kh of the class
           const int r_hi = min(r_top, rb - 1);
           const int r_lo = max(r_first, ra);
           const bool new_row = (q == 0) && (r_top <= rb - 1);    // first contribution to row r_top (kh = 0)
-          const uint32_t rel_lo = cnt + (uint32_t)(r_lo - ra);
-          const uint32_t slot_lo = rel_lo % NSLOT;
           const int n_all = r_hi - r_lo + 1;                     // >= 1 inside the item's range of t
-          if (new_row) {
-            const uint32_t rel = cnt + (uint32_t)(r_top - ra);
-            pv_mbar_wait(&bar_rempty[rel % NSLOT], ((rel / NSLOT) & 1u) ^ 1u, p.err, 2);
-          }
-          pv_mbar_wait(&bar_full[stage], phase, p.err, 3);
-          pv_tc_fence_after();
-          // weight tile of this parity class, first block = row r_lo
-          const uint32_t lbo = (uint32_t)(nq * NC);                                        // (nq*NC*16) >> 4
-          const uint32_t tile16 = (uint32_t)(((S == 2 && q == 1) ? G::kTile1Bytes : G::kTile0Bytes) >> 4);
-          const uint32_t wq16 = w_addr16 + ((S == 2 && q == 1) ? (uint32_t)(G::kQ1Base >> 4) : 0u) +
-                                (uint32_t)(r_lo - r_first) * (uint32_t)((NC / 8) * 128 >> 4);
+          int slot_lo = slot_top - (r_top - r_lo);
+          if (slot_lo < 0) slot_lo += NSLOT;
           // segments of consecutive rows / slots: [r_lo .. r_lo+n1-1] at slot_lo, the rest from slot 0 (ring wrap)
-          const int n1 = min(n_all, (int)(NSLOT - slot_lo));
+          const int n1 = min(n_all, NSLOT - slot_lo);
           const int n2 = n_all - n1;
-          // first (kw, chunk) of a new row: old rows accumulate, the new row starts from zero
-          const int nn = new_row ? 1 : 0;
-          const int o1 = min(n_all - nn, n1), o2 = n_all - nn - o1;
-          const uint32_t slot_new = (slot_lo + (uint32_t)(n_all - 1)) % NSLOT;
-          const uint32_t a0 = (ring_lo + (uint32_t)stage * (uint32_t)(G::kStageBytes >> 4)) | (1u << 16);
+          const uint32_t d1 = tmem_base + (uint32_t)(slot_lo * NC);
+          const uint32_t id1 = idesc0 | ((uint32_t)(n1 * NC >> 3) << 17);
+          const uint32_t id2 = idesc0 | ((uint32_t)(n2 * NC >> 3) << 17);
+          // weight tile of this parity class, first block = row r_lo
+          const uint32_t tile16 = (uint32_t)((odd ? G::kTile1Bytes : G::kTile0Bytes) >> 4);
+          const uint32_t bb1 = (w_addr16 + (odd ? (uint32_t)(G::kQ1Base >> 4) : 0u) + (uint32_t)(r_lo - r_first) * BLK16) | (1u << 16);
+          const uint32_t bb2 = bb1 + (uint32_t)n1 * BLK16;
+          const uint32_t a0 = ring_lo + (uint32_t)stage * (uint32_t)(G::kStageBytes >> 4);
           const uint32_t a1 = a0 + (uint32_t)(G::kSeg0Bytes >> 4);
+          // next input row of this item: its barriers are checked in the middle of this row's MMAs
+          const bool has_next = t < t1;
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == p.n_stages) { nstage = 0; nphase ^= 1u; }
+          const bool top_moves = S == 1 || q == 1;               // r_top(t+1) = r_top(t) + 1
+          int nslot = slot_top;
+          uint32_t npar = par_top;
+          if (top_moves && ++nslot == NSLOT) { nslot = 0; npar ^= 1u; }
+          const bool next_new = has_next && top_moves && (r_top + 1 <= rb - 1);
 #pragma unroll
           for (int kw = 0; kw < KW; ++kw) {
 #pragma unroll
@@ -258,32 +283,53 @@ __global__ void __launch_bounds__(kThreads, 1) rsconv_kernel(const __grid_consta
                 a_lo = a1 + (uint32_t)((kw * G::kRowB1 + (kc * 16 - G::kRowEl0) * 2) >> 4);
                 a_hi = AHI1;
               }
-              const uint32_t b_lo = ((wq16 + (uint32_t)(kw * G::kKch + kc) * tile16) & 0x3FFFu) | (lbo << 16);
-              const uint32_t blk16 = (uint32_t)((NC / 8) * 128 >> 4);     // one row's block of the B tile
+              const uint32_t boff = (uint32_t)(kw * G::kKch + kc) * tile16;
               if (kw == 0 && kc == 0 && new_row) {
-                if (o1 > 0)
-                  rs_umma(tmem_base + slot_lo * NC, a_lo, a_hi, b_lo, BHI, idesc0 | ((uint32_t)(o1 * NC >> 3) << 17), 1u);
-                if (o2 > 0)
-                  rs_umma(tmem_base, a_lo, a_hi, b_lo + (uint32_t)o1 * blk16, BHI, idesc0 | ((uint32_t)(o2 * NC >> 3) << 17), 1u);
-                rs_umma(tmem_base + slot_new * NC, a_lo, a_hi, b_lo + (uint32_t)(n_all - 1) * blk16, BHI,
+                // first contribution to the new row: older rows accumulate, the new row starts from zero
+                const int o1 = min(n_all - 1, n1), o2 = n_all - 1 - o1;
+                if (o1 > 0) rs_umma(d1, a_lo, a_hi, bb1, BHI, idesc0 | ((uint32_t)(o1 * NC >> 3) << 17), 1u);
+                if (o2 > 0) rs_umma(tmem_base, a_lo, a_hi, bb1 + (uint32_t)o1 * BLK16, BHI, idesc0 | ((uint32_t)(o2 * NC >> 3) << 17), 1u);
+                rs_umma(tmem_base + (uint32_t)(slot_top * NC), a_lo, a_hi, bb1 + (uint32_t)(n_all - 1) * BLK16, BHI,
                         idesc0 | ((uint32_t)(NC >> 3) << 17), 0u);
               } else {
-                rs_umma(tmem_base + slot_lo * NC, a_lo, a_hi, b_lo, BHI, idesc0 | ((uint32_t)(n1 * NC >> 3) << 17), 1u);
-                if (n2 > 0)
-                  rs_umma(tmem_base, a_lo, a_hi, b_lo + (uint32_t)n1 * blk16, BHI, idesc0 | ((uint32_t)(n2 * NC >> 3) << 17), 1u);
+                rs_umma(d1, a_lo, a_hi, bb1 + boff, BHI, id1, 1u);
+                if (n2 > 0) rs_umma(tmem_base, a_lo, a_hi, bb2 + boff, BHI, id2, 1u);
               }
+            }
+            if (kw == (KW - 1) / 2 && has_next) {
+              // the tensor pipe has this row's MMAs queued: look at the next row's barriers now
+              c0 = p.dbg ? clock64() : 0;
+              if (next_new) pv_mbar_wait(&bar_rempty[nslot], npar ^ 1u, p.err, 2);
+              c1 = p.dbg ? clock64() : 0;
+              pv_mbar_wait(&bar_full[nstage], nphase, p.err, 3);
+              c2 = p.dbg ? clock64() : 0;
+              if (p.dbg) { c_rempty += c1 - c0; c_full += c2 - c1; }
             }
           }
           pv_umma_commit(&bar_empty[stage]);
-          if (++stage == p.n_stages) { stage = 0; phase ^= 1u; }
           // the row whose last filter row (kh = KH-1) this was is complete
-          const int tc = t - (KH - 1);
-          if (tc >= t0 && (S == 1 || (tc & 1) == 0)) {
-            const int rc = S == 2 ? (tc >> 1) : tc;
-            if (rc < rb) pv_umma_commit(&bar_rfull[(cnt + (uint32_t)(rc - ra)) % NSLOT]);
+          if (S == 1 || q == 0) {
+            const int rc = r_top - DC;
+            if (rc >= ra && rc < rb) {
+              int sc = slot_top - DC;
+              if (sc < 0) sc += NSLOT;
+              pv_umma_commit(&bar_rfull[sc]);
+            }
           }
+          stage = nstage;
+          phase = nphase;
+          slot_top = nslot;
+          par_top = npar;
+          if (p.dbg) ++c_rows;
         }
-        cnt += (uint32_t)(rb - ra);
+        if (p.dbg) c_issue += clock64() - c2;
+        const int adv = (slot_base + (rb - ra)) / NSLOT;
+        slot_base = (slot_base + (rb - ra)) % NSLOT;
+        par_base ^= (uint32_t)(adv & 1);
+      }
+      if (p.dbg) {
+        long long* d = p.dbg + (long long)blockIdx.x * 8;
+        d[0] = c_rempty; d[1] = c_full; d[2] = c_issue; d[3] = c_rows;
       }
     }
   } else {
@@ -291,6 +337,8 @@ __global__ void __launch_bounds__(kThreads, 1) rsconv_kernel(const __grid_consta
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     uint32_t cnt = 0;
+    long long e_wait = 0, e_work = 0;
+    const long long e_start = p.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int b = item / items_per_img;
       const int r_img = item - b * items_per_img;
@@ -303,8 +351,10 @@ __global__ void __launch_bounds__(kThreads, 1) rsconv_kernel(const __grid_consta
       for (int r = ra; r < rb; ++r) {
         const uint32_t rel = cnt + (uint32_t)(r - ra);
         const uint32_t slot = rel % NSLOT;
+        const long long e0 = p.dbg ? clock64() : 0;
         pv_mbar_wait(&bar_rfull[slot], (rel / NSLOT) & 1u, p.err, 4);
         pv_tc_fence_after();
+        const long long e1 = p.dbg ? clock64() : 0;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * NC;
         uint32_t v[NC / 16][16];
 #pragma unroll
@@ -345,8 +395,13 @@ __global__ void __launch_bounds__(kThreads, 1) rsconv_kernel(const __grid_consta
             }
           }
         }
+        if (p.dbg) { e_wait += e1 - e0; e_work += clock64() - e1; }
       }
       cnt += (uint32_t)(rb - ra);
+    }
+    if (p.dbg && threadIdx.x == 64) {
+      long long* d = p.dbg + (long long)blockIdx.x * 8;
+      d[4] = e_wait; d[5] = e_work; d[6] = clock64() - e_start;
     }
   }
   pv_tc_fence_before();
@@ -382,7 +437,9 @@ struct RsPlan {
   size_t smem_bytes = 0;
   int num_sms = 0;
   int Bmax = 0;
+  int ctas = 1;
   int* d_err = nullptr;
+  long long* d_dbg = nullptr;
 };
 
 struct RsInstance {
@@ -411,8 +468,9 @@ cudaError_t rs_launch(const RsPlan* plan, const RsParams& p, int grid, cudaStrea
 }
 
 template <int C, int N, int KH, int KW, int S>
-void rs_geometry(int* aw, int* rowel0, int* rowel1, int* stage_bytes, int* w_bytes) {
+void rs_geometry(int* aw, int* rowel0, int* rowel1, int* stage_bytes, int* w_bytes, int* ctas) {
   using G = RsGeo<C, N, KH, KW, S>;
+  *ctas = G::kCtas;
   *aw = G::kAW;
   *rowel0 = G::kRowEl0;
   *rowel1 = G::kRowEl1;
@@ -442,17 +500,17 @@ extern "C" int pv_rsconv_create(const PvDetconvDesc* d, void** out_handle) {
              d->out_pitch, d->out_cs);
   PV_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w_img) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "pv_rsconv_create: operands must be 16-byte aligned");
-  int aw, rowel0, rowel1, stage_bytes, w_bytes;
+  int aw, rowel0, rowel1, stage_bytes, w_bytes, ctas;
   switch (kind) {
-    case 0: rs_geometry<16, 32, 5, 5, 2>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes); break;
-    case 1: rs_geometry<32, 32, 5, 5, 2>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes); break;
-    case 2: rs_geometry<32, 48, 5, 5, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes); break;
-    case 3: rs_geometry<48, 48, 5, 5, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes); break;
-    default: rs_geometry<48, 16, 9, 1, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes); break;
+    case 0: rs_geometry<16, 32, 5, 5, 2>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
+    case 1: rs_geometry<32, 32, 5, 5, 2>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
+    case 2: rs_geometry<32, 48, 5, 5, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
+    case 3: rs_geometry<48, 48, 5, 5, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
+    default: rs_geometry<48, 16, 9, 1, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
   }
   PV_REQUIRE(d->w_bytes == (int64_t)w_bytes, "pv_rsconv_create: weight image is %lld bytes, expected %d", (long long)d->w_bytes, w_bytes);
   const size_t fixed = (2 * kMaxStages + 2 * kMaxSlots + 1) * sizeof(uint64_t) + 2 * in.N * sizeof(float) + 64;
-  const long long budget = 227 * 1024 - 1024 - 1024 - (long long)fixed - rs_align1k(w_bytes);
+  const long long budget = (227 * 1024) / ctas - 1024 - 1024 - (long long)fixed - rs_align1k(w_bytes);
   int n_stages = (int)(budget / stage_bytes);
   if (n_stages > kMaxStages) n_stages = kMaxStages;
   PV_REQUIRE(n_stages >= 3, "pv_rsconv_create: input row of %d bytes (+%d weights) does not fit a 3-deep ring", stage_bytes, w_bytes);
@@ -498,6 +556,11 @@ extern "C" int pv_rsconv_create(const PvDetconvDesc* d, void** out_handle) {
     return PV_ERR_CUDA;
   }
   cudaMemset(plan->d_err, 0, sizeof(int));
+  if (getenv("PV_RS_DEBUG")) {
+    cudaMalloc(&plan->d_dbg, sizeof(long long) * 8 * plan->num_sms * 2);
+    cudaMemset(plan->d_dbg, 0, sizeof(long long) * 8 * plan->num_sms * 2);
+  }
+  p.dbg = plan->d_dbg;
   p.w_img = static_cast<const uint8_t*>(d->w_img);
   p.w_bytes = (uint32_t)w_bytes;
   p.scale = d->scale;
@@ -512,11 +575,12 @@ extern "C" int pv_rsconv_create(const PvDetconvDesc* d, void** out_handle) {
   // rows per work item: enough items for ~8 per SM at the full batch, at least 8 rows (halo rows cost little:
   // their MMAs are narrower, only their A reads are extra)
   {
-    const long long want = 8ll * plan->num_sms;
+    const long long want = 8ll * plan->num_sms * ctas;
     long long per_col = (want + (long long)d->B * p.strips - 1) / ((long long)d->B * p.strips);   // segments wanted per strip
     if (per_col < 1) per_col = 1;
     int rows = (int)((OH + per_col - 1) / per_col);
-    if (rows < 8) rows = 8;
+    const int min_rows = 4 * ((in.KH - 1) / in.S) > 8 ? 4 * ((in.KH - 1) / in.S) : 8;   // halo rows <= 25 % of an item
+    if (rows < min_rows) rows = min_rows;
     if (rows > OH) rows = OH;
     p.seg_rows = rows;
     p.segs = (OH + rows - 1) / rows;
@@ -525,6 +589,7 @@ extern "C" int pv_rsconv_create(const PvDetconvDesc* d, void** out_handle) {
   p.n_stages = n_stages;
   p.err = plan->d_err;
   plan->kind = kind;
+  plan->ctas = ctas;
   plan->Bmax = d->B;
   plan->smem_bytes = (size_t)rs_align1k(w_bytes) + (size_t)n_stages * stage_bytes + fixed + 1024;
   *out_handle = plan;
@@ -540,7 +605,8 @@ extern "C" int pv_rsconv_run(void* handle, int B, void* stream) {
   const long long ni = (long long)B * p.segs * p.strips;
   PV_REQUIRE(ni < (1ll << 31), "pv_rsconv_run: too many work items");
   p.num_items = (int)ni;
-  const int grid = p.num_items < plan->num_sms ? p.num_items : plan->num_sms;
+  const int max_grid = plan->num_sms * plan->ctas;
+  const int grid = p.num_items < max_grid ? p.num_items : max_grid;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   switch (plan->kind) {
@@ -566,6 +632,20 @@ extern "C" int pv_rsconv_info(void* handle, int* n_stages, int* smem_bytes, int*
   return PV_OK;
 }
 
+/* role timing of the last launch (PV_RS_DEBUG=1 at create time): out[8] = sums over CTAs of
+ * {mma: wait slot, wait data, issue, rows; epilogue: wait row, work, total; -} in cycles */
+extern "C" int pv_rsconv_debug(void* handle, long long* out8) {
+  PV_REQUIRE(handle && out8, "pv_rsconv_debug: null argument");
+  RsPlan* plan = static_cast<RsPlan*>(handle);
+  PV_REQUIRE(plan->d_dbg, "pv_rsconv_debug: plan was created without PV_RS_DEBUG");
+  std::vector<long long> h(8 * plan->num_sms * 2);
+  PV_CUDA_CHECK(cudaMemcpy(h.data(), plan->d_dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 8; ++k) out8[k] = 0;
+  for (int i = 0; i < plan->num_sms * 2; ++i)
+    for (int k = 0; k < 8; ++k) out8[k] += h[8 * i + k];
+  return PV_OK;
+}
+
 extern "C" int pv_rsconv_check(void* handle, void* stream) {
   PV_REQUIRE(handle, "pv_rsconv_check: null handle");
   RsPlan* plan = static_cast<RsPlan*>(handle);
@@ -588,6 +668,7 @@ extern "C" int pv_rsconv_destroy(void* handle) {
   if (!handle) return PV_OK;
   RsPlan* plan = static_cast<RsPlan*>(handle);
   cudaFree(plan->d_err);
+  if (plan->d_dbg) cudaFree(plan->d_dbg);
   delete plan;
   return PV_OK;
 }

@@ -123,8 +123,8 @@ class DetConv:
 
 def pack_weight_image_rs(w, c_in, n_out, stride):
     """weight image of csrc/rsconv.cu (include/pv_b200.h): tiles ordered [q][kw][j]; tile (q,kw,j) has nq*n_out
-    rows (block b = filter row kh = q + stride*(nq-1-b)) x 16 channels of chunk j, un-swizzled K-major core
-    matrices: element (nn,k) at (k>>3)*(nq*n_out*16) + (nn>>3)*128 + (nn&7)*16 + (k&7)*2."""
+    rows (block b = filter row kh = q + stride*(nq-1-b)) x 16 channels of chunk j; K-major rows of 32 bytes with
+    the 32-byte swizzle: element (nn,k) at nn*32 + (((k>>3) ^ ((nn>>2)&1)) * 16) + (k&7)*2."""
     w = torch.as_tensor(w).float()
     Cout, Cin, KH, KW = w.shape
     assert Cout <= n_out and Cin <= c_in and c_in % 16 == 0 and n_out % 16 == 0 and stride in (1, 2)
@@ -137,11 +137,14 @@ def pack_weight_image_rs(w, c_in, n_out, stride):
         nq = len(khs)
         if nq == 0:
             continue
+        nn = torch.arange(nq * n_out)
+        swap = ((nn >> 2) & 1).bool()
         for kw in range(KW):
             for j in range(kch):
-                # [nq*n_out, 16]: row nn = b*n_out + n
-                tile = torch.stack([wp[:, j * 16:(j + 1) * 16, kh, kw] for kh in khs], dim=0).reshape(nq * n_out, 16)
-                t = tile.reshape(nq * n_out // 8, 8, 2, 8).permute(2, 0, 1, 3).contiguous()   # [k>>3][nn>>3][nn&7][k&7]
+                # [nq*n_out, 2, 8]: row nn = b*n_out + n, two 16-byte chunks
+                tile = torch.stack([wp[:, j * 16:(j + 1) * 16, kh, kw] for kh in khs], dim=0).reshape(nq * n_out, 2, 8)
+                t = tile.clone()
+                t[swap] = tile[swap].flip(1)              # chunk c is stored at c ^ ((nn>>2)&1)
                 parts.append(t.reshape(-1))
     img = torch.cat(parts).to(torch.bfloat16).view(torch.uint8).reshape(-1)
     return img
@@ -162,7 +165,7 @@ def unpack_weight_image_rs(img, c_in, n_out, KH, KW, stride):
                     for n in range(n_out):
                         nn = b * n_out + n
                         for k in range(16):
-                            off = base + (k >> 3) * (nq * n_out * 16) + (nn >> 3) * 128 + (nn & 7) * 16 + (k & 7) * 2
+                            off = base + nn * 32 + (((k >> 3) ^ ((nn >> 2) & 1)) * 16) + (k & 7) * 2
                             out[n, j * 16 + k, kh, kw] = v[off // 2]
                 base += nq * n_out * 32
     return out

@@ -61,6 +61,17 @@ def main():
         acc["pyramid"] += a0.elapsed_time(a1)
         acc["forward_scores"] += a1.elapsed_time(a2)
     out = {k: round(v / args.reps * 1000.0, 1) for k, v in acc.items()}
+    if os.environ.get("PV_RS_DEBUG") and det.conv_impl == "rsconv":
+        import ctypes as C
+        from pyannote_video_b200 import _lib
+        dbg = {}
+        for (op, _), n in zip(det.convs[1:], names[1:]):
+            a = (C.c_longlong * 8)()
+            _lib.check(_lib.lib().pv_rsconv_debug(op.h, a), "pv_rsconv_debug")
+            rows = max(1, a[3])
+            dbg[n] = dict(rows=a[3], wait_slot=round(a[0] / rows), wait_data=round(a[1] / rows), issue=round(a[2] / rows),
+                          epi_wait=round(a[4] / rows), epi_work=round(a[5] / rows), total_per_row=round(a[6] / rows))
+        out["rs_debug_cycles_per_input_row"] = dbg
     out["mode"] = det.conv1_mode
     out["frames"] = B
     out["unit"] = "us"
