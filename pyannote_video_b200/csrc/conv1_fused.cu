@@ -10,10 +10,12 @@
 // buffer: in the un-swizzled K-major layout the 8 rows of a core matrix are 16 bytes apart, which is
 // exactly the 2-pixel step between neighbouring outputs of a stride-2 convolution, so the A rows
 // (the 5-pixel windows) simply OVERLAP in shared memory and no im2col gather is ever materialised.
-//   A row m, filter row kh  = pixels 2m .. 2m+5 of buffer row kh   (3 chunks of 2 pixels = 8 bf16)
-//   MMA j = 0..4 : chunks 0,1 of filter row j               (LBO = 16 B)
-//   MMA 5, 6     : chunk 2 of filter rows (0,1) and (2,3)   (LBO = one buffer row)
-//   MMA 7        : chunk 2 of filter row 4 (+ a zero-weight chunk)
+//   A row m of input row i = pixels 2m .. 2m+5 of buffer row i   (3 chunks of 2 pixels = 8 bf16)
+// One input row serves every output row of the tile that reads it (kh = i - 2r), so its A operand is read
+// ONCE and multiplied against the filter rows of all those output rows side by side (N = 16, 32 or 48):
+//   11 "main" MMAs : chunks 0,1 of input row i (kw 0..3, LBO = 16 B)  x  [W_kh(r_lo) | .. | W_kh(r_hi)]
+//    6 "pair" MMAs : chunk 2 (kw 4) of input rows (i, i+1) (LBO = one buffer row)
+// = 17 MMAs per 4 x 126 outputs instead of 32 single-row ones (A traffic from shared memory -47 %).
 // A tile is 126 consecutive outputs of FOUR consecutive output rows (2*125 + 5 = 255 input pixels fit one
 // 256-pixel TMA box; rows 126/127 of each MMA are padding; 2*4 + 3 = 11 input rows).  Four rows per tile
 // mean every input pixel is fetched and converted 11/8 = 1.4 times instead of 2.5 times, and the per-tile
@@ -42,8 +44,22 @@ constexpr int kPxRowBytes = (kRawW + 8) * 8;      // 264 pixels x 8 B; the 8 tra
 constexpr int kPxSlotBytes = 23296;               // 11 rows (23232 B) rounded up to 128
 constexpr int kPxRing = 2;
 constexpr int kAcc = 2;                           // tiles in flight in TMEM (kRows accumulators each)
-constexpr int kNumMma = 8;                        // per output row
-constexpr int kWBytes = kNumMma * 512;            // 8 B operands of 16 x 16 bf16
+constexpr int kNumMma = 17;                       // per tile: 11 main + 6 pair (see the header comment)
+
+// ---- the MMA schedule of a tile (compile-time arithmetic, also run at setup to lay the weights out) ----
+// order: main(4) and main(10) first — between them they touch every accumulator and open each with accumulate = 0
+__host__ __device__ constexpr bool ent_pair(int e) { return e >= 11; }
+__host__ __device__ constexpr int ent_row(int e) {
+  return e == 0 ? 4 : (e == 1 ? 10 : (e < 11 ? (e - 2 < 4 ? e - 2 : e - 1) : 2 * (e - 11)));
+}
+__host__ __device__ constexpr int ent_rlo(int e) { return ent_row(e) - 3 > 0 ? (ent_row(e) - 3) >> 1 : 0; }
+__host__ __device__ constexpr int ent_rhi(int e) {
+  return ((ent_row(e) + (ent_pair(e) ? 1 : 0)) >> 1) < kRows - 1 ? ((ent_row(e) + (ent_pair(e) ? 1 : 0)) >> 1) : kRows - 1;
+}
+__host__ __device__ constexpr int ent_n(int e) { return (ent_rhi(e) - ent_rlo(e) + 1) * kN; }       // MMA N
+__host__ __device__ constexpr int ent_boff(int e) { return e == 0 ? 0 : ent_boff(e - 1) + ent_n(e - 1) * 32; }
+constexpr int kWBytes = ent_boff(kNumMma);        // all B tiles (N x 16 bf16 each)
+static_assert(ent_rlo(0) == 0 && ent_rhi(0) == 2 && ent_rlo(1) == 3 && ent_rhi(1) == 3, "opening MMAs must cover all rows");
 constexpr int kConvWarps = 8;
 // warps: 0 = TMA, 1 = MMA, 2..9 = converters, 10..13 = epilogue
 constexpr int kThreads = 32 * (2 + kConvWarps + 4);
@@ -63,7 +79,6 @@ struct C1Params {
   PvRowMap dst;
   float c0, c1, c2;      // -mean/256
   int num_tiles;
-  int swap_ls;
   int* err;
 };
 
@@ -109,6 +124,22 @@ __device__ __forceinline__ uint64_t desc_kmajor_plain(uint32_t smem_addr, uint32
   return d;
 }
 
+// the 17 MMAs of a tile, schedule entries forced to compile-time constants (template recursion)
+template <int E>
+__device__ __forceinline__ void issue_tile(uint32_t a0, uint32_t w0, uint32_t tmem_tile, uint32_t idesc0, uint32_t lead) {
+  if constexpr (E < kNumMma) {
+    constexpr int i0 = ent_row(E), N = ent_n(E), rlo = ent_rlo(E), boff = ent_boff(E);
+    constexpr bool pair = ent_pair(E);
+    // (the last pair has no second input row: its second K chunk re-reads this row — finite data, zero weights)
+    constexpr uint32_t a_off = pair ? (uint32_t)(i0 * kPxRowBytes + 32) : (uint32_t)(i0 * kPxRowBytes);
+    constexpr uint32_t a_lbo = pair ? (i0 + 1 < kInRows ? (uint32_t)kPxRowBytes : 16u) : 16u;
+    const uint64_t ad = desc_kmajor_plain(a0 + a_off, a_lbo, 128u);
+    const uint64_t bd = desc_kmajor_plain(w0 + (uint32_t)boff, (uint32_t)(N * 16), 128u);
+    pv_umma_bf16_pred(tmem_tile + (uint32_t)(rlo * kN), ad, bd, idesc0 | ((uint32_t)(N >> 3) << 17), E >= 2 ? 1u : 0u, lead);
+    issue_tile<E + 1>(a0, w0, tmem_tile, idesc0, lead);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_constant__ C1Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -129,21 +160,32 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
   const int lane = threadIdx.x & 31;
 
   // ---- setup ----
-  // B operand j: element (n, k) at j*512 + (k>>3)*256 + (n>>3)*128 + (n&7)*16 + (k&7)*2
-  for (int i = threadIdx.x; i < kNumMma * kN * 16; i += kThreads) {
-    const int j = i >> 8, n = (i >> 4) & 15, k = i & 15;
-    const int ch = k & 3;
-    int kh, kw;
-    if (j < 5) {
-      kh = j;
-      kw = k >> 2;
-    } else {
-      kh = (j - 5) * 2 + (k >> 3);
-      kw = 4 + ((k >> 2) & 1);
+  // B tile of schedule entry e: rows nn = (r - r_lo)*16 + n, element (nn, k) at
+  //   boff(e) + (k>>3)*(N*16) + (nn>>3)*128 + (nn&7)*16 + (k&7)*2          (un-swizzled K-major core matrices)
+  // main: k = (kw 0..3, ch) of input row i, kh = i - 2r;  pair: k<8 -> (kw 4|pad, ch) of row i, k>=8 -> of row i+1
+  int boff = 0;
+  for (int e = 0; e < kNumMma; boff += ent_n(e) * 32, ++e) {
+    const int i0 = ent_row(e), rlo = ent_rlo(e), N = ent_n(e);
+    const bool pair = ent_pair(e);
+    for (int idx = threadIdx.x; idx < N * 16; idx += kThreads) {
+      const int nn = idx >> 4, k = idx & 15;
+      const int r = rlo + (nn >> 4), n = nn & 15;
+      const int ch = k & 3;
+      int kh, kw;
+      bool ok = ch < 3;
+      if (!pair) {
+        kw = k >> 2;
+        kh = i0 - 2 * r;
+      } else {
+        const int ii = i0 + (k >> 3);
+        kw = 4 + ((k >> 2) & 1);
+        kh = ii - 2 * r;
+        ok = ok && kw == 4 && ii < kInRows;
+      }
+      ok = ok && kh >= 0 && kh < kKH;
+      const __nv_bfloat16 v = ok ? p.w[((n * 3 + ch) * 5 + kh) * 5 + kw] : __float2bfloat16(0.f);
+      *reinterpret_cast<__nv_bfloat16*>(wsm + boff + (k >> 3) * (N * 16) + (nn >> 3) * 128 + (nn & 7) * 16 + (k & 7) * 2) = v;
     }
-    const bool ok = ch < 3 && kw < 5 && kh < 5;
-    const __nv_bfloat16 v = ok ? p.w[((n * 3 + ch) * 5 + kh) * 5 + kw] : __float2bfloat16(0.f);
-    *reinterpret_cast<__nv_bfloat16*>(wsm + j * 512 + (k >> 3) * 256 + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = v;
   }
   // trailing 8 pixels of every buffer row: read by the padding rows of the MMA, must be finite
   for (int i = threadIdx.x; i < kPxRing * kInRows * 8; i += kThreads) {
@@ -197,13 +239,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t lead = pv_elect_one() ? 1u : 0u;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    const uint32_t a_sbo = 128u, b_lbo = 256u, b_sbo = 128u;
-    uint64_t bdesc[kNumMma];
-#pragma unroll
-    for (int j = 0; j < kNumMma; ++j)
-      bdesc[j] = p.swap_ls ? desc_kmajor_plain(pv_smem_u32(wsm + j * 512), b_sbo, b_lbo)
-                           : desc_kmajor_plain(pv_smem_u32(wsm + j * 512), b_lbo, b_sbo);
+    const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileM >> 4) << 24);   // + (N >> 3) << 17
+    const uint32_t w0 = pv_smem_u32(wsm);
     int slot = 0, buf = 0;
     uint32_t phase = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -211,18 +248,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
       pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
       pv_tc_fence_after();
       const uint32_t a0 = pv_smem_u32(pxb + slot * kPxSlotBytes);
-#pragma unroll
-      for (int r = 0; r < kRows; ++r) {
-        const uint32_t tmem_d = tmem_base + (uint32_t)((buf * kRows + r) * kN);
-        const uint32_t ar = a0 + (uint32_t)(2 * r * kPxRowBytes);
-#pragma unroll
-        for (int j = 0; j < kNumMma; ++j) {
-          const uint32_t addr = j < 5 ? ar + j * kPxRowBytes : ar + (j - 5) * 2 * kPxRowBytes + 32;
-          const uint32_t lbo = (j == 5 || j == 6) ? (uint32_t)kPxRowBytes : 16u;
-          const uint64_t ad = p.swap_ls ? desc_kmajor_plain(addr, a_sbo, lbo) : desc_kmajor_plain(addr, lbo, a_sbo);
-          pv_umma_bf16_pred(tmem_d, ad, bdesc[j], idesc, j > 0 ? 1u : 0u, lead);
-        }
-      }
+      issue_tile<0>(a0, w0, tmem_base + (uint32_t)(buf * kRows * kN), idesc0, lead);
       pv_umma_commit_pred(&bar_empty[slot], lead);
       pv_umma_commit_pred(&bar_tfull[buf], lead);
       if (++slot == kPxRing) { slot = 0; phase ^= 1u; }
@@ -340,7 +366,6 @@ extern "C" int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, con
   PV_REQUIRE((reinterpret_cast<uintptr_t>(plane_rgba) & 15) == 0, "pv_conv1_fused: plane must be 16-byte aligned");
   static EncodeTiledFn encode = nullptr;
   static int num_sms = 0;
-  static int swap_ls = 0;
   if (!encode) {
     void* fp = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -350,8 +375,6 @@ extern "C" int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, con
     PV_CUDA_CHECK(cudaGetDevice(&dev));
     PV_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     PV_CUDA_CHECK(cudaFuncSetAttribute(conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    const char* e = getenv("PV_C1_SWAP");
-    swap_ls = (e && e[0] == '1') ? 1 : 0;
     encode = reinterpret_cast<EncodeTiledFn>(fp);
   }
   C1Params p;
@@ -387,7 +410,6 @@ extern "C" int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, con
   const long long nt = (long long)B * p.oh_tiles * p.tiles_per_row;
   PV_REQUIRE(nt < (1ll << 31), "pv_conv1_fused: too many tiles");
   p.num_tiles = (int)nt;
-  p.swap_ls = swap_ls;
   p.err = err_flag;
   int grid = num_sms * 2;
   if (grid > p.num_tiles) grid = p.num_tiles;
