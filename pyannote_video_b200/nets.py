@@ -192,6 +192,7 @@ class DetectorNet:
         self.geo = geo = pyramid_geometry(H, W_, upsample)
         Hp, Wp = geo.plane_h, geo.plane_w
         self.plane = torch.zeros(B, Hp, Wp, 4, dtype=torch.uint8, device=device)
+        self.planes = [self.plane]        # a second plane (enable_double_buffer) lets the next batch's pyramid be built early
         self.conv1_mode = config.DET_CONV1 if conv1_mode is None else conv1_mode
         self.conv_impl = config.DET_CONVS if conv_impl is None else conv_impl
         if self.conv_impl in ("detconv", "rsconv"):
@@ -350,6 +351,19 @@ class DetectorNet:
         self.out_counts = torch.zeros(B, dtype=torch.int32, device=device)
         cm, ca = det_cell_to_plane(1, 1)[0] - det_cell_to_plane(0, 0)[0], det_cell_to_plane(0, 0)[0]
         self.cell_mul, self.cell_add = cm, ca
+
+    def enable_double_buffer(self):
+        """allocate a second pyramid plane: build_plane of batch s+1 (issue-bound CUDA-core work) can then run on
+        another stream while the tensor-core convs of batch s read the first plane"""
+        if len(self.planes) == 1:
+            self.planes.append(torch.zeros_like(self.planes[0]))
+
+    def use_plane(self, slot):
+        """select the plane that the next build_plane / forward_scores calls bind (host-side pointer switch)"""
+        self.plane = self.planes[slot]
+        op = self.convs[0][0]
+        if isinstance(op, FusedConv1):
+            op.plane = self.plane
 
     def build_plane(self, frames, M):
         """frames: uint8 [M,H,W,3] device tensor -> tiled pyramid plane (RGBA u8)."""
