@@ -470,7 +470,7 @@ def main():
         if det.conv_impl in ("detconv", "rsconv") and os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            if tj.get("plane") == [det.geo.plane_h, det.geo.plane_w]:
+            if tj.get("plane") == [det.geo.plane_h, det.geo.plane_w] and tj.get("impl", "detconv") == det.conv_impl:
                 traffic = tj["detconv_dram_bytes_per_frame"] * B
         achieved = dom_fl / (dom_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
@@ -509,7 +509,8 @@ def main():
                 config=dict(workload="synthetic 1080p@25fps, batched CNN detect (upsample 1, every frame) + %d faces/frame "
                                      "68-pt landmarks + ResNet-v1 embed" % FACES_PER_FRAME,
                             frames_per_step=B, faces_per_frame=FACES_PER_FRAME, parallelism="frame-shard x%d" % world, pipeline=("pyramid of batch s+1 under the convs of batch s" if pipelined else "none"),
-                            l2="4 distinct input batches (199 MB) + >1 GB/frame of activations per step: inputs larger than L2"),
+                            l2="%d distinct input batches (%d MB) + ~1.4 GB/frame of plane and activation traffic per step: "
+                               "inputs larger than L2" % (n_sets, n_sets * B * H * W * 3 // 1000000)),
                 clocks=sampler.summary(),
                 e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps),
                 gpu_launches=int(launches), host_enqueue_ms_per_step=round(host_ms, 3),
