@@ -205,6 +205,10 @@ int pv_plane_to_pixrows(const void* rgba, void* out, int B, int H, int W, int64_
 int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, const void* w_bf16, const float* scale,
                    const float* shift, int relu, void* out, const PvRowMap* dst, int oh, int ow, const float* mean_host,
                    int* err_flag, void* stream);
+/* role timing of the last pv_conv1_fused launch when the environment variable PV_C1_DEBUG is set: out8 (HOST) =
+ * cycles summed over CTAs {MMA: wait accumulator, wait pixels, issue, tiles; converter: wait raw, wait slot, work;
+ * epilogue: wait} */
+int pv_conv1_debug(long long* out8);
 /* dlib max_pool<3,3,2,2> (pad 0) on bf16 NHWC [B,H,W,C] -> rows of `dst` */
 int pv_maxpool3x3s2(const void* in, void* out, int B, int H, int W, int C, const PvRowMap* dst, void* stream);
 /* dlib avg_pool<2,2,2,2> skip path of ares_down: parity-layout input -> skip (zero-extended to Cout)

@@ -43,7 +43,7 @@ constexpr int kRawRing = 3;
 constexpr int kPxRowBytes = (kRawW + 8) * 8;      // 264 pixels x 8 B; the 8 trailing pixels stay zero
 constexpr int kPxSlotBytes = 23296;               // 11 rows (23232 B) rounded up to 128
 constexpr int kPxRing = 2;
-constexpr int kAcc = 2;                           // tiles in flight in TMEM (kRows accumulators each)
+constexpr int kAcc = 4;                           // tiles in flight in TMEM (kRows accumulators each): 256 columns per CTA
 constexpr int kNumMma = 17;                       // per tile: 11 main + 6 pair (see the header comment)
 
 // ---- the MMA schedule of a tile (compile-time arithmetic, also run at setup to lay the weights out) ----
@@ -64,6 +64,7 @@ constexpr int kConvWarps = 8;
 // warps: 0 = TMA, 1 = MMA, 2..9 = converters, 10..13 = epilogue
 constexpr int kThreads = 32 * (2 + kConvWarps + 4);
 static_assert(kPxSlotBytes >= kInRows * kPxRowBytes, "slot too small");
+static_assert(kRows % 2 == 0, "the epilogue drains two rows per pass");
 
 struct C1Params {
   CUtensorMap raw;       // uint32 [B*Hp rows, Wp cols], box 256 x 11
@@ -80,6 +81,7 @@ struct C1Params {
   float c0, c1, c2;      // -mean/256
   int num_tiles;
   int* err;
+  long long* dbg;   // optional [grid][8] role cycle counters (PV_C1_DEBUG), nullptr = off
 };
 
 __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint32_t y, uint32_t x) {
@@ -243,29 +245,43 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
     const uint32_t w0 = pv_smem_u32(wsm);
     int slot = 0, buf = 0;
     uint32_t phase = 0, aphase = 0;
+    long long m_wt = 0, m_wf = 0, m_is = 0, m_n = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long c0 = p.dbg ? clock64() : 0;
       pv_mbar_wait(&bar_tempty[buf], aphase ^ 1u, p.err, 2);
+      const long long c1 = p.dbg ? clock64() : 0;
       pv_mbar_wait(&bar_full[slot], phase, p.err, 3);
       pv_tc_fence_after();
+      const long long c2 = p.dbg ? clock64() : 0;
       const uint32_t a0 = pv_smem_u32(pxb + slot * kPxSlotBytes);
       issue_tile<0>(a0, w0, tmem_base + (uint32_t)(buf * kRows * kN), idesc0, lead);
       pv_umma_commit_pred(&bar_empty[slot], lead);
       pv_umma_commit_pred(&bar_tfull[buf], lead);
       if (++slot == kPxRing) { slot = 0; phase ^= 1u; }
       if (++buf == kAcc) { buf = 0; aphase ^= 1u; }
+      if (p.dbg) { m_wt += c1 - c0; m_wf += c2 - c1; m_is += clock64() - c2; ++m_n; }
+    }
+    if (p.dbg && lead) {
+      long long* d = p.dbg + (long long)blockIdx.x * 8;
+      d[0] = m_wt; d[1] = m_wf; d[2] = m_is; d[3] = m_n;
     }
   } else if (warp < 2 + kConvWarps) {
     // ===================== converters: every raw pixel -> bf16 RGB0, once =====================
     const int ct = threadIdx.x - 64;               // pixel column 0..255 of the block
     int rs = 0, slot = 0;
     uint32_t rphase = 0, phase = 0;
+    long long k_wr = 0, k_we = 0, k_work = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long k0 = p.dbg ? clock64() : 0;
       pv_mbar_wait(&bar_rfull[rs], rphase, p.err, 5);
+      const long long k1 = p.dbg ? clock64() : 0;
       const uint32_t* rb = reinterpret_cast<const uint32_t*>(raw + rs * kRawBytes) + ct;
       uint32_t v[kInRows];
 #pragma unroll
       for (int kh = 0; kh < kInRows; ++kh) v[kh] = rb[kh * kRawW];
+      const long long k2 = p.dbg ? clock64() : 0;
       pv_mbar_wait(&bar_empty[slot], phase ^ 1u, p.err, 6);
+      const long long k3 = p.dbg ? clock64() : 0;
       uint8_t* dstp = pxb + slot * kPxSlotBytes + ct * 8;
 #pragma unroll
       for (int kh = 0; kh < kInRows; ++kh) {
@@ -287,6 +303,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
       }
       if (++rs == kRawRing) { rs = 0; rphase ^= 1u; }
       if (++slot == kPxRing) { slot = 0; phase ^= 1u; }
+      if (p.dbg) { k_wr += k1 - k0; k_we += k3 - k2; k_work += (k2 - k1) + (clock64() - k3); }
+    }
+    if (p.dbg && threadIdx.x == 64) {
+      long long* d = p.dbg + (long long)blockIdx.x * 8;
+      d[4] = k_wr; d[5] = k_we; d[6] = k_work;
     }
   } else {
     // ===================== epilogue =====================
@@ -300,38 +321,42 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
       const uint32_t x = t.ct * kTileOut + m;
       const bool xvalid = (m < (uint32_t)kTileOut) && (x < (uint32_t)p.ow);
       const uint32_t oy0 = t.oy * kRows;
+      const long long q0 = p.dbg ? clock64() : 0;
       pv_mbar_wait_backoff(&bar_tfull[buf], aphase, p.err, 4, 32);
       pv_tc_fence_after();
+      if (p.dbg && threadIdx.x == 320) p.dbg[(long long)blockIdx.x * 8 + 7] += clock64() - q0;
+      // two rows per pass: two TMEM loads in flight, scale / shift come from shared memory as 16-byte ld.shared
+      const uint32_t sc_addr = pv_smem_u32(s_scale), sh_addr = pv_smem_u32(s_shift);
 #pragma unroll 1
-      for (int r = 0; r < kRows; ++r) {
-        uint32_t v[16];
-        pv_tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * kRows + r) * kN), v);
+      for (int r = 0; r < kRows; r += 2) {
+        uint32_t v[2][16];
+        const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * kRows + r) * kN);
+        pv_tmem_ld16(tcol, v[0]);
+        pv_tmem_ld16(tcol + kN, v[1]);
         pv_tmem_ld_wait();
-        if (r == kRows - 1) {
+        if (r == kRows - 2) {
           pv_tc_fence_before();
           __syncwarp();
-          if (lane == 0) pv_mbar_arrive(&bar_tempty[buf]);   // last accumulator is in registers: release the buffer
+          if (lane == 0) pv_mbar_arrive(&bar_tempty[buf]);   // last accumulators are in registers: release the buffer
         }
-        if (xvalid && oy0 + r < (uint32_t)p.oh) {
-          const long long drow = row_of(p.dst, t.n, oy0 + r, x);
-          float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[j] = fmaf(__uint_as_float(v[j]), s_scale[j], s_shift[j]);
-            if (p.relu) f[j] = fmaxf(f[j], 0.f);
+        for (int h = 0; h < 2; ++h) {
+          if (xvalid && oy0 + r + h < (uint32_t)p.oh) {
+            const long long drow = row_of(p.dst, t.n, oy0 + r + h, x);
+            uint32_t o[8];
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const uint4 sc = pv_lds128(sc_addr + g4 * 16), sh = pv_lds128(sh_addr + g4 * 16);
+              float f0 = fmaf(__uint_as_float(v[h][4 * g4 + 0]), __uint_as_float(sc.x), __uint_as_float(sh.x));
+              float f1 = fmaf(__uint_as_float(v[h][4 * g4 + 1]), __uint_as_float(sc.y), __uint_as_float(sh.y));
+              float f2 = fmaf(__uint_as_float(v[h][4 * g4 + 2]), __uint_as_float(sc.z), __uint_as_float(sh.z));
+              float f3 = fmaf(__uint_as_float(v[h][4 * g4 + 3]), __uint_as_float(sc.w), __uint_as_float(sh.w));
+              if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+              o[2 * g4] = pv_pack_bf16x2(f0, f1);
+              o[2 * g4 + 1] = pv_pack_bf16x2(f2, f3);
+            }
+            pv_stg256(p.out + drow * p.dst.cols, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
           }
-          uint4 o0, o1;
-          o0.x = pv_pack_bf16x2(f[0], f[1]);
-          o0.y = pv_pack_bf16x2(f[2], f[3]);
-          o0.z = pv_pack_bf16x2(f[4], f[5]);
-          o0.w = pv_pack_bf16x2(f[6], f[7]);
-          o1.x = pv_pack_bf16x2(f[8], f[9]);
-          o1.y = pv_pack_bf16x2(f[10], f[11]);
-          o1.z = pv_pack_bf16x2(f[12], f[13]);
-          o1.w = pv_pack_bf16x2(f[14], f[15]);
-          uint4* dp = reinterpret_cast<uint4*>(p.out + drow * p.dst.cols);
-          dp[0] = o0;
-          dp[1] = o1;
         }
       }
       if (++buf == kAcc) { buf = 0; aphase ^= 1u; }
@@ -353,13 +378,28 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+long long* g_c1_dbg = nullptr;
+
 }  // namespace
+
+/* role timing of the last pv_conv1_fused launch when PV_C1_DEBUG is set: out8 (HOST) = cycles summed over CTAs
+ * {MMA: wait accumulator, wait pixels, issue, tiles; converter: wait raw, wait slot, work; epilogue: wait} */
+extern "C" int pv_conv1_debug(long long* out8) {
+  PV_REQUIRE(out8 && g_c1_dbg, "pv_conv1_debug: PV_C1_DEBUG was not set");
+  static long long h[8 * 1024];
+  PV_CUDA_CHECK(cudaMemcpy(h, g_c1_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 8; ++k) out8[k] = 0;
+  for (int i = 0; i < 1024; ++i)
+    for (int k = 0; k < 8; ++k) out8[k] += h[8 * i + k];
+  return PV_OK;
+}
 
 extern "C" int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, const void* w_bf16, const float* scale,
                               const float* shift, int relu, void* out, const PvRowMap* dst, int oh, int ow,
                               const float* mean_host, int* err_flag, void* stream) {
   PV_REQUIRE(plane_rgba && w_bf16 && scale && shift && out && dst && mean_host && err_flag, "pv_conv1_fused: null argument");
-  PV_REQUIRE(dst->cols >= kN && dst->cols % 8 == 0, "pv_conv1_fused: dst.cols=%d", dst->cols);
+  PV_REQUIRE(dst->cols >= kN && dst->cols % 16 == 0, "pv_conv1_fused: dst.cols=%d (rows are written with 32-byte stores)", dst->cols);
+  PV_REQUIRE((reinterpret_cast<uintptr_t>(out) & 31) == 0, "pv_conv1_fused: output must be 32-byte aligned");
   PV_REQUIRE(B > 0 && Hp >= kKH && Wp >= 5 && oh > 0 && ow > 0, "pv_conv1_fused: bad extent B=%d Hp=%d Wp=%d", B, Hp, Wp);
   PV_REQUIRE(2 * (oh - 1) + kKH <= Hp && 2 * (ow - 1) + 5 <= Wp, "pv_conv1_fused: output %dx%d does not fit plane %dx%d", oh, ow, Hp, Wp);
   PV_REQUIRE(Wp % 4 == 0, "pv_conv1_fused: plane width %d must be a multiple of 4 pixels (16-byte TMA row pitch)", Wp);
@@ -411,6 +451,11 @@ extern "C" int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, con
   PV_REQUIRE(nt < (1ll << 31), "pv_conv1_fused: too many tiles");
   p.num_tiles = (int)nt;
   p.err = err_flag;
+  static long long* d_dbg = nullptr;
+  if (getenv("PV_C1_DEBUG") && !d_dbg) cudaMalloc(&d_dbg, sizeof(long long) * 8 * 1024);
+  if (d_dbg) cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 8 * 1024, static_cast<cudaStream_t>(stream));
+  p.dbg = d_dbg;
+  g_c1_dbg = d_dbg;
   int grid = num_sms * 2;
   if (grid > p.num_tiles) grid = p.num_tiles;
   conv1_fused_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);

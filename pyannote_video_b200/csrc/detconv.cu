@@ -279,24 +279,15 @@ __global__ void __launch_bounds__(kThreads, 1) detconv_kernel(const __grid_const
             if (p.relu) f[k] = fmaxf(f[k], 0.f);
           }
           if (F32) {
-            float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cs + j * 16);
-            dp[0] = make_float4(f[0], f[1], f[2], f[3]);
-            dp[1] = make_float4(f[4], f[5], f[6], f[7]);
-            dp[2] = make_float4(f[8], f[9], f[10], f[11]);
-            dp[3] = make_float4(f[12], f[13], f[14], f[15]);
+            float* dp = reinterpret_cast<float*>(p.out) + pix * p.out_cs + j * 16;
+            pv_stg256(dp, __float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]),
+                      __float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7]));
+            pv_stg256(dp + 8, __float_as_uint(f[8]), __float_as_uint(f[9]), __float_as_uint(f[10]), __float_as_uint(f[11]),
+                      __float_as_uint(f[12]), __float_as_uint(f[13]), __float_as_uint(f[14]), __float_as_uint(f[15]));
           } else {
-            uint4 o0, o1;
-            o0.x = pv_pack_bf16x2(f[0], f[1]);
-            o0.y = pv_pack_bf16x2(f[2], f[3]);
-            o0.z = pv_pack_bf16x2(f[4], f[5]);
-            o0.w = pv_pack_bf16x2(f[6], f[7]);
-            o1.x = pv_pack_bf16x2(f[8], f[9]);
-            o1.y = pv_pack_bf16x2(f[10], f[11]);
-            o1.z = pv_pack_bf16x2(f[12], f[13]);
-            o1.w = pv_pack_bf16x2(f[14], f[15]);
-            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + j * 16);
-            dp[0] = o0;
-            dp[1] = o1;
+            pv_stg256(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + j * 16, pv_pack_bf16x2(f[0], f[1]),
+                      pv_pack_bf16x2(f[2], f[3]), pv_pack_bf16x2(f[4], f[5]), pv_pack_bf16x2(f[6], f[7]), pv_pack_bf16x2(f[8], f[9]),
+                      pv_pack_bf16x2(f[10], f[11]), pv_pack_bf16x2(f[12], f[13]), pv_pack_bf16x2(f[14], f[15]));
           }
         }
       }
@@ -389,10 +380,10 @@ extern "C" int pv_detconv_create(const PvDetconvDesc* d, void** out_handle) {
   const int pad_y = in.S == 1 ? in.KH / 2 : 0, pad_x = in.S == 1 ? in.KW / 2 : 0;
   const int OH = (d->H + 2 * pad_y - in.KH) / in.S + 1, OW = (d->W + 2 * pad_x - in.KW) / in.S + 1;
   PV_REQUIRE(OH > 0 && OW > 0, "pv_detconv_create: empty output");
-  PV_REQUIRE(d->out_pitch >= OW && d->out_cs >= in.N && d->out_cs % 8 == 0, "pv_detconv_create: output pitch %d / channel stride %d",
+  PV_REQUIRE(d->out_pitch >= OW && d->out_cs >= in.N && d->out_cs % 16 == 0, "pv_detconv_create: output pitch %d / channel stride %d (rows are written with 32-byte stores)",
              d->out_pitch, d->out_cs);
   PV_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w_img) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "pv_detconv_create: operands must be 16-byte aligned");
+                 (reinterpret_cast<uintptr_t>(d->out) & 31) == 0, "pv_detconv_create: operands must be 16-byte (output: 32-byte) aligned");
   const int kch = in.C / 16;
   const uint32_t w_bytes = (uint32_t)(in.KH * in.KW * kch * in.N * 32);
   PV_REQUIRE(d->w_bytes == (int64_t)w_bytes, "pv_detconv_create: weight image is %lld bytes, expected %u", (long long)d->w_bytes, w_bytes);

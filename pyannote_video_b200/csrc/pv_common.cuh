@@ -234,6 +234,15 @@ __device__ __forceinline__ uint64_t pv_umma_desc(uint32_t smem_addr, uint32_t sb
   return d;
 }
 
+// one 256-bit global store (STG.E.256, sm_100+): a lane's 32 bytes leave as ONE full sector instead of two half-sector
+// 128-bit stores (the epilogues write 32 / 64 / 96 bytes per pixel with lanes on neighbouring pixels)
+__device__ __forceinline__ void pv_stg256(void* gptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                          uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+               "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t pv_pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

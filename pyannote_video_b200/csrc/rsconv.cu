@@ -374,24 +374,15 @@ __global__ void __launch_bounds__(kThreads, (NC <= 32 ? 2 : 1)) rsconv_kernel(co
               if (p.relu) f[k] = fmaxf(f[k], 0.f);
             }
             if (F32) {
-              float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cs + j * 16);
-              dp[0] = make_float4(f[0], f[1], f[2], f[3]);
-              dp[1] = make_float4(f[4], f[5], f[6], f[7]);
-              dp[2] = make_float4(f[8], f[9], f[10], f[11]);
-              dp[3] = make_float4(f[12], f[13], f[14], f[15]);
+              float* dp = reinterpret_cast<float*>(p.out) + pix * p.out_cs + j * 16;
+              pv_stg256(dp, __float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]),
+                        __float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7]));
+              pv_stg256(dp + 8, __float_as_uint(f[8]), __float_as_uint(f[9]), __float_as_uint(f[10]), __float_as_uint(f[11]),
+                        __float_as_uint(f[12]), __float_as_uint(f[13]), __float_as_uint(f[14]), __float_as_uint(f[15]));
             } else {
-              uint4 o0, o1;
-              o0.x = pv_pack_bf16x2(f[0], f[1]);
-              o0.y = pv_pack_bf16x2(f[2], f[3]);
-              o0.z = pv_pack_bf16x2(f[4], f[5]);
-              o0.w = pv_pack_bf16x2(f[6], f[7]);
-              o1.x = pv_pack_bf16x2(f[8], f[9]);
-              o1.y = pv_pack_bf16x2(f[10], f[11]);
-              o1.z = pv_pack_bf16x2(f[12], f[13]);
-              o1.w = pv_pack_bf16x2(f[14], f[15]);
-              uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + j * 16);
-              dp[0] = o0;
-              dp[1] = o1;
+              pv_stg256(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + j * 16, pv_pack_bf16x2(f[0], f[1]),
+                        pv_pack_bf16x2(f[2], f[3]), pv_pack_bf16x2(f[4], f[5]), pv_pack_bf16x2(f[6], f[7]), pv_pack_bf16x2(f[8], f[9]),
+                        pv_pack_bf16x2(f[10], f[11]), pv_pack_bf16x2(f[12], f[13]), pv_pack_bf16x2(f[14], f[15]));
             }
           }
         }
@@ -496,10 +487,10 @@ extern "C" int pv_rsconv_create(const PvDetconvDesc* d, void** out_handle) {
   const int pad_y = in.S == 1 ? in.KH / 2 : 0, pad_x = in.S == 1 ? in.KW / 2 : 0;
   const int OH = (d->H + 2 * pad_y - in.KH) / in.S + 1, OW = (d->W + 2 * pad_x - in.KW) / in.S + 1;
   PV_REQUIRE(OH > 0 && OW > 0, "pv_rsconv_create: empty output");
-  PV_REQUIRE(d->out_pitch >= OW && d->out_cs >= in.N && d->out_cs % 8 == 0, "pv_rsconv_create: output pitch %d / channel stride %d",
+  PV_REQUIRE(d->out_pitch >= OW && d->out_cs >= in.N && d->out_cs % 16 == 0, "pv_rsconv_create: output pitch %d / channel stride %d (rows are written with 32-byte stores)",
              d->out_pitch, d->out_cs);
   PV_REQUIRE((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w_img) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "pv_rsconv_create: operands must be 16-byte aligned");
+                 (reinterpret_cast<uintptr_t>(d->out) & 31) == 0, "pv_rsconv_create: operands must be 16-byte (output: 32-byte) aligned");
   int aw, rowel0, rowel1, stage_bytes, w_bytes, ctas;
   switch (kind) {
     case 0: rs_geometry<16, 32, 5, 5, 2>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
@@ -572,18 +563,29 @@ extern "C" int pv_rsconv_create(const PvDetconvDesc* d, void** out_handle) {
   p.out_pitch = d->out_pitch;
   p.out_cs = d->out_cs;
   p.strips = (OW + kTileW - 1) / kTileW;
-  // rows per work item: enough items for ~8 per SM at the full batch, at least 8 rows (halo rows cost little:
-  // their MMAs are narrower, only their A reads are extra)
+  // rows per work item: items are dealt round-robin to the persistent CTAs, so the launch lasts as long as the CTA
+  // with the most items; pick the segment height that minimises  ceil(items / CTAs) x (input rows per item)
+  // among heights whose halo (KH - 1 extra input rows) stays below ~25 % of the item
   {
-    const long long want = 8ll * plan->num_sms * ctas;
-    long long per_col = (want + (long long)d->B * p.strips - 1) / ((long long)d->B * p.strips);   // segments wanted per strip
-    if (per_col < 1) per_col = 1;
-    int rows = (int)((OH + per_col - 1) / per_col);
-    const int min_rows = 4 * ((in.KH - 1) / in.S) > 8 ? 4 * ((in.KH - 1) / in.S) : 8;   // halo rows <= 25 % of an item
-    if (rows < min_rows) rows = min_rows;
-    if (rows > OH) rows = OH;
-    p.seg_rows = rows;
-    p.segs = (OH + rows - 1) / rows;
+    const int grid_max = plan->num_sms * ctas;
+    const int halo = in.KH - 1;
+    const int min_rows = 4 * (halo / in.S) > 8 ? 4 * (halo / in.S) : 8;
+    long long best_cost = -1;
+    int best_rows = OH;
+    for (int segs = 1; segs <= OH; ++segs) {
+      const int rows = (OH + segs - 1) / segs;
+      if (rows < min_rows && segs > 1) break;
+      const int nseg = (OH + rows - 1) / rows;
+      const long long items = (long long)d->B * nseg * p.strips;
+      const long long waves = (items + grid_max - 1) / grid_max;
+      const long long cost = waves * ((long long)rows * in.S + halo);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_rows = rows;
+      }
+    }
+    p.seg_rows = best_rows;
+    p.segs = (OH + best_rows - 1) / best_rows;
   }
   p.relu = d->relu;
   p.n_stages = n_stages;

@@ -72,6 +72,17 @@ def main():
             dbg[n] = dict(rows=a[3], wait_slot=round(a[0] / rows), wait_data=round(a[1] / rows), issue=round(a[2] / rows),
                           epi_wait=round(a[4] / rows), epi_work=round(a[5] / rows), total_per_row=round(a[6] / rows))
         out["rs_debug_cycles_per_input_row"] = dbg
+    if os.environ.get("PV_C1_DEBUG") and det.conv1_mode == "fused":
+        import ctypes as C
+        from pyannote_video_b200 import _lib
+        det.convs[0][0].run(B * det.convs[0][1])
+        torch.cuda.synchronize()
+        a = (C.c_longlong * 8)()
+        _lib.check(_lib.lib().pv_conv1_debug(a), "pv_conv1_debug")
+        t = max(1, a[3])
+        out["c1_debug_cycles_per_tile"] = dict(tiles=a[3], mma_wait_acc=round(a[0] / t), mma_wait_px=round(a[1] / t), mma_issue=round(a[2] / t),
+                                               conv_wait_raw=round(a[4] / t), conv_wait_slot=round(a[5] / t), conv_work=round(a[6] / t),
+                                               epi_wait=round(a[7] / t))
     out["mode"] = det.conv1_mode
     out["frames"] = B
     out["unit"] = "us"

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_golden_gpu.py tests/test_detconv_gpu.py tests/test_nets_gpu.py -m gpu -q -x > gpurun_out/pytest_b.log 2>&1; echo "pytest rc=$?"
+grep -E "passed|failed|Error|assert" gpurun_out/pytest_b.log | tail -6
+timeout 300 python scripts/gpu_probe_det.py --frames 8 2>&1 | tail -1
+timeout 300 python scripts/gpu_probe_det.py --frames 16 2>&1 | tail -1
+timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_n1.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print({k:d[k] for k in ('value','ms_per_step','host_enqueue_ms_per_step')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['traffic'], d['roofline']['all_convs'], d['roofline']['stage_ms_per_step'])"

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_golden_gpu.py tests/test_nets_gpu.py -m gpu -q -x -k "golden or detector" > gpurun_out/pytest_c.log 2>&1; echo "pytest rc=$?"
+grep -E "passed|failed|Error|assert" gpurun_out/pytest_c.log | tail -4
+PV_C1_DEBUG=1 timeout 300 python scripts/gpu_probe_det.py --frames 8 --reps 2 2>&1 | tail -1
+timeout 300 python scripts/gpu_probe_det.py --frames 8 2>&1 | tail -1
