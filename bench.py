@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 H, W = 1080, 1920
 FACES_PER_FRAME = 4
 METRIC = "frames/sec detect+track+embed on 1080p"
+WORKLOAD = ("synthetic 1080p@25fps, batched CNN detect (upsample 1, every frame) + %d faces/frame 68-pt landmarks + "
+            "ResNet-v1 embed" % 4)
 
 
 def load_peaks():
@@ -127,8 +129,8 @@ def run_reference(args, rank, world):
     line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=steps, warmup=warm,
                 ms_per_step=1000.0 * el / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload="synthetic 1080p, CNN detect (upsample 1) + %d faces/frame landmarks+embed" % FACES_PER_FRAME,
-                            frames_per_step=n_per_step, faces_per_frame=FACES_PER_FRAME),
+                config=dict(workload=WORKLOAD, frames_per_step=n_per_step, faces_per_frame=FACES_PER_FRAME,
+                            sample="each step = one 1080p frame of the same workload through the CPU restatement"),
                 cpu_baseline=dict(value=fps, unit="frames/s", cores=cores, kind="port",
                                   sample="%d x 1080p frame(s), oracle restatement (torch-CPU fp32 convs + numpy)" % steps),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -506,9 +508,7 @@ def main():
     line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                 data="synthetic",
-                config=dict(workload="synthetic 1080p@25fps, batched CNN detect (upsample 1, every frame) + %d faces/frame "
-                                     "68-pt landmarks + ResNet-v1 embed" % FACES_PER_FRAME,
-                            frames_per_step=B, faces_per_frame=FACES_PER_FRAME, parallelism="frame-shard x%d" % world, pipeline=("pyramid of batch s+1 under the convs of batch s" if pipelined else "none"),
+                config=dict(workload=WORKLOAD, frames_per_step=B, faces_per_frame=FACES_PER_FRAME, parallelism="frame-shard x%d" % world, pipeline=("pyramid of batch s+1 under the convs of batch s" if pipelined else "none"),
                             l2="%d distinct input batches (%d MB) + ~1.4 GB/frame of plane and activation traffic per step: "
                                "inputs larger than L2" % (n_sets, n_sets * B * H * W * 3 // 1000000)),
                 clocks=sampler.summary(),

@@ -237,9 +237,15 @@ __device__ void target_hat(Smem& s, const TrackerTables& tb, float px, float py)
 }
 
 template <bool START>
-__global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const __grid_constant__ TrackerTables tb) {
+__global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const __grid_constant__ TrackerTables tbc) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem s = carve(smem_raw);
+  // the tables are indexed per lane (twiddles, window): from the constant bank every distinct index of a warp is a
+  // replay, so they are copied to shared memory once
+  __shared__ TrackerTables tb;
+  for (int i = threadIdx.x; i < (int)(sizeof(TrackerTables) / 4); i += kThreads)
+    reinterpret_cast<uint32_t*>(&tb)[i] = reinterpret_cast<const uint32_t*>(&tbc)[i];
+  __syncthreads();
   __shared__ float tf[4];
   __shared__ float peak[4];  // ppx, ppy
   const int tid = threadIdx.x;
@@ -465,8 +471,12 @@ struct ScaleParams {
 __device__ __forceinline__ int rev5(int v) { return (int)(__brev((unsigned)v) >> 27); }
 
 template <bool START>
-__global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, const __grid_constant__ ScaleTables tb) {
+__global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, const __grid_constant__ ScaleTables tbc) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ ScaleTables tb;        // per-lane indexed tables: shared memory, not the constant bank (see tracker_kernel)
+  for (int i = threadIdx.x; i < (int)(sizeof(ScaleTables) / 4); i += kThreads)
+    reinterpret_cast<uint32_t*>(&tb)[i] = reinterpret_cast<const uint32_t*>(&tbc)[i];
+  __syncthreads();
   float2* Z = reinterpret_cast<float2*>(smem_raw);                 // [SF][ZP]
   float* s_mag = reinterpret_cast<float*>(Z + SF * ZP);             // [SW*SW]
   float* s_hist = s_mag + SW * SW;                                  // [36*18]
