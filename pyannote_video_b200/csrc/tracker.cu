@@ -488,7 +488,18 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
   __shared__ double s_rre[NS], s_rim[NS];
   __shared__ float s_resp[NS];
   __shared__ float s_peak;
+  __shared__ int s_cwi[SW];                 // FHOG cell-4 bilinear weights of pixel coordinate c:
+  __shared__ float s_cw0[SW], s_cw1[SW];    //   cp = (c + 0.5)/4 - 0.5, s_cwi = floor(cp), s_cw0 = cp - floor(cp), s_cw1 = 1 - s_cw0
   const int tid = threadIdx.x;
+  if (tid < SW) {
+    const float cp = __fsub_rn(__fdiv_rn(__fadd_rn((float)tid, 0.5f), 4.0f), 0.5f);
+    const int icp = (int)floorf(cp);
+    const float v0 = __fsub_rn(cp, (float)icp);
+    s_cwi[tid] = icp;
+    s_cw0[tid] = v0;
+    s_cw1[tid] = __fsub_rn(1.0f, v0);
+  }
+  __syncthreads();
   const int slot = p.ids[blockIdx.x];
   float2* As = p.As + (size_t)slot * SF * NS;
   float* Bs = p.Bs + (size_t)slot * NS;
@@ -550,6 +561,8 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
     }
     __syncthreads();
     // ---- cell histograms: every (cell, orientation) bin gathers its pixels in raster order ----
+    // (the bilinear cell weights depend on the pixel coordinate only: s_cw* tables, computed once per launch —
+    // two IEEE divisions per pixel visit were 80 % of this kernel's instructions)
     for (int bi = tid; bi < SCELLS * SCELLS * 18; bi += kThreads) {
       const int o = bi % 18, cell = bi / 18;
       const int cyi = cell / SCELLS, cxi = cell - cyi * SCELLS;
@@ -557,18 +570,14 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
       const int y0 = max(1, 4 * cyi - 2), y1 = min(SW - 2, 4 * cyi + 5);
       const int x0 = max(1, 4 * cxi - 2), x1 = min(SW - 2, 4 * cxi + 5);
       for (int y = y0; y <= y1; ++y) {
-        const float yp = __fsub_rn(__fdiv_rn(__fadd_rn((float)y, 0.5f), 4.0f), 0.5f);
-        const int iyp = (int)floorf(yp);
-        const float vy0 = __fsub_rn(yp, (float)iyp), vy1 = __fsub_rn(1.0f, vy0);
+        const int iyp = s_cwi[y];
         float wy;
-        if (iyp == cyi) wy = vy1; else if (iyp + 1 == cyi) wy = vy0; else continue;
+        if (iyp == cyi) wy = s_cw1[y]; else if (iyp + 1 == cyi) wy = s_cw0[y]; else continue;
         for (int x = x0; x <= x1; ++x) {
           if (s_ori[y * SW + x] != o) continue;
-          const float xp = __fsub_rn(__fdiv_rn(__fadd_rn((float)x, 0.5f), 4.0f), 0.5f);
-          const int ixp = (int)floorf(xp);
-          const float vx0 = __fsub_rn(xp, (float)ixp), vx1 = __fsub_rn(1.0f, vx0);
+          const int ixp = s_cwi[x];
           float wx;
-          if (ixp == cxi) wx = vx1; else if (ixp + 1 == cxi) wx = vx0; else continue;
+          if (ixp == cxi) wx = s_cw1[x]; else if (ixp + 1 == cxi) wx = s_cw0[x]; else continue;
           acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wx, wy), s_mag[y * SW + x]));
         }
       }

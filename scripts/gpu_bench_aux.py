@@ -73,10 +73,13 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=200)
     ap.add_argument("--n", type=int, default=100000)
+    ap.add_argument("--only", default="", help="tracker | cluster")
     a = ap.parse_args()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "aux_bench.jsonl"), "a") as f:
         for fn, arg in ((bench_tracker, a.frames), (bench_cluster, a.n)):
+            if a.only and a.only not in fn.__name__:
+                continue
             try:
                 r = fn(arg)
             except Exception as e:  # noqa: BLE001
