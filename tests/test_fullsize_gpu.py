@@ -71,3 +71,46 @@ def test_c2_full_1080p_detector_is_deterministic_and_batch_independent(cuda):
     assert torch.equal(s1[0], s2[1])
     # plane borders (padding) are zero in the conv1 input and stay zero
     assert int(net.plane[0, :11].max()) == 0 and int(net.plane[0, :, :11].max()) == 0
+
+
+def test_c2_full_1080p_three_conv_implementations_agree(cuda):
+    """at full size the CPU oracle is too slow, but the three independent tensor-core formulations of the detector
+    convs (row streaming, 2-D tiles, 1-D shifted rows) must produce the same score map up to fp32 summation order"""
+    from pyannote_video_b200 import weights as W
+    from pyannote_video_b200.nets import DetectorNet
+    model = W.make_detector(seed=2, score_bias=0.0)
+    frames = make_frames(1, 1080, 1920, seed=3, device=cuda)
+    ref = None
+    for impl in ("rsconv", "detconv", "srgemm"):
+        net = DetectorNet(model, 1080, 1920, 1, max_batch=1, device=cuda, conv_impl=impl)
+        net.build_plane(frames, 1)
+        s = net.forward_scores(1).clone()
+        net.check()
+        assert torch.isfinite(s).all()
+        if ref is None:
+            ref = s
+        else:
+            d = float((s - ref).abs().max())
+            assert d < 0.02 * max(1.0, float(ref.abs().max())), (impl, d)
+        del net
+        torch.cuda.empty_cache()
+
+
+def test_c4_one_4k_frame_through_the_detector(cuda):
+    """BASELINE.json configs[3] frame size (3840x2160, upsample 1: a 6852 x 16760 plane, 108 M pyramid pixels):
+    index arithmetic at the largest size, determinism, zero borders"""
+    from pyannote_video_b200 import weights as W
+    from pyannote_video_b200.nets import DetectorNet
+    model = W.make_detector(seed=2)          # score bias -3: few candidates (with bias 0 decode reports overflow as a negative count)
+    frames = make_frames(1, 2160, 3840, seed=1, device=cuda)
+    net = DetectorNet(model, 2160, 3840, 1, max_batch=1, device=cuda)
+    net.build_plane(frames, 1)
+    a = net.forward_scores(1).clone()
+    net.check()
+    net.build_plane(frames, 1)
+    b = net.forward_scores(1).clone()
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    assert a.shape[1:] == (net.OH, net.OW)
+    boxes, scores, counts = net.decode(1)
+    assert 0 <= int(counts[0]) <= net.MAX_DET
+    assert int(net.plane[0, :11].max()) == 0 and int(net.plane[0, -11:].max()) == 0
