@@ -2,7 +2,7 @@
 """bench.py — frames/sec of the face hot path (CNN detect -> 68-pt landmarks -> chip -> ResNet embed)
 on synthetic 1080p, BASELINE.json configs[1], on N GPUs of one node.
 
-    python bench.py --gpus 1 --steps 125 --warmup 3
+    python bench.py --gpus 1 --steps 60 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
            --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the CPU restatement of the reference's dlib path
@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=16)
+    ap.add_argument("--frames-per-step", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-convs", type=int, default=2, help="instrumented steps for the roofline leg")
     ap.add_argument("--pipeline", action="store_true",
