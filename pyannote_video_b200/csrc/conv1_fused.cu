@@ -39,7 +39,7 @@ constexpr int kRows = 4;                          // output rows per tile
 constexpr int kInRows = 2 * kRows + 3;            // 11 input rows
 constexpr int kRawW = 256;                        // pixels per raw row (TMA box)
 constexpr int kRawBytes = kInRows * kRawW * 4;    // 11 KB
-constexpr int kRawRing = 3;
+constexpr int kRawRing = 4;
 constexpr int kPxRowBytes = (kRawW + 8) * 8;      // 264 pixels x 8 B; the 8 trailing pixels stay zero
 constexpr int kPxSlotBytes = 23296;               // 11 rows (23232 B) rounded up to 128
 constexpr int kPxRing = 2;
@@ -67,7 +67,9 @@ static_assert(kPxSlotBytes >= kInRows * kPxRowBytes, "slot too small");
 static_assert(kRows % 2 == 0, "the epilogue drains two rows per pass");
 
 struct C1Params {
-  CUtensorMap raw;       // uint32 [B*Hp rows, Wp cols], box 256 x 11
+  CUtensorMap raw;       // uint32 [B*Hp rows, Wp cols], box 256 x 11 (default)
+  const uint32_t* plane; // the same plane for the direct-load variant (PV_C1_TMA=0)
+  int use_tma;
   int B, Hp, Wp;
   int oh, ow;            // valid output extent
   int oh_tiles;          // ceil(oh / kRows)
@@ -82,6 +84,9 @@ struct C1Params {
   int num_tiles;
   int* err;
   long long* dbg;   // optional [grid][8] role cycle counters (PV_C1_DEBUG), nullptr = off
+  int ablate;       // PV_C1_ABLATE (probe only, results become wrong): 1 no output stores, 2 no epilogue math/stores,
+                    // 4 converters store without converting, 8 only the two opening MMAs per tile, 16 converters do not store,
+                    // 32 no fence.proxy.async, 64 epilogue does not read TMEM, 128 no nanosleep back-off in the producer / epilogue waits
 };
 
 __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint32_t y, uint32_t x) {
@@ -115,6 +120,11 @@ struct TileWalk {
   }
 };
 
+__device__ __forceinline__ void c1_prefetch_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // un-swizzled K-major operand: start address, LBO = byte step between the two 8-element K chunks,
 // SBO = byte step between 8-row groups (cute::UMMA::SmemDescriptor, LayoutType::INTERLEAVE; version 1)
 __device__ __forceinline__ uint64_t desc_kmajor_plain(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -128,7 +138,8 @@ __device__ __forceinline__ uint64_t desc_kmajor_plain(uint32_t smem_addr, uint32
 
 // the 17 MMAs of a tile, schedule entries forced to compile-time constants (template recursion)
 template <int E>
-__device__ __forceinline__ void issue_tile(uint32_t a0, uint32_t w0, uint32_t tmem_tile, uint32_t idesc0, uint32_t lead) {
+__device__ __forceinline__ void issue_tile(uint32_t a0, uint32_t w0, uint32_t tmem_tile, uint32_t idesc0, uint32_t lead,
+                                           uint32_t lead_rest) {
   if constexpr (E < kNumMma) {
     constexpr int i0 = ent_row(E), N = ent_n(E), rlo = ent_rlo(E), boff = ent_boff(E);
     constexpr bool pair = ent_pair(E);
@@ -137,8 +148,9 @@ __device__ __forceinline__ void issue_tile(uint32_t a0, uint32_t w0, uint32_t tm
     constexpr uint32_t a_lbo = pair ? (i0 + 1 < kInRows ? (uint32_t)kPxRowBytes : 16u) : 16u;
     const uint64_t ad = desc_kmajor_plain(a0 + a_off, a_lbo, 128u);
     const uint64_t bd = desc_kmajor_plain(w0 + (uint32_t)boff, (uint32_t)(N * 16), 128u);
-    pv_umma_bf16_pred(tmem_tile + (uint32_t)(rlo * kN), ad, bd, idesc0 | ((uint32_t)(N >> 3) << 17), E >= 2 ? 1u : 0u, lead);
-    issue_tile<E + 1>(a0, w0, tmem_tile, idesc0, lead);
+    pv_umma_bf16_pred(tmem_tile + (uint32_t)(rlo * kN), ad, bd, idesc0 | ((uint32_t)(N >> 3) << 17), E >= 2 ? 1u : 0u,
+                      E >= 2 ? lead_rest : lead);
+    issue_tile<E + 1>(a0, w0, tmem_tile, idesc0, lead, lead_rest);
   }
 }
 
@@ -223,14 +235,29 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0) {
-    // ===================== TMA: raw pixel blocks =====================
-    if (pv_elect_one()) {
-      TileWalk t;
+    // ===================== TMA: raw pixel blocks (PV_C1_TMA=1 only) =====================
+    if (p.use_tma && pv_elect_one()) {
+      TileWalk t, tp;
       t.init(p, blockIdx.x, gridDim.x);
+      // the plane streams from HBM once: an L2 prefetch runs kPrefetch tiles ahead of the shared-memory ring so that
+      // the ring's loads find their lines in L2 (ablation probe: the bare pipeline was paced by load latency)
+      constexpr int kPrefetch = 8;
+      tp.init(p, blockIdx.x, gridDim.x);
+      int ahead = blockIdx.x;
+      for (int k = 0; k < kPrefetch && ahead < p.num_tiles; ++k, ahead += gridDim.x) {
+        if (k >= kRawRing) c1_prefetch_2d(&p.raw, (int32_t)(2 * kTileOut * tp.ct), (int32_t)(tp.n * (uint32_t)p.Hp + 2 * kRows * tp.oy));
+        tp.next(p);
+      }
       int rs = 0;
       uint32_t rphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        pv_mbar_wait_backoff(&bar_rempty[rs], rphase ^ 1u, p.err, 1, 64);
+        if (ahead < p.num_tiles) {
+          c1_prefetch_2d(&p.raw, (int32_t)(2 * kTileOut * tp.ct), (int32_t)(tp.n * (uint32_t)p.Hp + 2 * kRows * tp.oy));
+          tp.next(p);
+          ahead += gridDim.x;
+        }
+        if (p.ablate & 128) pv_mbar_wait(&bar_rempty[rs], rphase ^ 1u, p.err, 1);
+        else pv_mbar_wait_backoff(&bar_rempty[rs], rphase ^ 1u, p.err, 1, 64);
         pv_mbar_arrive_expect_tx(&bar_rfull[rs], kRawBytes);
         pv_tma_load_2d(raw + rs * kRawBytes, &p.raw, &bar_rfull[rs], (int32_t)(2 * kTileOut * t.ct),
                        (int32_t)(t.n * (uint32_t)p.Hp + 2 * kRows * t.oy));
@@ -254,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
       pv_tc_fence_after();
       const long long c2 = p.dbg ? clock64() : 0;
       const uint32_t a0 = pv_smem_u32(pxb + slot * kPxSlotBytes);
-      issue_tile<0>(a0, w0, tmem_base + (uint32_t)(buf * kRows * kN), idesc0, lead);
+      issue_tile<0>(a0, w0, tmem_base + (uint32_t)(buf * kRows * kN), idesc0, lead, (p.ablate & 8) ? 0u : lead);
       pv_umma_commit_pred(&bar_empty[slot], lead);
       pv_umma_commit_pred(&bar_tfull[buf], lead);
       if (++slot == kPxRing) { slot = 0; phase ^= 1u; }
@@ -271,35 +298,65 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
     int rs = 0, slot = 0;
     uint32_t rphase = 0, phase = 0;
     long long k_wr = 0, k_we = 0, k_work = 0;
+    // Alternative (PV_C1_TMA=0): the converters fetch their raw pixels themselves — one coalesced 4-byte load per input
+    // row, issued one tile AHEAD (registers).  Measured slower than the TMA ring (1030 vs 872 us per 8 frames on the same
+    // box); kept as a probe: it shows that the TMA unit is not what paces the bare pipeline (profiles/README.md).
+    TileWalk tw;
+    tw.init(p, blockIdx.x, gridDim.x);
+    const long long total_rows = (long long)p.B * p.Hp;
+    uint32_t vn[kInRows];
+    auto fetch = [&](const TileWalk& t) {
+      const long long row0 = (long long)t.n * p.Hp + (long long)(2 * kRows) * t.oy;
+      const uint32_t x = 2u * kTileOut * t.ct + (uint32_t)ct;
+      const uint32_t* src = p.plane + row0 * p.Wp + x;
+#pragma unroll
+      for (int kh = 0; kh < kInRows; ++kh)
+        vn[kh] = (x < (uint32_t)p.Wp && row0 + kh < total_rows) ? __ldg(src + (long long)kh * p.Wp) : 0u;
+    };
+    if (!p.use_tma && blockIdx.x < p.num_tiles) fetch(tw);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const long long k0 = p.dbg ? clock64() : 0;
-      pv_mbar_wait(&bar_rfull[rs], rphase, p.err, 5);
-      const long long k1 = p.dbg ? clock64() : 0;
-      const uint32_t* rb = reinterpret_cast<const uint32_t*>(raw + rs * kRawBytes) + ct;
       uint32_t v[kInRows];
+      long long k1 = k0;
+      if (p.use_tma) {
+        pv_mbar_wait(&bar_rfull[rs], rphase, p.err, 5);
+        k1 = p.dbg ? clock64() : 0;
+        const uint32_t* rb = reinterpret_cast<const uint32_t*>(raw + rs * kRawBytes) + ct;
 #pragma unroll
-      for (int kh = 0; kh < kInRows; ++kh) v[kh] = rb[kh * kRawW];
+        for (int kh = 0; kh < kInRows; ++kh) v[kh] = rb[kh * kRawW];
+      } else {
+#pragma unroll
+        for (int kh = 0; kh < kInRows; ++kh) v[kh] = vn[kh];
+        tw.next(p);
+        if (tile + (int)gridDim.x < p.num_tiles) fetch(tw);      // next tile's pixels travel while this one is converted
+      }
       const long long k2 = p.dbg ? clock64() : 0;
       pv_mbar_wait(&bar_empty[slot], phase ^ 1u, p.err, 6);
       const long long k3 = p.dbg ? clock64() : 0;
       uint8_t* dstp = pxb + slot * kPxSlotBytes + ct * 8;
 #pragma unroll
       for (int kh = 0; kh < kInRows; ++kh) {
-        // (v - mean)/256 == fma(v, 2^-8, -mean*2^-8) bit for bit (power-of-two scaling commutes with rounding)
-        const float r = fmaf((float)(v[kh] & 255u), 0.00390625f, p.c0);
-        const float g = fmaf((float)((v[kh] >> 8) & 255u), 0.00390625f, p.c1);
-        const float b = fmaf((float)((v[kh] >> 16) & 255u), 0.00390625f, p.c2);
-        const bool a = (v[kh] >> 24) != 0u;          // alpha 0 = pyramid padding / TMA zero fill -> exact 0
         uint2 o;
-        o.x = a ? pv_pack_bf16x2(r, g) : 0u;
-        o.y = a ? pv_pack_bf16x2(b, 0.f) : 0u;
-        *reinterpret_cast<uint2*>(dstp + kh * kPxRowBytes) = o;
+        if (p.ablate & 4) {
+          o.x = v[kh] & 0x3f003f00u;
+          o.y = 0u;
+        } else {
+          // (v - mean)/256 == fma(v, 2^-8, -mean*2^-8) bit for bit (power-of-two scaling commutes with rounding)
+          const float r = fmaf((float)(v[kh] & 255u), 0.00390625f, p.c0);
+          const float g = fmaf((float)((v[kh] >> 8) & 255u), 0.00390625f, p.c1);
+          const float b = fmaf((float)((v[kh] >> 16) & 255u), 0.00390625f, p.c2);
+          const bool a = (v[kh] >> 24) != 0u;          // alpha 0 = pyramid padding / TMA zero fill -> exact 0
+          o.x = a ? pv_pack_bf16x2(r, g) : 0u;
+          o.y = a ? pv_pack_bf16x2(b, 0.f) : 0u;
+        }
+        if (!(p.ablate & 16)) *reinterpret_cast<uint2*>(dstp + kh * kPxRowBytes) = o;
+        else if (o.x == 0x7fffffffu) p.err[0] = 2;
       }
-      pv_fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core
+      if (!(p.ablate & 32)) pv_fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) {
         pv_mbar_arrive(&bar_full[slot]);
-        pv_mbar_arrive(&bar_rempty[rs]);
+        if (p.use_tma) pv_mbar_arrive(&bar_rempty[rs]);
       }
       if (++rs == kRawRing) { rs = 0; rphase ^= 1u; }
       if (++slot == kPxRing) { slot = 0; phase ^= 1u; }
@@ -322,7 +379,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
       const bool xvalid = (m < (uint32_t)kTileOut) && (x < (uint32_t)p.ow);
       const uint32_t oy0 = t.oy * kRows;
       const long long q0 = p.dbg ? clock64() : 0;
-      pv_mbar_wait_backoff(&bar_tfull[buf], aphase, p.err, 4, 32);
+      if (p.ablate & 128) pv_mbar_wait(&bar_tfull[buf], aphase, p.err, 4);
+      else pv_mbar_wait_backoff(&bar_tfull[buf], aphase, p.err, 4, 32);
       pv_tc_fence_after();
       if (p.dbg && threadIdx.x == 320) p.dbg[(long long)blockIdx.x * 8 + 7] += clock64() - q0;
       // two rows per pass: two TMEM loads in flight, scale / shift come from shared memory as 16-byte ld.shared
@@ -331,9 +389,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
       for (int r = 0; r < kRows; r += 2) {
         uint32_t v[2][16];
         const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * kRows + r) * kN);
-        pv_tmem_ld16(tcol, v[0]);
-        pv_tmem_ld16(tcol + kN, v[1]);
-        pv_tmem_ld_wait();
+        if (!(p.ablate & 64)) {
+          pv_tmem_ld16(tcol, v[0]);
+          pv_tmem_ld16(tcol + kN, v[1]);
+          pv_tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[0][j] = v[1][j] = (uint32_t)j;
+        }
         if (r == kRows - 2) {
           pv_tc_fence_before();
           __syncwarp();
@@ -341,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          if (xvalid && oy0 + r + h < (uint32_t)p.oh) {
+          if (xvalid && oy0 + r + h < (uint32_t)p.oh && !(p.ablate & 2)) {
             const long long drow = row_of(p.dst, t.n, oy0 + r + h, x);
             uint32_t o[8];
 #pragma unroll
@@ -355,7 +418,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv1_fused_kernel(const __grid_c
               o[2 * g4] = pv_pack_bf16x2(f0, f1);
               o[2 * g4 + 1] = pv_pack_bf16x2(f2, f3);
             }
-            pv_stg256(p.out + drow * p.dst.cols, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+            if (!(p.ablate & 1)) pv_stg256(p.out + drow * p.dst.cols, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+            else if (o[0] == 0x12345u) p.err[0] = 1;   // keep the math alive
           }
         }
       }
@@ -431,6 +495,11 @@ extern "C" int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, con
       return PV_ERR_CUDA;
     }
   }
+  p.plane = static_cast<const uint32_t*>(plane_rgba);
+  {
+    const char* ut = getenv("PV_C1_TMA");
+    p.use_tma = (ut && ut[0] == '0') ? 0 : 1;    // default: TMA raw-pixel ring; PV_C1_TMA=0 selects the direct-load variant
+  }
   p.B = B;
   p.Hp = Hp;
   p.Wp = Wp;
@@ -455,6 +524,10 @@ extern "C" int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, con
   if (getenv("PV_C1_DEBUG") && !d_dbg) cudaMalloc(&d_dbg, sizeof(long long) * 8 * 1024);
   if (d_dbg) cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 8 * 1024, static_cast<cudaStream_t>(stream));
   p.dbg = d_dbg;
+  {
+    const char* ab = getenv("PV_C1_ABLATE");
+    p.ablate = ab ? atoi(ab) : 0;
+  }
   g_c1_dbg = d_dbg;
   int grid = num_sms * 2;
   if (grid > p.num_tiles) grid = p.num_tiles;
