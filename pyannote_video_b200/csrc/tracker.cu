@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
   __shared__ double s_rre[NS], s_rim[NS];
   __shared__ float s_resp[NS];
   __shared__ float s_peak;
+  __shared__ unsigned s_histi[SCELLS * SCELLS * 18];   // fixed-point cell histograms (scatter target)
   __shared__ int s_cwi[SW];                 // FHOG cell-4 bilinear weights of pixel coordinate c:
   __shared__ float s_cw0[SW], s_cw1[SW];    //   cp = (c + 0.5)/4 - 0.5, s_cwi = floor(cp), s_cw0 = cp - floor(cp), s_cw1 = 1 - s_cw0
   const int tid = threadIdx.x;
@@ -560,29 +561,35 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
       s_ori[i] = (uint8_t)bo;
     }
     __syncthreads();
-    // ---- cell histograms: every (cell, orientation) bin gathers its pixels in raster order ----
-    // (the bilinear cell weights depend on the pixel coordinate only: s_cw* tables, computed once per launch —
-    // two IEEE divisions per pixel visit were 80 % of this kernel's instructions)
-    for (int bi = tid; bi < SCELLS * SCELLS * 18; bi += kThreads) {
-      const int o = bi % 18, cell = bi / 18;
-      const int cyi = cell / SCELLS, cxi = cell - cyi * SCELLS;
-      float acc = 0.f;
-      const int y0 = max(1, 4 * cyi - 2), y1 = min(SW - 2, 4 * cyi + 5);
-      const int x0 = max(1, 4 * cxi - 2), x1 = min(SW - 2, 4 * cxi + 5);
-      for (int y = y0; y <= y1; ++y) {
-        const int iyp = s_cwi[y];
-        float wy;
-        if (iyp == cyi) wy = s_cw1[y]; else if (iyp + 1 == cyi) wy = s_cw0[y]; else continue;
-        for (int x = x0; x <= x1; ++x) {
-          if (s_ori[y * SW + x] != o) continue;
-          const int ixp = s_cwi[x];
-          float wx;
-          if (ixp == cxi) wx = s_cw1[x]; else if (ixp + 1 == cxi) wx = s_cw0[x]; else continue;
-          acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wx, wy), s_mag[y * SW + x]));
+    // ---- cell histograms: every pixel SCATTERS its magnitude into the (up to) 2 x 2 cells it overlaps ----
+    // A gather (one thread per (cell, orientation) bin scanning its 8 x 8 support) visited 41 k pixels per scale to use
+    // 1.8 k of them and was 2/3 of this kernel (ncu, profiles/README.md).  The scatter adds 17-bit fixed point with
+    // shared-memory integer atomics: integer addition is associative, so the result does not depend on the order of
+    // arrival (deterministic), at a resolution of 2^-17 on sums < 2^15 — finer than float32 at these magnitudes.
+    for (int bi = tid; bi < SCELLS * SCELLS * 18; bi += kThreads) s_histi[bi] = 0u;
+    __syncthreads();
+    for (int i = tid; i < SW * SW; i += kThreads) {
+      const int y = i / SW, x = i - y * SW;
+      if (y < 1 || y > SW - 2 || x < 1 || x > SW - 2) continue;
+      const float m = s_mag[i];
+      const int o = s_ori[i];
+      const int iyp = s_cwi[y], ixp = s_cwi[x];
+      const float wy[2] = {s_cw1[y], s_cw0[y]}, wx[2] = {s_cw1[x], s_cw0[x]};   // cell iyp gets 1 - frac, cell iyp + 1 gets frac
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int cyi = iyp + dy;
+        if (cyi < 0 || cyi >= SCELLS) continue;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int cxi = ixp + dx;
+          if (cxi < 0 || cxi >= SCELLS) continue;
+          const float v = __fmul_rn(__fmul_rn(wx[dx], wy[dy]), m);
+          atomicAdd(&s_histi[(cyi * SCELLS + cxi) * 18 + o], (unsigned)__float2uint_rn(__fmul_rn(v, 131072.0f)));
         }
       }
-      s_hist[bi] = acc;   // layout [cell][o]
     }
+    __syncthreads();
+    for (int bi = tid; bi < SCELLS * SCELLS * 18; bi += kThreads) s_hist[bi] = __fmul_rn((float)s_histi[bi], 1.0f / 131072.0f);   // [cell][o]
     __syncthreads();
     if (tid < SCELLS * SCELLS) {
       float n = 0.f;
