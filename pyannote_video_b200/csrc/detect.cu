@@ -14,6 +14,12 @@ extern std::atomic<long long> g_pv_launches;
 
 namespace {
 
+// u8 -> f32 and floor without the conversion unit (I2F / F2I / FRND run at a quarter of the FP32 rate):
+// (2^23 | b) - 2^23 is exact; floor(t) for 0 <= t < 2^22 is the mantissa of t (+) 2^23 rounded down
+__device__ __forceinline__ float pv_u8f(uint32_t b) { return __fsub_rn(__uint_as_float(0x4B000000u | b), 8388608.0f); }
+// floor of 0 <= t < 2^22, as float bits with the integer in the mantissa
+__device__ __forceinline__ uint32_t pv_floor_bits(float t) { return __float_as_uint(__fadd_rd(t, 8388608.0f)); }
+
 // one output pixel of dlib's resize_image/interpolate_bilinear (explicitly rounded, unfused float32)
 template <int SRC_CH>
 __device__ __forceinline__ uchar4 bilinear_px(const uint8_t* __restrict__ s, int src_pitch_px, int sx0, int sy0, int sw,
@@ -22,13 +28,13 @@ __device__ __forceinline__ uchar4 bilinear_px(const uint8_t* __restrict__ s, int
   o.w = 255;
   const float y = __fmul_rn((float)r, ys);
   const float x = __fmul_rn((float)c, xs);
-  int top = (int)floorf(y), left = (int)floorf(x);
+  int top = (int)(pv_floor_bits(y) & 0x7FFFFFu), left = (int)(pv_floor_bits(x) & 0x7FFFFFu);   // y, x >= 0
   top = min(top, sh - 1);
   left = min(left, sw - 1);
   const int bot = min(top + 1, sh - 1), right = min(left + 1, sw - 1);
   const float tb = __fsub_rn(y, (float)top), lr = __fsub_rn(x, (float)left);
   const float omlr = __fsub_rn(1.0f, lr), omtb = __fsub_rn(1.0f, tb);
-  uint8_t tl[3], tr[3], bl[3], br[3];
+  uint32_t tl[3], tr[3], bl[3], br[3];
   if (SRC_CH == 4) {   // one 4-byte load per tap
     const uchar4* s4 = reinterpret_cast<const uchar4*>(s);
     const uchar4 a = s4[(long long)(sy0 + top) * src_pitch_px + sx0 + left];
@@ -50,12 +56,11 @@ __device__ __forceinline__ uchar4 bilinear_px(const uint8_t* __restrict__ s, int
   uint8_t res[3];
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    const float a = __fadd_rn(__fmul_rn(omlr, (float)tl[ch]), __fmul_rn(lr, (float)tr[ch]));
-    const float b = __fadd_rn(__fmul_rn(omlr, (float)bl[ch]), __fmul_rn(lr, (float)br[ch]));
-    float v = __fadd_rn(__fmul_rn(omtb, a), __fmul_rn(tb, b));
-    v = floorf(__fadd_rn(v, 0.5f));
-    v = fminf(fmaxf(v, 0.f), 255.f);
-    res[ch] = (uint8_t)v;
+    const float a = __fadd_rn(__fmul_rn(omlr, pv_u8f(tl[ch])), __fmul_rn(lr, pv_u8f(tr[ch])));
+    const float b = __fadd_rn(__fmul_rn(omlr, pv_u8f(bl[ch])), __fmul_rn(lr, pv_u8f(br[ch])));
+    const float v = __fadd_rn(__fmul_rn(omtb, a), __fmul_rn(tb, b));
+    // floor(v + 0.5) clamped to [0, 255]: v >= 0, so only the upper clamp can bind
+    res[ch] = (uint8_t)(pv_floor_bits(fminf(__fadd_rn(v, 0.5f), 255.5f)) & 0xFFu);
   }
   o.x = res[0];
   o.y = res[1];
@@ -80,9 +85,6 @@ __device__ __forceinline__ float pv_u8f_sel(uint32_t v, uint32_t magic) {
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(magic), "n"(0x7540 | SEL));
   return __fsub_rn(__uint_as_float(r), 8388608.0f);
 }
-__device__ __forceinline__ float pv_u8f(uint32_t b) { return __fsub_rn(__uint_as_float(0x4B000000u | b), 8388608.0f); }
-// floor of 0 <= t < 2^22, as float bits with the integer in the mantissa
-__device__ __forceinline__ uint32_t pv_floor_bits(float t) { return __float_as_uint(__fadd_rd(t, 8388608.0f)); }
 
 // horizontally interpolated source row: h[ch] = omlr * S[il][ch] + lr * S[ir][ch]  (il, ir: pixel indices in the image)
 template <int SRC_CH>
