@@ -296,6 +296,12 @@ int pv_tracker_enable_scale(void* handle, const float* hann32_host, const float*
 int pv_tracker_start(void* handle, const void* frame, int H, int W, const int* ids, const float* rects, int n,
                      void* stream);
 int pv_tracker_update(void* handle, const void* frame, int H, int W, const int* ids, int n, void* stream);
+/* batched forms (tracks of many shots advance in one launch): frames u8 [F,H,W,3], frame_idx i32 [n] = frame of
+ * track ids[i] (NULL: all tracks read frame 0) */
+int pv_tracker_start_frames(void* handle, const void* frames, int H, int W, const int* frame_idx, const int* ids,
+                            const float* rects, int n, void* stream);
+int pv_tracker_update_frames(void* handle, const void* frames, int H, int W, const int* frame_idx, const int* ids, int n,
+                             void* stream);
 /* device pointers owned by the bank: positions f32 [capacity,4] and PSR f32 [capacity] */
 int pv_tracker_state(void* handle, float** pos, float** psr);
 

@@ -9,12 +9,13 @@ as recalled in SURVEY.md App. A.3 / A.4 (dlib 19.12 absent: parity unpinned).
 
 Stated deviations from dlib, shared with the CUDA path: the 2-D similarity fit uses the closed
 form (equal to Umeyama's optimum for proper rotations) evaluated in float32; chips are sampled with
-plain bilinear interpolation (no pyramid_down pre-shrink for large faces); the 51 mean-face
-constants come from our synthetic mean shape.
+plain bilinear interpolation (no pyramid_down pre-shrink for large faces).  The 51 mean-face constants
+and the landmark exclusion list (eyebrows 17..26, lower lip 55..59 and 65..67) are dlib's, as recalled
+(oracle/constants.py).
 """
 import numpy as np
 
-from pyannote_video_b200 import weights as W
+from . import constants as W
 
 f32 = np.float32
 
@@ -102,20 +103,27 @@ def ert_predict(model, rgb, rects):
     return out
 
 
-CHIP_POINTS = [i for i in range(17, 68) if not (17 <= i <= 26) and not (55 <= i <= 59)]
+CHIP_POINTS = W.chip_points()
+
+
+def chip_from_points(size=W.EMB_CHIP, padding=W.EMB_CHIP_PADDING):
+    """chip-space alignment targets of get_face_chip_details: ((padding + mean) / (2 padding + 1)) * size for the
+    landmarks that take part (others stay 0), float32 [68,2]"""
+    mean = W.mean_face()                                         # [51,2] for landmarks 17..67
+    frm = np.zeros((68, 2), f32)
+    pad = f32(padding)
+    scale = f32(2.0) * pad + f32(1.0)
+    for i in CHIP_POINTS:
+        frm[i, 0] = ((pad + mean[i - 17, 0]) / scale) * f32(size)
+        frm[i, 1] = ((pad + mean[i - 17, 1]) / scale) * f32(size)
+    return frm
 
 
 def chip_transform(parts, size=W.EMB_CHIP, padding=W.EMB_CHIP_PADDING):
     """get_face_chip_details: similarity mapping chip pixel coords -> image coords.  parts int [M,68,2]."""
     parts = np.asarray(parts)
     Mn = parts.shape[0]
-    mean = W.chip_mean_face()                                    # [51,2] for landmarks 17..67
-    frm = np.zeros((Mn, 68, 2), f32)
-    pad = f32(padding)
-    scale = f32(2.0) * pad + f32(1.0)
-    for i in CHIP_POINTS:
-        frm[:, i, 0] = ((pad + mean[i - 17, 0]) / scale) * f32(size)
-        frm[:, i, 1] = ((pad + mean[i - 17, 1]) / scale) * f32(size)
+    frm = np.broadcast_to(chip_from_points(size, padding), (Mn, 68, 2)).astype(f32)
     to = parts.astype(f32)
     return similarity_fit(frm, to, CHIP_POINTS)
 

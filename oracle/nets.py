@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from pyannote_video_b200 import weights as W
+from . import constants as W
 
 
 def _r(x, bf16):

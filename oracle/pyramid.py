@@ -9,8 +9,8 @@ unpinned).  Deviations we chose ourselves (dlib's exact tile packing is not reca
 """
 import numpy as np
 
-from pyannote_video_b200.pyrgeom import (PYR_N, PYR_PAD, PYR_OUTER_PAD, PYR_MIN_SIDE, pyramid_geometry,
-                                         det_cell_to_plane)
+from . import constants as K
+from . import geometry as ogeo
 
 f32 = np.float32
 
@@ -45,12 +45,22 @@ def resize_bilinear_u8(src, oh, ow):
     return np.clip(v, 0, 255).astype(np.uint8)
 
 
-def build_plane(rgb, upsample=1):
+def placement_for(H, W, upsample):
+    """the tile placement is [OURS] and an INPUT to the oracle: it is taken from the product's packing and
+    validated by oracle.geometry.Geometry (sizes, padding, non-overlap) — the only thing the oracle takes
+    from the product; every other piece of geometry is restated independently in oracle/geometry.py."""
+    from pyannote_video_b200.pyrgeom import pyramid_geometry
+    return ogeo.from_product(pyramid_geometry(H, W, upsample))
+
+
+def build_plane(rgb, upsample=1, geo=None):
     """rgb: uint8 [H,W,3] -> (plane uint8 [Hp,Wp,4] RGBA with A=255 inside pyramid tiles, geometry).
     Level 0 is the (optionally 2x bilinear-upsampled, dlib pyramid_up) image; level i+1 is level i
-    resized to floor(5/6) of its size (pyramid_down<6>)."""
+    resized to floor(5/6) of its size (pyramid_down<6>).  `geo`: an oracle.geometry.Geometry (validated
+    placement); by default the product's placement for this frame size, validated."""
     H, W, _ = rgb.shape
-    geo = pyramid_geometry(H, W, upsample)
+    if geo is None:
+        geo = placement_for(H, W, upsample)
     plane = np.zeros((geo.plane_h, geo.plane_w, 4), np.uint8)
     cur = rgb
     for lv, (x0, y0, w, h) in enumerate(geo.rects):
@@ -65,20 +75,23 @@ def build_plane(rgb, upsample=1):
 
 def normalize_plane(plane_rgba):
     """RGBA u8 plane -> float32 [3,Hp,Wp]: (v-mean)/256 inside tiles, 0 in the padding."""
-    from pyannote_video_b200.weights import PIXEL_MEAN, PIXEL_SCALE
     v = plane_rgba[..., :3].astype(f32)
-    out = (v - np.asarray(PIXEL_MEAN, f32)) * f32(PIXEL_SCALE)
+    out = (v - np.asarray(K.PIXEL_MEAN, f32)) * f32(K.PIXEL_SCALE)
     out = out * (plane_rgba[..., 3:4] > 0)
     return np.ascontiguousarray(out.transpose(2, 0, 1))
 
 
 def decode(scores, geo, window, adjust_threshold, iou_thresh, covered_thresh, max_candidates=None):
     """loss_mmod::to_label restated.  scores: float32 [OH,OW] -> list of (l,t,r,b,score) in
-    original-image pixel coordinates (integers, dlib `rectangle`, inclusive right/bottom)."""
+    original-image pixel coordinates (integers, dlib `rectangle`, inclusive right/bottom).
+    `geo` may be an oracle.geometry.Geometry or any object with H/W/upsample/rects/plane_h/plane_w (it is
+    re-validated and only the oracle's own geometry functions are used on it)."""
+    if not isinstance(geo, ogeo.Geometry):
+        geo = ogeo.from_product(geo)
     ys, xs = np.nonzero(scores > f32(adjust_threshold))
     cands = []
     for r, c in zip(ys.tolist(), xs.tolist()):
-        px, py = det_cell_to_plane(c, r)
+        px, py = ogeo.cell_to_plane(c), ogeo.cell_to_plane(r)
         lv = geo.level_at(px, py)
         if lv < 0:
             continue  # [OURS] cells whose centre falls into padding do not produce boxes

@@ -34,7 +34,8 @@ struct BankParams {
   float* psr;       // [cap]
   const int* ids;   // [n] slots handled by this launch
   const float* rects;  // start only: [n][4]
-  const uint8_t* frame;  // uint8 [H,W,3]
+  const uint8_t* frame;  // uint8 [F,H,W,3]
+  const int* frame_idx;  // [n] frame of each track of this launch (nullptr: frame 0)
   int H, W;
   float padding, lambda, nu;
 };
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
   __shared__ float peak[4];  // ppx, ppy
   const int tid = threadIdx.x;
   const int slot = p.ids[blockIdx.x];
+  if (p.frame_idx) p.frame += (size_t)p.frame_idx[blockIdx.x] * p.H * p.W * 3;
   float2* A = p.A + (size_t)slot * NCH * NPIX;
   float* B = p.B + (size_t)slot * NPIX;
   float rect[4];
@@ -477,6 +479,7 @@ struct ScaleParams {
   float* pos;      // [cap][4]
   const int* ids;
   const uint8_t* frame;
+  const int* frame_idx;
   int H, W;
 };
 
@@ -514,6 +517,7 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
   }
   __syncthreads();
   const int slot = p.ids[blockIdx.x];
+  if (p.frame_idx) p.frame += (size_t)p.frame_idx[blockIdx.x] * p.H * p.W * 3;
   float2* As = p.As + (size_t)slot * SF * NS;
   float* Bs = p.Bs + (size_t)slot * NS;
   const float l = p.pos[slot * 4 + 0], t = p.pos[slot * 4 + 1], r = p.pos[slot * 4 + 2], b = p.pos[slot * 4 + 3];
@@ -818,8 +822,8 @@ extern "C" int pv_tracker_destroy(void* handle) {
   return PV_OK;
 }
 
-static int launch(Bank* b, bool start, const void* frame, int H, int W, const int* ids, const float* rects, int n,
-                  void* stream) {
+static int launch(Bank* b, bool start, const void* frame, const int* frame_idx, int H, int W, const int* ids,
+                  const float* rects, int n, void* stream) {
   if (n == 0) return PV_OK;
   BankParams p;
   p.A = b->A;
@@ -829,6 +833,7 @@ static int launch(Bank* b, bool start, const void* frame, int H, int W, const in
   p.ids = ids;
   p.rects = rects;
   p.frame = static_cast<const uint8_t*>(frame);
+  p.frame_idx = frame_idx;
   p.H = H;
   p.W = W;
   p.padding = b->padding;
@@ -873,7 +878,8 @@ extern "C" int pv_tracker_enable_scale(void* handle, const float* hann32_host, c
   return PV_OK;
 }
 
-static int launch_scale(Bank* b, bool start, const void* frame, int H, int W, const int* ids, int n, void* stream) {
+static int launch_scale(Bank* b, bool start, const void* frame, const int* frame_idx, int H, int W, const int* ids, int n,
+                        void* stream) {
   if (n == 0 || !b->has_scale) return PV_OK;
   ScaleParams p;
   p.As = b->As;
@@ -881,6 +887,7 @@ static int launch_scale(Bank* b, bool start, const void* frame, int H, int W, co
   p.pos = b->pos;
   p.ids = ids;
   p.frame = static_cast<const uint8_t*>(frame);
+  p.frame_idx = frame_idx;
   p.H = H;
   p.W = W;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -896,18 +903,30 @@ static int launch_scale(Bank* b, bool start, const void* frame, int H, int W, co
 /* start trackers in slots ids[0..n) on `frame` (uint8 [H,W,3]) at rects [n,4] (l,t,r,b floats) */
 extern "C" int pv_tracker_start(void* handle, const void* frame, int H, int W, const int* ids, const float* rects, int n,
                                 void* stream) {
-  PV_REQUIRE(handle && frame && ids && rects, "pv_tracker_start: null argument");
-  int rc = launch(static_cast<Bank*>(handle), true, frame, H, W, ids, rects, n, stream);
-  if (rc != PV_OK) return rc;
-  return launch_scale(static_cast<Bank*>(handle), true, frame, H, W, ids, n, stream);
+  return pv_tracker_start_frames(handle, frame, H, W, nullptr, ids, rects, n, stream);
 }
 
 /* advance the trackers in slots ids[0..n) to `frame`; PSR and positions are left in the bank */
 extern "C" int pv_tracker_update(void* handle, const void* frame, int H, int W, const int* ids, int n, void* stream) {
-  PV_REQUIRE(handle && frame && ids, "pv_tracker_update: null argument");
-  int rc = launch(static_cast<Bank*>(handle), false, frame, H, W, ids, nullptr, n, stream);
+  return pv_tracker_update_frames(handle, frame, H, W, nullptr, ids, n, stream);
+}
+
+/* batched forms: frames uint8 [F,H,W,3], frame_idx[i] = frame of track ids[i] (tracks of many shots / videos advance
+ * in one launch; tracking state is independent per shot, pyannote/video/tracking.py:410-417) */
+extern "C" int pv_tracker_start_frames(void* handle, const void* frames, int H, int W, const int* frame_idx, const int* ids,
+                                       const float* rects, int n, void* stream) {
+  PV_REQUIRE(handle && frames && ids && rects, "pv_tracker_start: null argument");
+  int rc = launch(static_cast<Bank*>(handle), true, frames, frame_idx, H, W, ids, rects, n, stream);
   if (rc != PV_OK) return rc;
-  return launch_scale(static_cast<Bank*>(handle), false, frame, H, W, ids, n, stream);
+  return launch_scale(static_cast<Bank*>(handle), true, frames, frame_idx, H, W, ids, n, stream);
+}
+
+extern "C" int pv_tracker_update_frames(void* handle, const void* frames, int H, int W, const int* frame_idx, const int* ids,
+                                        int n, void* stream) {
+  PV_REQUIRE(handle && frames && ids, "pv_tracker_update: null argument");
+  int rc = launch(static_cast<Bank*>(handle), false, frames, frame_idx, H, W, ids, nullptr, n, stream);
+  if (rc != PV_OK) return rc;
+  return launch_scale(static_cast<Bank*>(handle), false, frames, frame_idx, H, W, ids, n, stream);
 }
 
 /* device pointers to the bank's state: positions float [capacity,4], psr float [capacity] */

@@ -63,7 +63,7 @@ class ShapePredictor:
             pass
 
 
-CHIP_POINTS = [i for i in range(17, 68) if not (17 <= i <= 26) and not (55 <= i <= 59)]
+CHIP_POINTS = list(W.CHIP_POINTS)
 
 
 def chip_from_points(size=W.EMB_CHIP, padding=W.EMB_CHIP_PADDING):

@@ -95,9 +95,10 @@ class TrackerBank(object):
 
     def start(self, frame, rect):
         if not self._free:
-            raise RuntimeError("TrackerBank: capacity %d exhausted" % self.capacity)
+            raise RuntimeError("TrackerBank: capacity %d exhausted (construct the bank with a larger capacity)"
+                               % self.capacity)
         frame = self.prepare_frame(frame)
-        if self._pending and self._pending_frame is not frame:
+        if self._pending and self._pending_frame.data_ptr() != frame.data_ptr():
             self._flush()
         slot = self._free.pop()
         self._pending.append((slot, (rect.left(), rect.top(), rect.right(), rect.bottom())))
@@ -129,6 +130,22 @@ class TrackerBank(object):
         for s, row in zip(handles, state):
             self._cache[s] = tuple(float(v) for v in row[:4])
         return [float(v) for v in state[:, 4]]
+
+    # ---- batched device-side interface (no host synchronisation): tracks of many shots in one launch ----
+    def start_batch(self, frames, frame_idx, ids, rects):
+        """frames u8 [F,H,W,3] (device); frame_idx i32 [n], ids i32 [n], rects f32 [n,4] device tensors"""
+        assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.is_contiguous()
+        _lib.check(_lib.lib().pv_tracker_start_frames(self.h, _lib.ptr(frames), frames.shape[1], frames.shape[2],
+                                                      _lib.ptr(frame_idx), _lib.ptr(ids), _lib.ptr(rects), int(ids.shape[0]),
+                                                      _lib.stream_ptr()), "pv_tracker_start_frames")
+
+    def update_batch(self, frames, frame_idx, ids):
+        """advance tracks `ids` (i32 [n], device) to frames[frame_idx[i]]; positions / PSR stay in the bank
+        (`read_state`)"""
+        assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.is_contiguous()
+        _lib.check(_lib.lib().pv_tracker_update_frames(self.h, _lib.ptr(frames), frames.shape[1], frames.shape[2],
+                                                       _lib.ptr(frame_idx), _lib.ptr(ids), int(ids.shape[0]),
+                                                       _lib.stream_ptr()), "pv_tracker_update_frames")
 
     def read_state(self, ids):
         """device tensor [n,5]: l,t,r,b,psr of the given slots"""

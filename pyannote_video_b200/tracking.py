@@ -160,11 +160,13 @@ class TrackingByDetection(object):
 
     # ------------------------------------------------------------------ helpers
     def _get_bank(self):
+        """resolve the tracker bank and the frame-upload hook (called at the top of __call__, before the first
+        frame is cached, so that the whole shot — not only its tail — is cached as device tensors)"""
         if self._bank is None:
             from .tracker import TrackerBank
             self._bank = TrackerBank()
-            if self._prepare_frame is None:
-                self._prepare_frame = self._bank.prepare_frame
+        if self._prepare_frame is None:
+            self._prepare_frame = getattr(self._bank, "prepare_frame", None)
         return self._bank
 
     def _match(self, rectangle1, rectangle2):
@@ -324,6 +326,7 @@ class TrackingByDetection(object):
 
         segment_generator = get_segment_generator(segmentation)
         segment_generator.send(None)
+        self._get_bank()
         self._reset()
 
         for i, (t, frame) in enumerate(video):

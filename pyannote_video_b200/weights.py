@@ -133,10 +133,31 @@ def make_shape_predictor(seed=4, stages=ERT_STAGES, trees=ERT_TREES, pool=ERT_PO
     )
 
 
-# mean_face_shape_x/y: dlib keeps 51 constants (landmarks 17..67) in image_transforms/interpolation.h;
-# they are not recoverable here, so the chip alignment targets are derived from our synthetic mean shape.
+# get_face_chip_details (dlib image_transforms/interpolation.h): mean_face_shape_x/y, 51 constants for
+# landmarks 17..67 [MEMORY of dlib 19.12].  The oracle keeps its own copy (oracle/constants.py).
+MEAN_FACE_X = (
+    0.000213256, 0.0752622, 0.18113, 0.29077, 0.393397, 0.586856, 0.689483, 0.799124,
+    0.904991, 0.98004, 0.490127, 0.490127, 0.490127, 0.490127, 0.36688, 0.426036,
+    0.490127, 0.554217, 0.613373, 0.121737, 0.187122, 0.265825, 0.334606, 0.260918,
+    0.182743, 0.645647, 0.714428, 0.793132, 0.858516, 0.79751, 0.719335, 0.254149,
+    0.340985, 0.428858, 0.490127, 0.551395, 0.639268, 0.726104, 0.642159, 0.556721,
+    0.490127, 0.423532, 0.338094, 0.290379, 0.428096, 0.490127, 0.552157, 0.689874,
+    0.553364, 0.490127, 0.42689)
+MEAN_FACE_Y = (
+    0.106454, 0.038915, 0.0187482, 0.0344891, 0.0773906, 0.0773906, 0.0344891,
+    0.0187482, 0.038915, 0.106454, 0.203352, 0.307009, 0.409805, 0.515625, 0.587326,
+    0.609345, 0.628106, 0.609345, 0.587326, 0.216423, 0.178758, 0.179852, 0.231733,
+    0.245099, 0.244077, 0.231733, 0.179852, 0.178758, 0.216423, 0.244077, 0.245099,
+    0.780233, 0.745405, 0.727388, 0.742578, 0.727388, 0.745405, 0.780233, 0.864805,
+    0.902192, 0.909281, 0.902192, 0.864805, 0.784792, 0.778746, 0.785343, 0.778746,
+    0.784792, 0.824182, 0.831803, 0.824182)
+# landmarks that take part in the chip alignment: 17..67 minus eyebrows (17..26) and lower lip (55..59, 65..67)
+CHIP_POINTS = tuple(i for i in range(17, 68)
+                    if not (17 <= i <= 26) and not (55 <= i <= 59) and not (65 <= i <= 67))
+
+
 def chip_mean_face():
-    return mean_shape()[17:].copy()
+    return np.stack([np.asarray(MEAN_FACE_X, np.float32), np.asarray(MEAN_FACE_Y, np.float32)], axis=1)
 
 
 # ---------------------------------------------------------------------------------------------
