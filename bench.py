@@ -1,17 +1,21 @@
 #!/usr/bin/env python
-"""bench.py — frames/sec of the face hot path (CNN detect -> 68-pt landmarks -> chip -> ResNet embed)
-on synthetic 1080p, BASELINE.json configs[1], on N GPUs of one node.
+"""bench.py — frames/sec of the face hot path (CNN detect -> correlation-tracker update -> 68-pt landmarks -> chip ->
+ResNet embed) on synthetic 1080p, BASELINE.json configs[1], on N GPUs of one node.
 
     python bench.py --gpus 1 --steps 60 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
            --master-port P bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the CPU restatement of the reference's dlib path
+    python bench.py --impl reference ...      # the C++ CPU restatement of the reference's dlib path, all usable cores
 
-A step = one batch of `--frames-per-step` 1080p frames through the whole path, every frame
-detected with upsample 1 (reference semantics, pyannote/video/face/face.py:66) plus F=4 seeded face
-boxes per frame through landmarks+embed (mirrors `extract`, scripts/pyannote-face.py:290-297).
-Prints ONE JSON line (contract in the task statement).  Only the `cpu_baseline` leg and
-`--impl reference` execute anything under oracle/.
+A step = `--frames-per-step` (32) concurrent shot streams each advancing by ONE 1080p frame (tracking state is
+independent per shot, pyannote/video/tracking.py:410-417, so shots are the unit that batches):
+  * every frame detected with upsample 1 (reference semantics, pyannote/video/face/face.py:66),
+  * K = 8 live tracks per stream, a forward and a backward correlation tracker each (tracking.py:199-206,331-337):
+    16 `correlation_tracker.update` per frame, all streams in one bank launch,
+  * F = 4 seeded face boxes per frame through landmarks + chip + embed (mirrors `extract`, where boxes come from the
+    track file, scripts/pyannote-face.py:290-297).
+Prints ONE JSON line (contract in the task statement).  Only the `cpu_baseline` leg and `--impl reference` execute
+anything under oracle/ (the C++ restatement oracle/cpu, as the timed CPU baseline).
 """
 import argparse
 import json
@@ -26,9 +30,19 @@ sys.path.insert(0, ROOT)
 
 H, W = 1080, 1920
 FACES_PER_FRAME = 4
+TRACKS_PER_STREAM = 8          # live tracks per shot stream; x2 (forward + backward tracker) updates per frame
+N_TIMES = 4                    # distinct time steps held per stream (ping-pong 0,1,2,3,2,1,...: motion stays continuous)
+SHIFT = (1.0, 0.5)             # px / frame global translation
 METRIC = "frames/sec detect+track+embed on 1080p"
-WORKLOAD = ("synthetic 1080p@25fps, batched CNN detect (upsample 1, every frame) + %d faces/frame 68-pt landmarks + "
-            "ResNet-v1 embed" % 4)
+WORKLOAD = ("synthetic 1080p@25fps: batched CNN detect (upsample 1, every frame) + %d correlation-tracker updates/frame "
+            "(%d live tracks x fwd+bwd) + %d faces/frame 68-pt landmarks + ResNet-v1 embed"
+            % (2 * TRACKS_PER_STREAM, TRACKS_PER_STREAM, FACES_PER_FRAME))
+TRACKER_BYTES_PER_UPDATE = 2.07e6      # A read + written (f32 complex 31x64x64), B, chip
+
+
+def time_index(s):
+    seq = list(range(N_TIMES)) + list(range(N_TIMES - 2, 0, -1))
+    return seq[s % len(seq)]
 
 
 def load_peaks():
@@ -76,63 +90,108 @@ class ClockSampler(threading.Thread):
                     samples=len(self.rows))
 
 
-# ------------------------------------------------------------------------------------------------
-# CPU restatement of the reference path (oracle) — used by cpu_baseline and --impl reference
-# ------------------------------------------------------------------------------------------------
-def cpu_reference_frames(n_frames, models, frames, boxes, fidx):
-    """runs the oracle path on `n_frames` frames; returns elapsed seconds"""
-    import numpy as np
-    import torch
-    from oracle import nets as onets, pyramid as opyr, landmarks as olm
-    det, sp, emb = models
-    t0 = time.perf_counter()
-    for i in range(n_frames):
-        rgb = frames[i].numpy()
-        plane, geo = opyr.build_plane(rgb, 1)
-        x = torch.from_numpy(opyr.normalize_plane(plane))[None]
-        scores = onets.detector_forward(det, x)[0].numpy()
-        opyr.decode(scores, geo, det["window"], det["adjust_threshold"], det["iou_thresh"], det["covered_thresh"],
-                    max_candidates=4096)
-        sel = (fidx == i).numpy()
-        parts = olm.ert_predict(sp, rgb, boxes[sel].numpy())
-        chips = olm.extract_chips(rgb, parts)
-        onets.embed_forward(emb, onets.normalize_rgb(chips))
-    return time.perf_counter() - t0
-
-
 def make_models():
     from pyannote_video_b200 import weights as Wt
     return Wt.make_detector(seed=2), Wt.make_shape_predictor(seed=4), Wt.make_embedder(seed=3)
 
 
+def track_rects(n_streams):
+    """TRACKS_PER_STREAM 96x96 boxes on a 4x2 grid per stream: float32 [n*K,4] (l,t,r,b), stream index int32 [n*K]"""
+    import torch
+    rects, sidx = [], []
+    for s in range(n_streams):
+        for k in range(TRACKS_PER_STREAM):
+            cx = 240.0 + 480.0 * (k % 4)
+            cy = 300.0 + 480.0 * (k // 4)
+            rects.append([cx - 48.0, cy - 48.0, cx + 48.0, cy + 48.0])
+            sidx.append(s)
+    return torch.tensor(rects, dtype=torch.float32), torch.tensor(sidx, dtype=torch.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+# C++ CPU restatement of the reference path (oracle/cpu) — used by cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------
+class CpuPath(object):
+    """the same per-frame work as one stream of the GPU step, on host cores: detect + 2K tracker updates + F faces"""
+
+    def __init__(self, models, threads):
+        from oracle import cpu_ref
+        self.cpu_ref = cpu_ref
+        self.threads = cpu_ref.set_threads(threads)
+        det, sp, emb = models
+        self.det = cpu_ref.Detector(det)
+        self.sp = cpu_ref.ShapePredictor(sp)
+        self.emb = cpu_ref.Embedder(emb)
+        self.bank = None
+
+    def start_tracks(self, frame):
+        import numpy as np
+        rects, _ = track_rects(1)
+        rects = np.concatenate([rects.numpy(), rects.numpy()]).astype(np.float64)       # forward + backward trackers
+        self.ids = np.arange(rects.shape[0], dtype=np.int32)
+        self.bank = self.cpu_ref.TrackerBank(len(self.ids), use_scale=True)
+        self.bank.start(frame, self.ids, rects)
+
+    def frame(self, rgb, boxes):
+        self.cpu_ref.set_threads(self.threads)
+        self.det.detect(rgb, 1)
+        self.bank.update(rgb, self.ids)
+        parts = self.sp.predict(rgb, boxes)
+        chips = self.cpu_ref.extract_chips(rgb, parts)
+        return self.emb.forward(chips)
+
+
+def cpu_sample(models, threads, n_frames, seed=0):
+    """times n_frames frames of ONE stream through the C++ path; returns (seconds, threads used)"""
+    from pyannote_video_b200.synth import make_frames, make_boxes
+    frames = make_frames(N_TIMES, H, W, seed=seed, shift_per_frame=SHIFT).numpy()
+    boxes, fidx = make_boxes(N_TIMES, FACES_PER_FRAME, H, W, seed=1)
+    boxes = boxes.numpy().reshape(N_TIMES, FACES_PER_FRAME, 4)
+    path = CpuPath(models, threads)
+    path.start_tracks(frames[0])
+    path.frame(frames[1], boxes[1])                       # warm-up (page faults, thread pool)
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        t = time_index(i + 2)
+        path.frame(frames[t], boxes[t])
+    return time.perf_counter() - t0, path.threads
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the oracle (CPU restatement of the reference's dlib path), all host threads."""
+    """--impl reference: the C++ restatement of the reference's dlib path with all usable host cores (rank 0 only)."""
     if rank != 0:
         return
-    import torch
+    from oracle import cpu_ref
     from pyannote_video_b200.synth import make_frames, make_boxes
     models = make_models()
-    n_per_step = 1
-    total = args.warmup + args.steps
-    total = min(total, 8)  # bounded sample: each step is one frame; cap the whole run to a few minutes
-    steps = max(1, total - args.warmup) if total > args.warmup else 1
-    warm = max(0, total - steps)
-    frames = make_frames(2, H, W, seed=0)
-    boxes, fidx = make_boxes(2, FACES_PER_FRAME, H, W, seed=1)
-    for _ in range(warm):
-        cpu_reference_frames(1, models, frames, boxes, fidx)
-    el = 0.0
-    for s in range(steps):
-        el += cpu_reference_frames(1, models, frames[s % 2:], boxes[(s % 2) * FACES_PER_FRAME:], fidx[(s % 2) * FACES_PER_FRAME:] - (s % 2))
-    fps = steps * n_per_step / el
-    cores = torch.get_num_threads()
-    line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=steps, warmup=warm,
+    cores = cpu_ref.host_cores()
+    frames_per_step = 2
+    frames = make_frames(N_TIMES, H, W, seed=0, shift_per_frame=SHIFT).numpy()
+    boxes, _ = make_boxes(N_TIMES, FACES_PER_FRAME, H, W, seed=1)
+    boxes = boxes.numpy().reshape(N_TIMES, FACES_PER_FRAME, 4)
+    path = CpuPath(models, cores)
+    path.start_tracks(frames[0])
+    k = 0
+    for _ in range(max(1, min(args.warmup, 3)) * frames_per_step):
+        k += 1
+        path.frame(frames[time_index(k)], boxes[time_index(k)])
+    steps = max(1, min(args.steps, 40))
+    t0 = time.perf_counter()
+    for _ in range(steps * frames_per_step):
+        k += 1
+        path.frame(frames[time_index(k)], boxes[time_index(k)])
+    el = time.perf_counter() - t0
+    fps = steps * frames_per_step / el
+    sample = "%d steps x %d 1080p frames of one stream (same per-frame work as the GPU step)" % (steps, frames_per_step)
+    line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 3),
                 ms_per_step=1000.0 * el / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload=WORKLOAD, frames_per_step=n_per_step, faces_per_frame=FACES_PER_FRAME,
-                            sample="each step = one 1080p frame of the same workload through the CPU restatement"),
-                cpu_baseline=dict(value=fps, unit="frames/s", cores=cores, kind="port",
-                                  sample="%d x 1080p frame(s), oracle restatement (torch-CPU fp32 convs + numpy)" % steps),
+                config=dict(workload=WORKLOAD, frames_per_step=frames_per_step, faces_per_frame=FACES_PER_FRAME,
+                            tracker_updates_per_frame=2 * TRACKS_PER_STREAM, sample=sample,
+                            implementation="restated dlib-style CPU baseline: C++ -O3 -march=native, fp32 blocked direct "
+                                           "convolutions, OpenMP (oracle/cpu); not dlib itself (absent here)"),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=path.threads, kind="port", sample=sample,
+                                  host_threads_visible=os.cpu_count()),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -145,10 +204,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tracker", action="store_true", help="leave the tracker updates out of the step (C2 without tracking)")
     ap.add_argument("--profile-convs", type=int, default=2, help="instrumented steps for the roofline leg")
-    ap.add_argument("--pipeline", action="store_true",
-                    help="build the pyramid of batch s+1 on a second stream under the convs of batch s (measured: +1.7 %, the "
-                         "pyramid's warps take issue slots from the MMA-issuing thread; off by default)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -176,175 +233,116 @@ def main():
         dist.barrier()
     from pyannote_video_b200 import _lib
     from pyannote_video_b200.face import Face
+    from pyannote_video_b200.tracker import TrackerBank
     from pyannote_video_b200.synth import make_frames, make_boxes
 
     det_m, sp_m, emb_m = make_models()
     B = args.frames_per_step
+    use_tracker = not args.no_tracker
     face = Face(landmarks=sp_m, embedding=emb_m, detector=det_m, upsample=1, device=dev, max_frames=B,
                 max_faces=B * FACES_PER_FRAME)
-    # distinct input batches, together larger than L2 (126 MB): 4 x B x 6.2 MB
-    n_sets = 4
-    host_sets, dev_sets, box_sets = [], [], []
-    for s in range(n_sets):
-        fr = make_frames(B, H, W, seed=1000 * rank + s, device=dev)
-        dev_sets.append(fr)
-        host_sets.append(fr.cpu().pin_memory())
-        bx, fi = make_boxes(B, FACES_PER_FRAME, H, W, seed=1 + s + 10 * rank)
+    # B streams x N_TIMES consecutive frames each (a translating canvas per stream): 4 x B x 6.2 MB, larger than L2
+    dev_sets = [torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev) for _ in range(N_TIMES)]
+    for b in range(B):
+        seq = make_frames(N_TIMES, H, W, seed=1000 * rank + b, device=dev, shift_per_frame=SHIFT)
+        for t in range(N_TIMES):
+            dev_sets[t][b] = seq[t]
+        del seq
+    host_sets = [fr.cpu().pin_memory() for fr in dev_sets]
+    box_sets = []
+    for t in range(N_TIMES):
+        bx, fi = make_boxes(B, FACES_PER_FRAME, H, W, seed=1 + t + 10 * rank)
         box_sets.append((bx.to(dev), fi.to(dev), bx.pin_memory(), fi.pin_memory()))
 
-    # landmarks + chips + embed of the seeded boxes do not depend on the detector (in `extract` the boxes
-    # come from the track file), so they run on a side stream and fill the SM slots the bandwidth-bound
-    # pyramid kernels leave free.
+    # tracker bank: forward + backward tracker of K tracks in each of the B streams, started on time step 0
+    n_tracks = 2 * TRACKS_PER_STREAM * B
+    bank = None
+    if use_tracker:
+        bank = TrackerBank(capacity=n_tracks, device=dev)
+        rects, sidx = track_rects(B)
+        trk_rects = torch.cat([rects, rects]).to(dev)
+        trk_frame = torch.cat([sidx, sidx]).to(dev)
+        trk_ids = torch.arange(n_tracks, dtype=torch.int32, device=dev)
+        bank.start_batch(dev_sets[0], trk_frame, trk_ids, trk_rects)
+        torch.cuda.synchronize(dev)
+
+    # landmarks + chips + embed of the seeded boxes and the tracker updates do not depend on this frame's detections
+    # (in `extract` the boxes come from the track file; trackers are updated before association, tracking.py:202-206),
+    # so they run on a side stream and fill the SM slots the pyramid kernels leave free.
     side = torch.cuda.Stream(device=dev)
-
     overlap = [True]
-
-    def embed_branch(fr, bx, fi):
-        main = torch.cuda.current_stream()
-        if not overlap[0]:      # instrumented (roofline) steps: everything on one stream, no co-running kernels
-            parts = face.shape_predictor_.predict(fr, bx, fi)
-            net = face.face_recognition_
-            face._chipper.extract(fr, parts, fi, net.chips)
-            return parts, net.forward_chips(bx.shape[0])
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            parts = face.shape_predictor_.predict(fr, bx, fi)
-            net = face.face_recognition_
-            face._chipper.extract(fr, parts, fi, net.chips)
-            emb = net.forward_chips(bx.shape[0])
-        return parts, emb
-
-    # Cross-step software pipeline: the pyramid of batch s+1 (CUDA-core, issue-bound) is built on a low-priority stream
-    # into the second plane while the tensor-core convs of batch s run; the timed region still contains exactly K
-    # pyramid builds and K forward passes (the first build is exposed, the last step prefetches nothing).
     det0 = face._detector_for(H, W)
-    pipelined = args.pipeline
-    if pipelined:
-        det0.enable_double_buffer()
-    lo_pri, hi_pri = torch.cuda.Stream.priority_range()      # (least, greatest) = (0, -5): lower number = higher priority
-    pyr_stream = torch.cuda.Stream(device=dev, priority=lo_pri)
-    if pipelined:
-        # the conv / decode chain runs on a high-priority stream so that its persistent CTAs are placed first and the
-        # pyramid's short CTAs fill what is left of each SM
-        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=hi_pri))
-    built = [None, None]            # event: plane k holds the pyramid of its batch
-    conv1_done = [None, None]       # event: the first conv has finished reading plane k
-    prebuilt = set()
 
-    def submit_build(s, fr, ready=None):
-        k = s % 2
-        with torch.cuda.stream(pyr_stream):
-            if ready is not None:
-                pyr_stream.wait_event(ready)
-            if conv1_done[k] is not None:
-                pyr_stream.wait_event(conv1_done[k])
-            det0.use_plane(k)
-            det0.build_plane(fr, fr.shape[0])
-            ev = torch.cuda.Event()
-            ev.record(pyr_stream)
-            built[k] = ev
-        prebuilt.add(s)
-
-    def detect_pipelined(s, fr, nxt=None):
-        """forward + decode of batch s on the current stream; `nxt` = (frames, ready event) of batch s+1 or None"""
+    def step_device(fr, bx, fi, out=None):
+        """one step on device-resident inputs; returns the dict of result tensors"""
         main = torch.cuda.current_stream()
-        k = s % 2
-        if s not in prebuilt:
-            pyr_stream.wait_stream(main)
-            submit_build(s, fr)
-        prebuilt.discard(s)
-        if nxt is not None:
-            submit_build(s + 1, nxt[0], nxt[1])
-        main.wait_event(built[k])
-        det0.use_plane(k)
-        det0.forward_scores(fr.shape[0])
-        ev = torch.cuda.Event()
-        ev.record(main)
-        conv1_done[k] = ev
-        return det0.decode(fr.shape[0])
-
-    def step_resident(s, last=True):
-        fr = dev_sets[s % n_sets]
-        bx, fi, _, _ = box_sets[s % n_sets]
-        parts, emb = embed_branch(fr, bx, fi)
-        if pipelined:
-            detect_pipelined(s, fr, None if last else (dev_sets[(s + 1) % n_sets], None))
+        if overlap[0]:
+            side.wait_stream(main)
+            ctx = torch.cuda.stream(side)
         else:
-            det0.detect(fr)
-        torch.cuda.current_stream().wait_stream(side)
-        return emb
+            ctx = torch.cuda.stream(main)
+        with ctx:
+            res = face.extract_batch(fr, bx, fi, detect=False, out=out)
+            if use_tracker:
+                bank.update_batch(fr, trk_frame, trk_ids)
+        boxes, scores, counts = det0.detect(fr)
+        res["det_boxes"], res["det_scores"], res["det_counts"] = boxes, scores, counts
+        if overlap[0]:
+            main.wait_stream(side)
+        return res
 
-    # end-to-end step: pinned host frames -> device (side stream, one step ahead) -> the same path ->
-    # detections / landmarks / embeddings copied back to pinned host memory and read one step later.
-    copy_stream = torch.cuda.Stream(device=dev)
-    det_e2e = face._detector_for(H, W)
-    out_host = [dict(boxes=torch.empty(B, det_e2e.MAX_DET, 4, dtype=torch.int32).pin_memory(),
+    res_buf = dict(landmarks=torch.empty(B * FACES_PER_FRAME, 68, 2, dtype=torch.int32, device=dev),
+                   embeddings=torch.empty(B * FACES_PER_FRAME, 128, dtype=torch.float32, device=dev))
+
+    def step_resident(s):
+        t = time_index(s)
+        bx, fi, _, _ = box_sets[t]
+        return step_device(dev_sets[t], bx, fi, out=res_buf)
+
+    # ---------------- end-to-end: pinned host frames -> Face.upload (public API, staging ring + copy stream) -> the same
+    # step -> detections / tracker state / landmarks / embeddings copied back to pinned host memory, read one step behind
+    out_host = [dict(boxes=torch.empty(B, det0.MAX_DET, 4, dtype=torch.int32).pin_memory(),
                      counts=torch.empty(B, dtype=torch.int32).pin_memory(),
                      parts=torch.empty(B * FACES_PER_FRAME, 68, 2, dtype=torch.int32).pin_memory(),
                      emb=torch.empty(B * FACES_PER_FRAME, 128, dtype=torch.float32).pin_memory(),
+                     trk=torch.empty(n_tracks, 5, dtype=torch.float32).pin_memory(),
                      ev=torch.cuda.Event()) for _ in range(2)]
-
-    # three device staging sets allocated once (no allocator traffic, no implicit syncs inside the pipeline):
-    # the copy stream refills set k only after the step that read it has been fully enqueued and finished.
-    n_stage = 3
-    stage = [dict(fr=torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev),
-                  bx=torch.empty(B * FACES_PER_FRAME, 4, dtype=torch.int32, device=dev),
-                  fi=torch.empty(B * FACES_PER_FRAME, dtype=torch.int32, device=dev),
-                  ready=torch.cuda.Event(), done=None) for _ in range(n_stage)]
+    staged = {}
 
     def upload(s):
-        st = stage[s % n_stage]
-        fr_h = host_sets[s % n_sets]
-        _, _, bx_h, fi_h = box_sets[s % n_sets]
-        with torch.cuda.stream(copy_stream):
-            if st["done"] is not None:
-                copy_stream.wait_event(st["done"])
-            st["fr"].copy_(fr_h, non_blocking=True)
-            st["bx"].copy_(bx_h, non_blocking=True)
-            st["fi"].copy_(fi_h, non_blocking=True)
-            st["ready"].record(copy_stream)
-        return st
+        t = time_index(s)
+        _, _, bx_h, fi_h = box_sets[t]
+        staged[s] = face.upload(host_sets[t], bx_h, fi_h, slot=s % 3)
 
     def step_e2e(s, n_total):
-        st = stage[s % n_stage]
+        fr, bx, fi, ready = staged.pop(s)
         main = torch.cuda.current_stream()
-        main.wait_event(st["ready"])
-        ahead = 2 if pipelined else 1             # inputs travel ahead of the pyramid that runs ahead of the convs
-        if s + ahead < n_total:
-            upload(s + ahead)
-        fr, bx, fi = st["fr"], st["bx"], st["fi"]
-        parts, emb = embed_branch(fr, bx, fi)
-        if pipelined:
-            nxt = None
-            if s + 1 < n_total:
-                sn = stage[(s + 1) % n_stage]
-                nxt = (sn["fr"], sn["ready"])
-            boxes, scores, counts = detect_pipelined(s, fr, nxt)
-        else:
-            boxes, scores, counts = det_e2e.detect(fr)
-        main.wait_stream(side)
-        parts.record_stream(main)
+        main.wait_event(ready)
+        if s + 1 < n_total:
+            upload(s + 1)                       # the next step's inputs travel while this step computes
+        res = step_device(fr, bx, fi, out=res_buf)
         o = out_host[s % 2]
-        o["boxes"].copy_(boxes, non_blocking=True)
-        o["counts"].copy_(counts, non_blocking=True)
-        o["parts"].copy_(parts, non_blocking=True)
-        o["emb"].copy_(emb, non_blocking=True)
+        o["boxes"].copy_(res["det_boxes"], non_blocking=True)
+        o["counts"].copy_(res["det_counts"], non_blocking=True)
+        o["parts"].copy_(res["landmarks"], non_blocking=True)
+        o["emb"].copy_(res["embeddings"], non_blocking=True)
+        if use_tracker:
+            o["trk"].copy_(bank.read_state(trk_ids), non_blocking=True)
         o["ev"].record()
-        st["done"] = o["ev"]
+        face.release_upload(s % 3, o["ev"])
+
+    def read_result(s):
+        o = out_host[s % 2]
+        o["ev"].synchronize()
+        return int(o["counts"].sum()) + float(o["emb"][0, 0]) + float(o["trk"][0, 4])   # touch the data on the host
 
     def run_e2e(n_total):
-        for k in range(min(2 if pipelined else 1, n_total)):
-            upload(k)
+        upload(0)
         for s in range(n_total):
             step_e2e(s, n_total)
             if s > 0:
                 read_result(s - 1)                # results are consumed on the host one step behind
         read_result(n_total - 1)
-
-    def read_result(s):
-        o = out_host[s % 2]
-        o["ev"].synchronize()
-        return int(o["counts"].sum()) + float(o["emb"][0, 0])   # touch the data on the host
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -354,7 +352,7 @@ def main():
 
     # ---------------- device-resident timing (value) ----------------
     for s in range(args.warmup):
-        step_resident(s, last=(s == args.warmup - 1))
+        step_resident(s)
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -362,20 +360,21 @@ def main():
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    embs = None
+    res = None
     t_host = time.perf_counter()
     host_ms = None
     n_host = min(4, args.steps)
     for s in range(args.steps):
-        embs = step_resident(s, last=(s == args.steps - 1))
+        res = step_resident(args.warmup + s)
         if s + 1 == n_host:
             # time the host needs to enqueue one step, taken over the first steps only: later the launch queue is full and
             # the host simply waits for the GPU
             host_ms = 1000.0 * (time.perf_counter() - t_host) / n_host
     if world > 1:
         # the path's one exchange: all-gather of the per-rank embeddings before clustering
+        embs = res["embeddings"].contiguous()
         gathered = [torch.empty_like(embs) for _ in range(world)]
-        dist.all_gather(gathered, embs.contiguous())
+        dist.all_gather(gathered, embs)
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
@@ -384,11 +383,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    face._detector_for(H, W).check()
+    det0.check()
     face.face_recognition_.check()
 
     # ---------------- end-to-end timing (host buffers, H2D + D2H inside) ----------------
-    run_e2e(min(args.warmup, 2))
+    run_e2e(min(max(args.warmup, 1), 2))
     sync_all()
     e2e_steps = max(4, args.steps // 2)
     torch.cuda.synchronize(dev)
@@ -405,17 +404,15 @@ def main():
         sampler.stop_flag = True
         sampler.join(timeout=3)
 
-    # ---------------- roofline leg: CUDA events around every tensor-core conv launch ----------------
-    # Dominant kernel family = detconv_kernel (detector convs 2..7, csrc/detconv.cu): achieved = algorithmic
-    # FLOPs of those six layers / their summed launch time.  conv1_fused and the embedder's srgemm launches
-    # are reported beside it ("layers", "all_convs").  `traffic` = dram bytes read+written by the six detconv
-    # launches from the committed `ncu --set full` capture (profiles/ncu_traffic.json, bytes per frame x B).
+    # ---------------- roofline leg: CUDA events around every tensor-core conv launch and every stage ----------------
+    # Dominant kernel family = rsconv_kernel (detector convs 2..7, csrc/rsconv.cu): achieved = algorithmic FLOPs of those
+    # six layers / their summed launch time.  conv1_fused, the embedder's srgemm launches and the tracker bank are reported
+    # beside it.  One un-timed instrumented step runs first (the first instrumented call after a sync absorbs host latency).
     roof = None
     if rank == 0 and args.profile_convs > 0:
-        det = face._detector_for(H, W)
         net = face.face_recognition_
-        det_names = ["conv%d" % (i + 1) for i in range(len(det.convs))]
-        conv_ops = [(n, op) for n, (op, _) in zip(det_names, det.convs)] + [("embed", a[0]) for k, a in net.ops if k == "conv"]
+        det_names = ["conv%d" % (i + 1) for i in range(len(det0.convs))]
+        conv_ops = [(n, op) for n, (op, _) in zip(det_names, det0.convs)] + [("embed", a[0]) for k, a in net.ops if k == "conv"]
         evs = []
         orig = {}
         for name, op in conv_ops:
@@ -428,7 +425,6 @@ def main():
                 b.record()
                 evs.append((_name, a, b))
             op.run = timed_run
-        # coarse stage timing of the same instrumented steps (CUDA events on the launch stream)
         stage_ev = {}
 
         def timed_stage(name, fn):
@@ -441,16 +437,26 @@ def main():
                 return r
             return wrapped
 
-        patched = [(det, "build_plane", "pyramid"), (det, "forward_scores", "convs+shift_sum"), (det, "decode", "decode+nms"),
+        patched = [(det0, "build_plane", "pyramid"), (det0, "forward_scores", "convs+shift_sum"), (det0, "decode", "decode+nms"),
                    (face.shape_predictor_, "predict", "landmarks"), (face._chipper, "extract", "chips"),
                    (net, "forward_chips", "embed")]
+        if use_tracker:
+            patched.append((bank, "update_batch", "tracker"))
         saved = [(o, n, getattr(o, n)) for o, n, _ in patched]
         for o, n, label in patched:
             setattr(o, n, timed_stage(label, getattr(o, n)))
         overlap[0] = False
-        for s in range(args.profile_convs):
-            step_resident(s)
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step_resident(0)                                     # un-timed instrumented step (warms the patched path)
         torch.cuda.synchronize(dev)
+        evs.clear()
+        stage_ev.clear()
+        ev_a.record()
+        for s in range(args.profile_convs):
+            step_resident(1 + s)
+        ev_b.record()
+        torch.cuda.synchronize(dev)
+        serial_ms = ev_a.elapsed_time(ev_b) / args.profile_convs
         overlap[0] = True
         for o, n, f in saved:
             setattr(o, n, f)
@@ -461,33 +467,43 @@ def main():
         layer_ms = {}
         for name, a, b in evs:
             layer_ms[name] = layer_ms.get(name, 0.0) + a.elapsed_time(b) / P
-        layer_flops = {n: B * f for n, f in zip(det_names, det.algorithmic_flops_per_layer)}   # per pyramid pixel, padding excluded
+        layer_flops = {n: B * f for n, f in zip(det_names, det0.algorithmic_flops_per_layer)}   # per pyramid pixel, padding excluded
         layer_flops["embed"] = B * FACES_PER_FRAME * net.flops_per_face
         peaks = load_peaks()
         peak = peaks["tf_sustained"]
         layers = {n: dict(ms=round(layer_ms[n], 4), tflops=round(layer_flops[n] / (layer_ms[n] * 1e-3) / 1e12, 1),
                           frac=round(layer_flops[n] / (layer_ms[n] * 1e-3) / 1e12 / peak, 4)) for n in layer_ms}
-        dom = [n for n in det_names[1:]] if det.conv_impl in ("detconv", "rsconv") else det_names
+        dom = det_names[1:]
         dom_ms = sum(layer_ms[n] for n in dom)
         dom_fl = sum(layer_flops[n] for n in dom)
         all_ms = sum(layer_ms.values())
         all_fl = sum(layer_flops.values())
-        traffic = None
+        traffic, traffic_source = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if det.conv_impl in ("detconv", "rsconv") and os.path.exists(tpath):
+        if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            if tj.get("plane") == [det.geo.plane_h, det.geo.plane_w] and tj.get("impl", "detconv") == det.conv_impl:
+            if tj.get("plane") == [det0.geo.plane_h, det0.geo.plane_w] and tj.get("impl", "detconv") == det0.conv_impl:
                 traffic = tj["detconv_dram_bytes_per_frame"] * B
+                traffic_source = ("static: dram__bytes_read+write of the six rsconv launches from the committed ncu --set full "
+                                  "capture (profiles/ncu_traffic.json: %s), x frames per step; not measured in this run"
+                                  % tj.get("source", "r01"))
         achieved = dom_fl / (dom_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
-                    peak_source=peaks["source"],
-                    kernel=("%s_kernel (detector convs 2..7, %d launches/step)" % (det.conv_impl, len(dom)))
-                    if det.conv_impl in ("detconv", "rsconv") else "srgemm_kernel (detector convs)",
+                    traffic_source=traffic_source, peak_source=peaks["source"],
+                    kernel="rsconv_kernel (detector convs 2..7, %d launches/step)" % len(dom),
                     kernel_ms_per_step=round(dom_ms, 4), algorithmic_flops_per_step=dom_fl,
                     all_convs=dict(ms_per_step=round(all_ms, 4), tflops=round(all_fl / (all_ms * 1e-3) / 1e12, 1),
                                    frac=round(all_fl / (all_ms * 1e-3) / 1e12 / peak, 4), launches_per_step=len(evs) // P),
-                    layers=layers, stage_ms_per_step={k: round(v, 3) for k, v in stage_ms.items()})
+                    layers=layers, stage_ms_per_step={k: round(v, 3) for k, v in stage_ms.items()},
+                    serial_step_ms=round(serial_ms, 3))
+        if use_tracker and "tracker" in stage_ms:
+            ups = n_tracks / (stage_ms["tracker"] * 1e-3)
+            roof["tracker"] = dict(bound="hbm", updates_per_step=n_tracks, ms=round(stage_ms["tracker"], 3),
+                                   updates_per_s=round(ups), achieved=round(ups * TRACKER_BYTES_PER_UPDATE / 1e9, 1),
+                                   peak=peaks["hbm_gbs"], unit="GB/s",
+                                   frac=round(ups * TRACKER_BYTES_PER_UPDATE / 1e9 / peaks["hbm_gbs"], 4),
+                                   algorithmic_bytes_per_update=TRACKER_BYTES_PER_UPDATE)
 
     if rank != 0:
         if world > 1:
@@ -498,26 +514,35 @@ def main():
     value = frames_total / (ms_max * 1e-3)
     e2e_value = e2e_steps * B * world / (ms_e2e * 1e-3)
     h2d = B * H * W * 3 + B * FACES_PER_FRAME * (16 + 4)
-    det = face._detector_for(H, W)
-    d2h = B * det.MAX_DET * 16 + B * 4 + B * FACES_PER_FRAME * (68 * 2 * 4 + 128 * 4)
+    d2h = B * det0.MAX_DET * 16 + B * 4 + B * FACES_PER_FRAME * (68 * 2 * 4 + 128 * 4) + (n_tracks * 20 if use_tracker else 0)
 
     cpu = None
     if not args.no_cpu_baseline:
-        n_cpu = 2
-        fr_cpu = host_sets[0][:n_cpu].clone()
-        bx, fi = make_boxes(n_cpu, FACES_PER_FRAME, H, W, seed=1)
-        el = cpu_reference_frames(n_cpu, (det_m, sp_m, emb_m), fr_cpu, bx, fi)
-        cpu = dict(value=n_cpu / el, unit="frames/s", cores=torch.get_num_threads(), kind="port",
-                   sample="%d x 1080p frames through the oracle restatement (torch-CPU fp32 convs + numpy), %.1f s" % (n_cpu, el))
+        from oracle import cpu_ref
+        models = (det_m, sp_m, emb_m)
+        cores = cpu_ref.host_cores()
+        el1, _ = cpu_sample(models, 1, 2)
+        n_all = max(4, min(40, int(2 * cores * 0.5)))
+        el_n, used = cpu_sample(models, cores, n_all)
+        cpu = dict(value=n_all / el_n, unit="frames/s", cores=used, kind="port",
+                   sample="%d x 1080p frames of one stream (detect + %d tracker updates + %d faces) through the C++ restatement "
+                          "oracle/cpu (-O3 -march=native, OpenMP), %.1f s" % (n_all, 2 * TRACKS_PER_STREAM, FACES_PER_FRAME, el_n),
+                   single_thread=dict(value=2 / el1, cores=1, sample="2 frames, %.1f s" % el1),
+                   core_scaling=round((n_all / el_n) / (2 / el1), 2), host_threads_visible=os.cpu_count())
 
     line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                 data="synthetic",
-                config=dict(workload=WORKLOAD, frames_per_step=B, faces_per_frame=FACES_PER_FRAME, parallelism="frame-shard x%d" % world, pipeline=("pyramid of batch s+1 under the convs of batch s" if pipelined else "none"),
+                config=dict(workload=WORKLOAD, frames_per_step=B, faces_per_frame=FACES_PER_FRAME,
+                            tracker_updates_per_frame=(2 * TRACKS_PER_STREAM if use_tracker else 0),
+                            streams="%d concurrent shot streams per GPU, one frame each per step" % B,
+                            parallelism="frame-shard x%d" % world,
                             l2="%d distinct input batches (%d MB) + ~1.4 GB/frame of plane and activation traffic per step: "
-                               "inputs larger than L2" % (n_sets, n_sets * B * H * W * 3 // 1000000)),
+                               "inputs larger than L2" % (N_TIMES, N_TIMES * B * H * W * 3 // 1000000)),
                 clocks=sampler.summary(),
-                e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps),
+                e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
+                         api="Face.upload (pinned host -> staging ring) + Face.extract_batch + DetectorNet.detect + "
+                             "TrackerBank.update_batch, results to pinned host memory"),
                 gpu_launches=int(launches), host_enqueue_ms_per_step=round(host_ms, 3),
                 roofline=roof, cpu_baseline=cpu)
     print(json.dumps(line), flush=True)

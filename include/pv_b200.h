@@ -278,6 +278,13 @@ int pv_pool_rows(const float* S, int64_t tin, const int* offs, const int* memb, 
 int pv_pool_cols(const float* R, int64_t tin, const int* offs, const int* memb, float* Sout, int64_t tout, void* stream);
 /* nearest cluster of every cluster under average linkage S[A][C]/(size_A*size_C) */
 int pv_row_argmin(const float* S, int64_t t, const float* sizes, int* nn, float* nnd, void* stream);
+/* one agglomeration round on the device (pyannote.algorithms' greedy loop behind clustering.py:138-148, as rounds of
+ * reciprocal-nearest-neighbour merges): plan -> (caller: exclusive prefix sum of keep) -> members -> contract -> relabel */
+int pv_hac_plan(const int* nn, const float* nnd, int64_t t, float threshold, int strict, int* keep, int* partner, void* stream);
+int pv_hac_members(const int* keep, const int* partner, const int* newidx, const int* nn, const float* sizes, int64_t t,
+                   int* m0, int* m1, float* sizes2, int* map, void* stream);
+int pv_hac_contract(const float* S, int64_t t, const int* m0, const int* m1, float* S2, int64_t tout, void* stream);
+int pv_hac_relabel(int* cl, int64_t n, const int* map, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * correlation-tracker bank (csrc/tracker.cu) — dlib.correlation_tracker start_track / update /

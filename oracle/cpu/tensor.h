@@ -5,7 +5,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <memory>
+#include <mutex>
+#include <vector>
 
 namespace pvc {
 
@@ -17,6 +20,42 @@ static inline v16 v16_max0(v16 v) {
   const v16 z = v16{};
   return v > z ? v : z;
 }
+
+// free-list of activation blocks keyed by size: a frame's tensors are reused by the next frame instead of being
+// returned to the OS (fresh zero pages cost a page fault per 4 KB: half of the run time at 16 threads)
+struct BlockPool {
+  std::mutex mu;
+  std::multimap<size_t, char*> free_blocks;
+  size_t held = 0;
+  static BlockPool& get() {
+    static BlockPool p;
+    return p;
+  }
+  char* take(size_t bytes, bool* fresh) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = free_blocks.find(bytes);
+      if (it != free_blocks.end()) {
+        char* p = it->second;
+        free_blocks.erase(it);
+        held -= bytes;
+        *fresh = false;
+        return p;
+      }
+    }
+    *fresh = true;
+    return static_cast<char*>(calloc(bytes, 1));
+  }
+  void give(size_t bytes, char* p) {
+    std::lock_guard<std::mutex> g(mu);
+    if (held + bytes > ((size_t)6 << 30)) {   // keep at most 6 GiB parked
+      free(p);
+      return;
+    }
+    free_blocks.emplace(bytes, p);
+    held += bytes;
+  }
+};
 
 struct Tensor {
   int N = 0, H = 0, W = 0, C = 0, Cp = 0, halo = 0;
@@ -32,9 +71,14 @@ struct Tensor {
     pitch_px = (long)W + 2 * halo + 48;     // slack: register tiles may read past the last output's window
     rows = (long)H + 2 * halo + 2;
     const size_t n_float = (size_t)N * rows * pitch_px * Cp + 64;
-    // calloc: large blocks come from fresh zero pages (no memset pass; first touch happens in the worker threads)
-    char* raw = static_cast<char*>(calloc(n_float * sizeof(float) + 64, 1));
-    raw_store = std::shared_ptr<char>(raw, free);
+    // pooled blocks; a fresh block is calloc'ed (zero pages, first touch in the worker threads).  A recycled block is
+    // cleared only when the tensor has a halo that must read as zero: without a halo every element a kept output
+    // depends on is written by the producer, and the slack only feeds register-tile lanes that are discarded.
+    const size_t bytes = n_float * sizeof(float) + 64;
+    bool fresh = false;
+    char* raw = BlockPool::get().take(bytes, &fresh);
+    raw_store = std::shared_ptr<char>(raw, [bytes](char* p) { BlockPool::get().give(bytes, p); });
+    if (!fresh && halo > 0) memset(raw, 0, bytes);
     base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(raw) + 63) & ~(uintptr_t)63);
   }
   inline long row_stride() const { return pitch_px * Cp; }

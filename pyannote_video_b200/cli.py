@@ -131,9 +131,12 @@ def face_generator(tracking, frame_width, frame_height, reference_quirks=False):
 
 
 def track(video, shot, output, detect_min_size=0.0, detect_every=0.0, track_min_overlap_ratio=MIN_OVERLAP_RATIO,
-          track_min_confidence=MIN_CONFIDENCE, track_max_gap=MAX_GAP, face=None, tracker_bank=None):
+          track_min_confidence=MIN_CONFIDENCE, track_max_gap=MAX_GAP, face=None, tracker_bank=None, detector=None):
     """Tracking by detection"""
     from .tracking import FaceTracking
+    if face is None:
+        from .face import Face
+        face = Face(detector=detector)
     tracking = FaceTracking(detect_min_size=detect_min_size, detect_every=detect_every,
                             track_min_overlap_ratio=track_min_overlap_ratio,
                             track_min_confidence=track_min_confidence, track_max_gap=track_max_gap, face=face,
@@ -179,9 +182,9 @@ def extract(video, landmark_model, embedding_model, tracking, landmark_output, e
             fembedding.flush()
 
 
-def detect(video, output, face=None):
+def detect(video, output, face=None, detector=None):
     from .face import Face
-    face = face if face is not None else Face()
+    face = face if face is not None else Face(detector=detector)
     w, h = video.frame_size
     with open(output, 'w') as f:
         for t, rgb in video:
@@ -195,9 +198,10 @@ def cluster_cmd(embeddings, output, threshold=0.6, metric="euclidean"):
     clustering = FaceClustering(threshold=threshold, metric=metric)
     starting_point, features = clustering.model.preprocess(embeddings)
     result = clustering(starting_point, features=features)
+    labels = result.to_dict()
     with open(output, 'w') as f:
-        for trk in sorted(result):
-            f.write('{0:d} {1:d}\n'.format(trk, result[trk]))
+        for trk in sorted(labels):
+            f.write('{0:d} {1:d}\n'.format(trk, labels[trk]))
     return result
 
 
@@ -206,6 +210,9 @@ def main(argv=None):
                                  formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--frame-rate", type=float, default=25.0)
+    ap.add_argument("--detector", default=None,
+                    help="CNN (MMOD) detector model: mmod_human_face_detector.dat, an .npz container, or 'synthetic' "
+                         "(default: $PYANNOTE_FACE_DETECTOR)")
     sub = ap.add_subparsers(dest="verb", required=True)
     p = sub.add_parser("track")
     p.add_argument("video")
@@ -236,12 +243,13 @@ def main(argv=None):
     a = ap.parse_args(argv)
     if a.verb == "track":
         track(open_video(a.video, a.frame_rate), a.shot, a.tracking, detect_min_size=a.min_size, detect_every=a.every,
-              track_min_overlap_ratio=a.min_overlap, track_min_confidence=a.min_confidence, track_max_gap=a.max_gap)
+              track_min_overlap_ratio=a.min_overlap, track_min_confidence=a.min_confidence, track_max_gap=a.max_gap,
+              detector=a.detector)
     elif a.verb in ("extract", "embed"):
         extract(open_video(a.video, a.frame_rate), a.landmark_model, a.embedding_model, a.tracking, a.landmarks,
                 a.embeddings, reference_quirks=a.reference_quirks)
     elif a.verb == "detect":
-        detect(open_video(a.video, a.frame_rate), a.detections)
+        detect(open_video(a.video, a.frame_rate), a.detections, detector=a.detector)
     elif a.verb == "cluster":
         cluster_cmd(a.embeddings, a.labels, threshold=a.threshold, metric=a.metric)
     return 0

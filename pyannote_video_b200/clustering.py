@@ -5,10 +5,10 @@ Reference semantics kept: embeddings are read from `embedding.txt` (`time track 
 by (track, time); tracks observed at a single timestamp are not clustered (clustering.py:78-79);
 initial clusters are tracks; linkage = mean of all pairwise EUCLIDEAN embedding distances between
 two clusters; merging stops once the closest pair is farther than `threshold` (default 0.6).
-`metric='cosine'` is the north_star's variant of the same kernels.  pyannote.core is not available
-here, so `__call__` returns a plain dict {track: cluster_label} (label = smallest track id in the
-cluster) instead of an `Annotation`; `FaceClustering.annotation(...)` renders the same information
-as (segment, track, label) triples.
+`metric='cosine'` is the north_star's variant of the same kernels.  `preprocess` returns the starting
+point as an `Annotation` (one segment per track, track name = label = track id) and `__call__` returns an
+`Annotation` with the merged labels (label = smallest track id of the cluster), like the reference;
+pyannote.core is absent here, `annotation.py` provides the duck types (`.to_dict()` gives {track: label}).
 """
 import ctypes as C
 
@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .annotation import Annotation, Segment
 
 
 def _i32(a, dev):
@@ -51,7 +52,6 @@ def cluster(emb, track_id, threshold=0.6, metric="euclidean", strict=False, devi
     _lib.check(L.pv_pdist(_lib.ptr(X), C.c_int64(N), 128, m, _lib.ptr(D), st), "pv_pdist")
     # members of current clusters, in terms of the rows/cols of the current matrix
     sizes = np.diff(np.append(start, N)).astype(np.int64)            # embeddings per track
-    groups = [[int(t)] for t in range(T)]                              # track indices per cluster
 
     def contract(S, tin, member_lists):
         tout = len(member_lists)
@@ -72,45 +72,44 @@ def cluster(emb, track_id, threshold=0.6, metric="euclidean", strict=False, devi
     else:
         S = contract(D, N, [order[start[t]:start[t] + sizes[t]].tolist() for t in range(T)])
         del D
-    csize = sizes.astype(np.float64)                                   # embeddings per cluster
+    # ---- agglomeration rounds, entirely on the device: the host only learns how many clusters are left ----
+    t = T
+    sz = torch.from_numpy(sizes.astype(np.float32)).to(dev)           # embeddings per cluster
+    cl = torch.arange(T, dtype=torch.int32, device=dev)               # cluster index of every track
     rounds = 0
-    while len(groups) > 1 and rounds < max_rounds:
-        t = len(groups)
-        sz = torch.from_numpy(csize.astype(np.float32)).to(dev)
+    while t > 1 and rounds < max_rounds:
         nn = torch.empty(t, dtype=torch.int32, device=dev)
         nnd = torch.empty(t, dtype=torch.float32, device=dev)
         _lib.check(L.pv_row_argmin(_lib.ptr(S), C.c_int64(t), _lib.ptr(sz), _lib.ptr(nn), _lib.ptr(nnd), st),
                    "pv_row_argmin")
-        nn_h, nnd_h = nn.cpu().numpy(), nnd.cpu().numpy()
-        idx = np.arange(t)
-        ok = (nnd_h < threshold) if strict else (nnd_h <= threshold)
-        recip = (nn_h[nn_h] == idx) & ok & (idx < nn_h)
-        pairs = idx[recip]
-        if len(pairs) == 0:
+        keep = torch.empty(t, dtype=torch.int32, device=dev)
+        partner = torch.empty(t, dtype=torch.int32, device=dev)
+        _lib.check(L.pv_hac_plan(_lib.ptr(nn), _lib.ptr(nnd), C.c_int64(t), C.c_float(threshold), int(bool(strict)),
+                                 _lib.ptr(keep), _lib.ptr(partner), st), "pv_hac_plan")
+        incl = torch.cumsum(keep, 0, dtype=torch.int32)
+        tout = int(incl[-1].item())                                   # the round's only device -> host read
+        if tout == t:
             break
-        merged_into = np.full(t, -1, np.int64)
-        merged_into[nn_h[pairs]] = pairs
-        new_members, new_groups, new_sizes = [], [], []
-        for a in range(t):
-            if merged_into[a] >= 0:
-                continue
-            if recip[a]:
-                b = int(nn_h[a])
-                new_members.append([a, b])
-                new_groups.append(groups[a] + groups[b])
-                new_sizes.append(csize[a] + csize[b])
-            else:
-                new_members.append([a])
-                new_groups.append(groups[a])
-                new_sizes.append(csize[a])
-        S = contract(S, t, new_members)
-        groups, csize = new_groups, np.asarray(new_sizes, np.float64)
+        newidx = (incl - keep).contiguous()
+        m0 = torch.empty(tout, dtype=torch.int32, device=dev)
+        m1 = torch.empty(tout, dtype=torch.int32, device=dev)
+        sz2 = torch.empty(tout, dtype=torch.float32, device=dev)
+        mp = torch.empty(t, dtype=torch.int32, device=dev)
+        _lib.check(L.pv_hac_members(_lib.ptr(keep), _lib.ptr(partner), _lib.ptr(newidx), _lib.ptr(nn), _lib.ptr(sz),
+                                    C.c_int64(t), _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(sz2), _lib.ptr(mp), st),
+                   "pv_hac_members")
+        S2 = torch.empty(tout, tout, dtype=torch.float32, device=dev)
+        _lib.check(L.pv_hac_contract(_lib.ptr(S), C.c_int64(t), _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(S2), C.c_int64(tout), st),
+                   "pv_hac_contract")
+        _lib.check(L.pv_hac_relabel(_lib.ptr(cl), C.c_int64(T), _lib.ptr(mp), st), "pv_hac_relabel")
+        S, sz, t = S2, sz2, tout
+        del S2
         rounds += 1
-    labels = np.zeros(T, np.int64)
-    for g in groups:
-        lab = tracks[min(g)]
-        for ti in g:
-            labels[ti] = lab
+    # label of a cluster = its smallest track id (tracks are sorted: the smallest track INDEX)
+    first = torch.full((t, ), T, dtype=torch.int64, device=dev)
+    first.scatter_reduce_(0, cl.long(), torch.arange(T, device=dev), reduce="amin")
+    labels = tracks[first[cl.long()].cpu().numpy()]
+    groups = range(t)
     if return_stats:
         return tracks, labels, dict(rounds=rounds, n_clusters=len(groups))
     return tracks, labels
@@ -120,20 +119,20 @@ class _Model(object):
     """Average Euclidean distance between face embeddings (reference: clustering.py:49-119)"""
 
     def preprocess(self, embedding):
-        """Read `embedding.txt`; returns (starting_point, data): starting_point maps track ->
-        (start, end) for tracks seen at more than one timestamp, data is a dict of arrays
-        time/track/X sorted by (track, time)."""
+        """Read `embedding.txt` (`time track d0..d127`); returns (starting_point, data): starting_point is an
+        Annotation with one segment [first, last timestamp] per track (tracks seen at a single timestamp give an
+        empty segment and are dropped, clustering.py:76-80), data a dict of arrays time/track/X sorted by
+        (track, time) (the reference's DataFrame)."""
         raw = np.loadtxt(embedding, ndmin=2, dtype=np.float64)
         if raw.shape[1] != 130:
             raise ValueError("embedding file must have 130 columns (time track d0..d127)")
         order = np.lexsort((raw[:, 0], raw[:, 1]))
         raw = raw[order]
         time, track, X = raw[:, 0], raw[:, 1].astype(np.int64), raw[:, 2:]
-        starting_point = {}
+        starting_point = Annotation(modality="face")
         for t in np.unique(track):
             ts = time[track == t]
-            if ts.max() > ts.min():            # empty Segment (single timestamp) is skipped
-                starting_point[int(t)] = (float(ts.min()), float(ts.max()))
+            starting_point[Segment(float(ts.min()), float(ts.max())), int(t)] = int(t)
         return starting_point, dict(time=time, track=track, X=X)
 
 
@@ -144,6 +143,11 @@ class FaceClustering(object):
     ----------
     threshold : float, optional
         Defaults to 0.6.
+    force : bool, optional
+        Passed by the reference to pyannote.algorithms' `DistanceThreshold(threshold, force)`
+        (clustering.py:140-141).  With `constraint=None` (clustering.py:143-144) no merge is ever vetoed, so the
+        flag cannot change the partition at the threshold [MEMORY of pyannote.algorithms 0.8 — unverified]; it is
+        accepted and recorded.
 
     Usage
     -----
@@ -153,20 +157,30 @@ class FaceClustering(object):
     """
 
     def __init__(self, threshold=0.6, force=False, logger=None, metric="euclidean"):
-        if force:
-            raise NotImplementedError("force=True is not used by the reference pipeline")
         self.threshold = threshold
+        self.force = bool(force)
         self.metric = metric
         self.logger = logger
         self.model = _Model()
 
     def __call__(self, starting_point, features=None):
-        keep = np.isin(features["track"], np.asarray(sorted(starting_point), np.int64))
+        if isinstance(starting_point, Annotation):
+            wanted = sorted(t for _, t in starting_point.itertracks())
+        else:
+            wanted = sorted(starting_point)
+        result = Annotation(modality="face") if not isinstance(starting_point, Annotation) else \
+            Annotation(starting_point.uri, starting_point.modality)
+        if not wanted:
+            return result
+        keep = np.isin(features["track"], np.asarray(wanted, np.int64))
         X = features["X"][keep].astype(np.float32)
         tr = features["track"][keep]
         tracks, labels = cluster(X, tr, threshold=self.threshold, metric=self.metric)
-        return {int(t): int(l) for t, l in zip(tracks, labels)}
-
-    @staticmethod
-    def annotation(starting_point, result):
-        return [(starting_point[t], t, result[t]) for t in sorted(result)]
+        lab = {int(t): int(l) for t, l in zip(tracks, labels)}
+        if isinstance(starting_point, Annotation):
+            for segment, track in starting_point.itertracks():
+                result[segment, track] = lab[int(track)]
+        else:
+            for track in wanted:
+                result[Segment(*starting_point[track]), track] = lab[int(track)]
+        return result

@@ -150,7 +150,115 @@ __global__ void __launch_bounds__(256) row_argmin_kernel(const float* __restrict
   }
 }
 
+// ---- one agglomeration round entirely on the device -------------------------------------------------------------
+// plan: cluster a merges with b = nn[a] iff they are reciprocal nearest neighbours and their average distance is under the
+// threshold; the pair is represented by its smaller index.  keep[a] = 1 for clusters that survive as a representative,
+// partner[a] = the absorbed cluster (or -1).
+__global__ void hac_plan_kernel(const int* __restrict__ nn, const float* __restrict__ nnd, int t, float thr, int strict,
+                                int* __restrict__ keep, int* __restrict__ partner) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= t) return;
+  const int b = nn[a];
+  bool absorbed = false, leads = false;
+  if (b >= 0 && nn[b] == a) {
+    const int lo = a < b ? a : b;
+    const bool ok = strict ? (nnd[lo] < thr) : (nnd[lo] <= thr);    // judged from the representative's row
+    leads = ok && a < b;
+    absorbed = ok && b < a;
+  }
+  keep[a] = absorbed ? 0 : 1;
+  partner[a] = leads ? b : -1;
+}
+
+// members of the new clusters (A = newidx[a] for kept a), their sizes, and the old -> new index map
+__global__ void hac_members_kernel(const int* __restrict__ keep, const int* __restrict__ partner, const int* __restrict__ newidx,
+                                   const int* __restrict__ nn, const float* __restrict__ sizes, int t, int* __restrict__ m0,
+                                   int* __restrict__ m1, float* __restrict__ sizes2, int* __restrict__ map) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= t) return;
+  if (keep[a]) {
+    const int A = newidx[a];
+    const int b = partner[a];
+    m0[A] = a;
+    m1[A] = b;
+    sizes2[A] = sizes[a] + (b >= 0 ? sizes[b] : 0.f);
+    map[a] = A;
+  } else {
+    map[a] = newidx[nn[a]];
+  }
+}
+
+// S2[A][B] = sum over the (at most 2 x 2) old clusters: rows pooled first, then columns (same order as pool_rows + pool_cols)
+__global__ void hac_contract_kernel(const float* __restrict__ S, long long t, const int* __restrict__ m0, const int* __restrict__ m1,
+                                    float* __restrict__ S2, long long tout) {
+  const long long A = blockIdx.y;
+  const long long B = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (A >= tout || B >= tout) return;
+  const int a0 = m0[A], a1 = m1[A], b0 = m0[B], b1 = m1[B];
+  const float* r0 = S + (long long)a0 * t;
+  float v = r0[b0];
+  if (a1 >= 0) v += S[(long long)a1 * t + b0];
+  if (b1 >= 0) {
+    float w = r0[b1];
+    if (a1 >= 0) w += S[(long long)a1 * t + b1];
+    v += w;
+  }
+  S2[A * tout + B] = v;
+}
+
+__global__ void hac_relabel_kernel(int* __restrict__ cl, long long n, const int* __restrict__ map) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cl[i] = map[cl[i]];
+}
+
 }  // namespace
+
+extern "C" int pv_hac_plan(const int* nn, const float* nnd, int64_t t, float threshold, int strict, int* keep, int* partner,
+                           void* stream) {
+  PV_REQUIRE(nn && nnd && keep && partner, "pv_hac_plan: null argument");
+  if (t == 0) return PV_OK;
+  hac_plan_kernel<<<(unsigned)((t + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(nn, nnd, (int)t, threshold, strict,
+                                                                                            keep, partner);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+/* newidx = exclusive prefix sum of keep (caller); writes members m0/m1 [tout], sizes2 [tout], map [t] */
+extern "C" int pv_hac_members(const int* keep, const int* partner, const int* newidx, const int* nn, const float* sizes,
+                              int64_t t, int* m0, int* m1, float* sizes2, int* map, void* stream) {
+  PV_REQUIRE(keep && partner && newidx && nn && sizes && m0 && m1 && sizes2 && map, "pv_hac_members: null argument");
+  if (t == 0) return PV_OK;
+  hac_members_kernel<<<(unsigned)((t + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(keep, partner, newidx, nn, sizes,
+                                                                                               (int)t, m0, m1, sizes2, map);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_hac_contract(const float* S, int64_t t, const int* m0, const int* m1, float* S2, int64_t tout, void* stream) {
+  PV_REQUIRE(S && m0 && m1 && S2, "pv_hac_contract: null argument");
+  if (tout == 0) return PV_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long maxy = 65535;
+  for (long long a0 = 0; a0 < tout; a0 += maxy) {
+    const long long na = (tout - a0 < maxy) ? tout - a0 : maxy;
+    hac_contract_kernel<<<dim3((unsigned)((tout + 255) / 256), (unsigned)na), 256, 0, s>>>(S, t, m0 + a0, m1 + a0, S2 + a0 * tout,
+                                                                                          tout);
+    g_pv_launches.fetch_add(1);
+  }
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_hac_relabel(int* cl, int64_t n, const int* map, void* stream) {
+  PV_REQUIRE(cl && map, "pv_hac_relabel: null argument");
+  if (n == 0) return PV_OK;
+  hac_relabel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cl, n, map);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
 
 extern "C" int pv_pdist(const float* X, int64_t n, int dim, int metric, float* D, void* stream) {
   PV_REQUIRE(X && D, "pv_pdist: null argument");

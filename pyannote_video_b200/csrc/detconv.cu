@@ -344,12 +344,11 @@ constexpr int kNumInstances = sizeof(kInstances) / sizeof(kInstances[0]);
 
 template <int C, int N, int KH, int KW, int S, bool F32>
 cudaError_t launch(const DcPlan* plan, const DcParams& p, int grid, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (pv_attr_needed(&attr)) {
     cudaError_t e = cudaFuncSetAttribute(detconv_kernel<C, N, KH, KW, S, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   detconv_kernel<C, N, KH, KW, S, F32><<<grid, kThreads, plan->smem_bytes, st>>>(p);
   return cudaGetLastError();

@@ -529,10 +529,9 @@ extern "C" int pv_det_nms(const int* counts, const float* cand_score, const int*
   g.iou_thresh = iou_thresh;
   g.covered_thresh = covered_thresh;
   const size_t smem = kNmsCap * (sizeof(float) + sizeof(int) + sizeof(int4) + 1);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;
+  if (pv_attr_needed(&attr_set)) {
     PV_CUDA_CHECK(cudaFuncSetAttribute(det_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   det_nms_kernel<<<B, 1024, smem, static_cast<cudaStream_t>(stream)>>>(counts, cand_score, cand_cell, cap, level_rects,
                                                                       level_fxy, g, max_det, out_boxes, out_scores,

@@ -249,3 +249,13 @@ __device__ __forceinline__ uint32_t pv_pack_bf16x2(float lo, float hi) {
 }
 
 #endif  // __CUDACC__
+
+// cudaFuncSetAttribute is per DEVICE: `flags` is a per-kernel static bitmask, bit d = attribute set on device d
+static inline bool pv_attr_needed(unsigned long long* flags) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const unsigned long long bit = 1ull << (d & 63);
+  if (*flags & bit) return false;
+  *flags |= bit;
+  return true;
+}

@@ -447,12 +447,11 @@ constexpr int kNumRsInstances = sizeof(kRsInstances) / sizeof(kRsInstances[0]);
 
 template <int C, int N, int KH, int KW, int S, bool F32>
 cudaError_t rs_launch(const RsPlan* plan, const RsParams& p, int grid, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (pv_attr_needed(&attr)) {
     cudaError_t e = cudaFuncSetAttribute(rsconv_kernel<C, N, KH, KW, S, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   rsconv_kernel<C, N, KH, KW, S, F32><<<grid, kThreads, plan->smem_bytes, st>>>(p);
   return cudaGetLastError();

@@ -45,76 +45,101 @@ __device__ __forceinline__ int rev6(int v) { return (int)(__brev((unsigned)v) >>
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ void bfly(float2& a, float2& b, const float2 w) {
+  const float2 t = cmul(w, b);
+  b = make_float2(a.x - t.x, a.y - t.y);
+  a = make_float2(a.x + t.x, a.y + t.y);
+}
+__device__ __forceinline__ void bfly1(float2& a, float2& b) {   // twiddle 1
+  const float2 t = b;
+  b = make_float2(a.x - t.x, a.y - t.y);
+  a = make_float2(a.x + t.x, a.y + t.y);
+}
 
-// in-place 2-D DIT FFT of a 64x64 complex tile whose input was stored bit-reversed in both dimensions; output in
-// natural order.  inverse: conjugate twiddles (no scaling).  Two radix-2 stages are done per pass in registers
-// (a radix-4 step: the same operations in the same order as two radix-2 stages, so results are unchanged), which
-// halves the block barriers and shared-memory round trips: 6 passes instead of 12 per 2-D transform.
+constexpr int PS = FS + 1;        // padded row pitch of the complex work plane (float2 elements): a warp that walks 32
+                                  // rows at one column then touches 16 distinct 8-byte bank pairs per half-warp
+
+// in-place 2-D DIT FFT of the 64x64 complex tile `x` (row pitch PS) whose input was stored bit-reversed in both
+// dimensions; output in natural order.  inverse: conjugate twiddles (no scaling).  Radix-8: two passes per dimension
+// (stages 1-3 on 8 consecutive elements with constant twiddles, stages 4-6 on elements 8 apart), i.e. 4 block barriers
+// and 4 shared-memory round trips per 2-D transform (the radix-4 version needed 6, the radix-2 one 12).  Thread t owns
+// line t & 63 and butterfly t >> 6, so a warp always walks 32 adjacent LINES: consecutive float2 for the column
+// transform, pitch-65 rows for the row transform — both free of bank conflicts — and the twiddles are warp-uniform.
 __device__ void fft2_64(float2* x, const TrackerTables& tb, bool inverse) {
-  const int tid = threadIdx.x;
-  const float sgn = inverse ? -1.f : 1.f;
+  const int line = threadIdx.x & 63, q = threadIdx.x >> 6;     // 512 threads = 64 lines x 8 butterflies
+  const float sg = inverse ? -1.f : 1.f;
+  const float r = 0.70710678118654752f;
+  const float2 w8 = make_float2(r, -sg * r), w16 = make_float2(0.f, -sg), w24 = make_float2(-r, -sg * r);
   for (int dim = 0; dim < 2; ++dim) {
-    const int es = dim == 0 ? 1 : FS;   // element stride along the transformed dimension
-    const int ls = dim == 0 ? FS : 1;   // stride between lines
-    for (int half = 1; half <= 16; half <<= 2) {          // stages (1,2), (3,4), (5,6): half = 1, 4, 16
-      for (int b = tid; b < FS * 16; b += kThreads) {
-        // rows: a warp walks butterflies of two lines; columns: a warp walks 32 adjacent lines of one butterfly, so
-        // that its shared-memory accesses are consecutive float2 (no bank conflicts)
-        const int line = dim == 0 ? (b >> 4) : (b & 63);
-        const int q = dim == 0 ? (b & 15) : (b >> 6);
-        const int grp = q / half, j = q - grp * half;
-        const int base = grp * (half << 2) + j;
-        float2* p0 = x + line * ls + base * es;
-        float2* p1 = p0 + half * es;
-        float2* p2 = p1 + half * es;
-        float2* p3 = p2 + half * es;
-        const int k1 = j * (32 / half), k2 = j * (16 / half);
-        const float2 w1 = make_float2(tb.tw_re[k1], sgn * tb.tw_im[k1]);
-        const float2 w2a = make_float2(tb.tw_re[k2], sgn * tb.tw_im[k2]);
-        const float2 w2b = make_float2(tb.tw_re[k2 + 16], sgn * tb.tw_im[k2 + 16]);
-        const float2 a = *p0, c = *p2;
-        const float2 tb1 = cmul(w1, *p1), td1 = cmul(w1, *p3);
-        const float2 u0 = make_float2(a.x + tb1.x, a.y + tb1.y), u1 = make_float2(a.x - tb1.x, a.y - tb1.y);
-        const float2 u2 = make_float2(c.x + td1.x, c.y + td1.y), u3 = make_float2(c.x - td1.x, c.y - td1.y);
-        const float2 t2 = cmul(w2a, u2), t3 = cmul(w2b, u3);
-        *p0 = make_float2(u0.x + t2.x, u0.y + t2.y);
-        *p2 = make_float2(u0.x - t2.x, u0.y - t2.y);
-        *p1 = make_float2(u1.x + t3.x, u1.y + t3.y);
-        *p3 = make_float2(u1.x - t3.x, u1.y - t3.y);
-      }
-      __syncthreads();
+    const int es = dim == 0 ? 1 : PS;   // element stride along the transformed dimension
+    const int ls = dim == 0 ? PS : 1;   // stride between lines
+    {
+      // ---- stages 1..3: elements 8q .. 8q+7 of the line ----
+      float2* p = x + line * ls + (q << 3) * es;
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = p[k * es];
+      bfly1(v[0], v[1]); bfly1(v[2], v[3]); bfly1(v[4], v[5]); bfly1(v[6], v[7]);
+      bfly1(v[0], v[2]); bfly(v[1], v[3], w16); bfly1(v[4], v[6]); bfly(v[5], v[7], w16);
+      bfly1(v[0], v[4]); bfly(v[1], v[5], w8); bfly(v[2], v[6], w16); bfly(v[3], v[7], w24);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) p[k * es] = v[k];
     }
+    __syncthreads();
+    {
+      // ---- stages 4..6: elements q + 8k of the line; twiddles exp(-2 pi i m / 64), m < 32, depend on q only ----
+      float2* p = x + line * ls + q * es;
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = p[(k << 3) * es];
+      const float2 t4 = make_float2(tb.tw_re[4 * q], sg * tb.tw_im[4 * q]);
+      bfly(v[0], v[1], t4); bfly(v[2], v[3], t4); bfly(v[4], v[5], t4); bfly(v[6], v[7], t4);
+      const float2 t2a = make_float2(tb.tw_re[2 * q], sg * tb.tw_im[2 * q]);
+      const float2 t2b = make_float2(tb.tw_re[2 * q + 16], sg * tb.tw_im[2 * q + 16]);
+      bfly(v[0], v[2], t2a); bfly(v[4], v[6], t2a); bfly(v[1], v[3], t2b); bfly(v[5], v[7], t2b);
+      bfly(v[0], v[4], make_float2(tb.tw_re[q], sg * tb.tw_im[q]));
+      bfly(v[1], v[5], make_float2(tb.tw_re[q + 8], sg * tb.tw_im[q + 8]));
+      bfly(v[2], v[6], make_float2(tb.tw_re[q + 16], sg * tb.tw_im[q + 16]));
+      bfly(v[3], v[7], make_float2(tb.tw_re[q + 24], sg * tb.tw_im[q + 24]));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) p[(k << 3) * es] = v[k];
+    }
+    __syncthreads();
   }
 }
 
+constexpr int NI = FS + 1;        // inverse-norm plane: entry (y0 + 1, x0 + 1) = 1 / sqrt(block(y0, x0) + eps), y0, x0 in [-1, 63]
+
 struct Smem {
-  uint8_t* chip;   // [4096*3]
-  uint8_t* ori;    // [4096]
-  float* mag;      // [4096]
-  float* osum;     // [4096]
-  float* bsum;     // [4096]
-  float2* plane;   // [4096]
-  float2* acc;     // [4096]
+  float2* plane;   // [64 * PS]   complex work plane (the chip lives here before the first transform)
+  float* mag;      // [4096]      gradient magnitude
+  float* osum;     // [4096]      0.5 * sum of the four clipped normalised magnitudes
+  float* invn;     // [NI * NI]   inverse block norms
+  float* bsum;     // [4096]      sum over channels of |F|^2
   float* red;      // [64]
   int* redi;       // [32]
+  uint8_t* ori;    // [4096]      snapped orientation 0..17
+  uint8_t* chip;   // [4096 * 3]  aliases `plane`
 };
 
 __device__ Smem carve(uint8_t* base) {
   Smem s;
   s.plane = reinterpret_cast<float2*>(base);
-  s.acc = s.plane + NPIX;
-  s.mag = reinterpret_cast<float*>(s.acc + NPIX);
+  s.mag = reinterpret_cast<float*>(s.plane + FS * PS);
   s.osum = s.mag + NPIX;
-  s.bsum = s.osum + NPIX;
+  s.invn = s.osum + NPIX;
+  s.bsum = s.invn + NI * NI + 3;
   s.red = s.bsum + NPIX;
   s.redi = reinterpret_cast<int*>(s.red + 64);
-  s.chip = reinterpret_cast<uint8_t*>(s.redi + 32);
-  s.ori = s.chip + NPIX * 3;
+  s.ori = reinterpret_cast<uint8_t*>(s.redi + 32);
+  s.chip = reinterpret_cast<uint8_t*>(s.plane);
   return s;
 }
-constexpr size_t kSmemBytes = 2 * NPIX * 8 + 3 * NPIX * 4 + 64 * 4 + 32 * 4 + NPIX * 3 + NPIX;
+constexpr size_t kSmemBytes = (size_t)FS * PS * 8 + 3 * NPIX * 4 + (NI * NI + 3) * 4 + 64 * 4 + 32 * 4 + NPIX;
+static_assert((size_t)NPIX * 3 <= (size_t)FS * PS * 8, "chip must fit into the work plane");
+static_assert(2 * (kSmemBytes + 2048) <= 227 * 1024, "two CTAs per SM");
 
-// chip + gradient orientation/magnitude + per-cell orientation feature value
+// chip + gradient orientation/magnitude + inverse block norms + per-cell orientation feature value
 __device__ void features_prepare(const BankParams& p, const TrackerTables& tb, const float* rect, Smem& s, float* tf) {
   const int tid = threadIdx.x;
   const float l = rect[0], t = rect[1], r = rect[2], b = rect[3];
@@ -174,18 +199,26 @@ __device__ void features_prepare(const BankParams& p, const TrackerTables& tb, c
     s.ori[i] = (uint8_t)bo;
   }
   __syncthreads();
+  // inverse norm of every 2x2 block of squared magnitudes, once per update (it was recomputed — 4 loads, a square root
+  // and a division — 4 times per pixel for the orientation sum and once per pixel for each of the 4 texture channels)
+  for (int j = tid; j < NI * NI; j += kThreads) {
+    const int y0 = j / NI - 1, x0 = j - (y0 + 1) * NI - 1;
+    float q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = y0 + (k >> 1), xx = x0 + (k & 1);
+      float m = 0.f;
+      if (yy >= 0 && yy < FS && xx >= 0 && xx < FS) m = s.mag[yy * FS + xx];
+      q[k] = __fmul_rn(m, m);
+    }
+    const float sum = __fadd_rn(__fadd_rn(__fadd_rn(q[0], q[1]), q[2]), q[3]);
+    s.invn[j] = __fdiv_rn(1.0f, sqrtf(__fadd_rn(sum, 0.0001f)));
+  }
+  __syncthreads();
 }
 
-__device__ __forceinline__ float nrm_at(const Smem& s, int y, int x) {
-  if (y < 0 || y >= FS || x < 0 || x >= FS) return 0.f;
-  const float m = s.mag[y * FS + x];
-  return __fmul_rn(m, m);
-}
-__device__ __forceinline__ float inv_block(const Smem& s, int y0, int x0) {
-  const float a = nrm_at(s, y0, x0), b = nrm_at(s, y0, x0 + 1), c = nrm_at(s, y0 + 1, x0), d = nrm_at(s, y0 + 1, x0 + 1);
-  const float sum = __fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d);
-  return __fdiv_rn(1.0f, sqrtf(__fadd_rn(sum, 0.0001f)));
-}
+__device__ __forceinline__ float inv_block(const Smem& s, int y0, int x0) { return s.invn[(y0 + 1) * NI + x0 + 1]; }
+
 __device__ void features_osum(Smem& s) {
   for (int i = threadIdx.x; i < NPIX; i += kThreads) {
     const int y = i >> 6, x = i & 63;
@@ -203,7 +236,7 @@ __device__ __forceinline__ float feature_value(const Smem& s, const TrackerTable
   const int o = s.ori[i];
   float v;
   if (ch < 18) v = (o == ch) ? s.osum[i] : 0.f;
-  else if (ch < 27) v = ((o % 9) == ch - 18) ? s.osum[i] : 0.f;
+  else if (ch < 27) v = ((o >= 9 ? o - 9 : o) == ch - 18) ? s.osum[i] : 0.f;
   else {
     const int k = ch - 27;
     const float nk = inv_block(s, y - 1 + (k >> 1), x - 1 + (k & 1));
@@ -223,34 +256,43 @@ __device__ void build_plane2(const Smem& s, const TrackerTables& tb, int cha, in
       va = feature_value(s, tb, cha, i, y, x);
       if (chb >= 0) vb = feature_value(s, tb, chb, i, y, x);
     }
-    s.plane[rev6(y) * FS + rev6(x)] = make_float2(va, vb);
+    s.plane[rev6(y) * PS + rev6(x)] = make_float2(va, vb);
   }
   __syncthreads();
 }
 
-__device__ __forceinline__ void split_spectra(const Smem& s, int i, float2& fa, float2& fb) {
-  const int y = i >> 6, x = i & 63;
-  const float2 z = s.plane[i];
-  const float2 zm = s.plane[((FS - y) & (FS - 1)) * FS + ((FS - x) & (FS - 1))];
+__device__ __forceinline__ void split_spectra(const Smem& s, int y, int x, float2& fa, float2& fb) {
+  const float2 z = s.plane[y * PS + x];
+  const float2 zm = s.plane[((FS - y) & (FS - 1)) * PS + ((FS - x) & (FS - 1))];
   fa = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
   fb = make_float2(0.5f * (z.y + zm.y), 0.5f * (zm.x - z.x));
 }
 
-// FFT of the Gaussian target centred at (px,py); leaves conj(G^) in s.acc
-__device__ void target_hat(Smem& s, const TrackerTables& tb, float px, float py) {
+// FFT of the Gaussian target centred at (px,py); conj(G^) of the thread's 8 bins is returned in g[]
+__device__ void target_hat(Smem& s, const TrackerTables& tb, float px, float py, float2 g[8]) {
   for (int i = threadIdx.x; i < NPIX; i += kThreads) {
     const int y = i >> 6, x = i & 63;
     const float dx = (float)x - px, dy = (float)y - py;
-    s.plane[rev6(y) * FS + rev6(x)] = make_float2(expf(-(dx * dx + dy * dy) / 3.0f), 0.f);
+    s.plane[rev6(y) * PS + rev6(x)] = make_float2(expf(-(dx * dx + dy * dy) / 3.0f), 0.f);
   }
   __syncthreads();
   fft2_64(s.plane, tb, false);
-  for (int i = threadIdx.x; i < NPIX; i += kThreads) s.acc[i] = make_float2(s.plane[i].x, -s.plane[i].y);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = threadIdx.x + k * kThreads;
+    const float2 v = s.plane[(i >> 6) * PS + (i & 63)];
+    g[k] = make_float2(v.x, -v.y);
+  }
   __syncthreads();
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Every thread owns the 8 spectrum bins i = tid + 512 k for the whole kernel: the response accumulator and conj(G^) live
+// in registers, so that the CTA needs 103 KB of shared memory and two CTAs (two tracks) share an SM — 256 tracks are one
+// wave on 148 SMs and one track's transforms overlap the other's state traffic.
 template <bool START>
-__global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const __grid_constant__ TrackerTables tbc) {
+__global__ void __launch_bounds__(kThreads, 2) tracker_kernel(BankParams p, const __grid_constant__ TrackerTables tbc) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem s = carve(smem_raw);
   // the tables are indexed per lane (twiddles, window): from the constant bank every distinct index of a warp is a
@@ -273,25 +315,30 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
   } else {
 #pragma unroll
     for (int k = 0; k < 4; ++k) rect[k] = p.pos[slot * 4 + k];
+    if ((tid & 15) == 0) prefetch_l2(A + tid), prefetch_l2(A + NPIX + tid);
   }
   features_prepare(p, tb, rect, s, tf);
   features_osum(s);
+  const int ybase = tid >> 6, xcol = tid & 63;    // bin k of this thread: row ybase + 8 k, column xcol
 
   if (START) {
-    target_hat(s, tb, 0.5f * (FS - 1), 0.5f * (FS - 1));
+    float2 g[8];
+    target_hat(s, tb, 0.5f * (FS - 1), 0.5f * (FS - 1), g);
     for (int i = tid; i < NPIX; i += kThreads) s.bsum[i] = 0.f;
     __syncthreads();
     for (int ch = 0; ch < NCH; ch += 2) {
       const bool two = ch + 1 < NCH;
       build_plane2(s, tb, ch, two ? ch + 1 : -1);
       fft2_64(s.plane, tb, false);
-      for (int i = tid; i < NPIX; i += kThreads) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = tid + k * kThreads;
         float2 fa, fb;
-        split_spectra(s, i, fa, fb);
-        A[(size_t)ch * NPIX + i] = cmul(s.acc[i], fa);
+        split_spectra(s, ybase + 8 * k, xcol, fa, fb);
+        A[(size_t)ch * NPIX + i] = cmul(g[k], fa);
         float bs = fa.x * fa.x + fa.y * fa.y;
         if (two) {
-          A[(size_t)(ch + 1) * NPIX + i] = cmul(s.acc[i], fb);
+          A[(size_t)(ch + 1) * NPIX + i] = cmul(g[k], fb);
           bs += fb.x * fb.x + fb.y * fb.y;
         }
         s.bsum[i] += bs;
@@ -305,47 +352,65 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
   }
 
   // ---- pass 1: response ----
-  for (int i = tid; i < NPIX; i += kThreads) {
-    s.acc[i] = make_float2(0.f, 0.f);
-    s.bsum[i] = 0.f;
-  }
+  float2 acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
+  for (int i = tid; i < NPIX; i += kThreads) s.bsum[i] = 0.f;
   __syncthreads();
   for (int ch = 0; ch < NCH; ch += 2) {
     const bool two = ch + 1 < NCH;
+    if (ch + 2 < NCH && (tid & 15) == 0) {   // the next pair's numerators travel to L2 under this pair's transform
+      prefetch_l2(A + (size_t)(ch + 2) * NPIX + tid);
+      prefetch_l2(A + (size_t)(ch + 2) * NPIX + 512 + tid);
+      if (ch + 3 < NCH) {
+        prefetch_l2(A + (size_t)(ch + 3) * NPIX + tid);
+        prefetch_l2(A + (size_t)(ch + 3) * NPIX + 512 + tid);
+      }
+    }
     build_plane2(s, tb, ch, two ? ch + 1 : -1);
     fft2_64(s.plane, tb, false);
-    for (int i = tid; i < NPIX; i += kThreads) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = tid + k * kThreads;
       float2 fa, fb;
-      split_spectra(s, i, fa, fb);
+      split_spectra(s, ybase + 8 * k, xcol, fa, fb);
       const float2 a = A[(size_t)ch * NPIX + i];
-      float2 acc = s.acc[i];
-      acc.x += fa.x * a.x + fa.y * a.y;   // f * conj(a)
-      acc.y += fa.y * a.x - fa.x * a.y;
+      acc[k].x += fa.x * a.x + fa.y * a.y;   // f * conj(a)
+      acc[k].y += fa.y * a.x - fa.x * a.y;
       float bs = fa.x * fa.x + fa.y * fa.y;
       if (two) {
         const float2 b2 = A[(size_t)(ch + 1) * NPIX + i];
-        acc.x += fb.x * b2.x + fb.y * b2.y;
-        acc.y += fb.y * b2.x - fb.x * b2.y;
+        acc[k].x += fb.x * b2.x + fb.y * b2.y;
+        acc[k].y += fb.y * b2.x - fb.x * b2.y;
         bs += fb.x * fb.x + fb.y * fb.y;
       }
-      s.acc[i] = acc;
       s.bsum[i] += bs;
     }
     __syncthreads();
   }
-  for (int i = tid; i < NPIX; i += kThreads) {
-    const int y = i >> 6, x = i & 63;
-    const float d = 1.0f / (B[i] + p.lambda);
-    s.plane[rev6(y) * FS + rev6(x)] = make_float2(s.acc[i].x * d, s.acc[i].y * d);
+  {
+    const float nu = p.nu, om = 1.0f - p.nu;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = tid + k * kThreads;
+      const int y = ybase + 8 * k;
+      const float bold = B[i];
+      const float d = 1.0f / (bold + p.lambda);
+      s.plane[rev6(y) * PS + rev6(xcol)] = make_float2(acc[k].x * d, acc[k].y * d);
+      B[i] = om * bold + nu * s.bsum[i];     // the denominator's running update needs nothing from pass 2
+    }
   }
   __syncthreads();
   fft2_64(s.plane, tb, true);
-  // real response (scaled by 1/4096) kept in s.osum (features are rebuilt in pass 2)
+  // real response (scaled by 1/4096) stays in the work plane (.x) until the target of pass 2 overwrites it
   float bestv = -INFINITY;
   int besti = 0x7fffffff;
-  for (int i = tid; i < NPIX; i += kThreads) {
-    const float v = s.plane[i].x * (1.0f / NPIX);
-    s.acc[i].x = v;   // stash R in acc.x until the target is built
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = tid + k * kThreads;
+    float2* e = s.plane + (ybase + 8 * k) * PS + xcol;
+    const float v = e->x * (1.0f / NPIX);
+    e->x = v;
     if (v > bestv || (v == bestv && i < besti)) { bestv = v; besti = i; }
   }
   // block argmax (first occurrence)
@@ -375,10 +440,11 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
   // PSR statistics outside the 8x8 window [px-4,px+3] x [py-4,py+3]
   double sum = 0.0, sumsq = 0.0;
   int cnt = 0;
-  for (int i = tid; i < NPIX; i += kThreads) {
-    const int y = i >> 6, x = i & 63;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int y = ybase + 8 * k, x = xcol;
     if (y >= py - 4 && y < py + 4 && x >= px - 4 && x < px + 4) continue;
-    const double v = (double)s.acc[i].x;
+    const double v = (double)s.plane[y * PS + x].x;
     sum += v;
     sumsq += v * v;
     ++cnt;
@@ -402,7 +468,8 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
     const double psr = ((double)rmax - mean) / sqrt(var > 0 ? var : 1e-300);
     double ppx = px, ppy = py;
     if (px > 0 && px < FS - 1 && py > 0 && py < FS - 1) {
-      const double c = s.acc[pi].x, xl = s.acc[pi - 1].x, xr = s.acc[pi + 1].x, yu = s.acc[pi - FS].x, yd = s.acc[pi + FS].x;
+      const float2* e = s.plane + py * PS + px;
+      const double c = e->x, xl = e[-1].x, xr = e[1].x, yu = e[-PS].x, yd = e[PS].x;
       const double dxx = xl - 2 * c + xr, dyy = yu - 2 * c + yd;
       if (dxx != 0) ppx += 0.5 * (xl - xr) / dxx;
       if (dyy != 0) ppy += 0.5 * (yu - yd) / dyy;
@@ -420,24 +487,34 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
   }
   __syncthreads();
 
-  // ---- pass 2: filter update ----
-  target_hat(s, tb, peak[0], peak[1]);
+  // ---- pass 2: filter update (features are recomputed rather than spilled: the state is read twice, written once) ----
+  float2 g[8];
+  target_hat(s, tb, peak[0], peak[1], g);
   const float nu = p.nu, om = 1.0f - p.nu;
   for (int ch = 0; ch < NCH; ch += 2) {
     const bool two = ch + 1 < NCH;
+    if (ch + 2 < NCH && (tid & 15) == 0) {
+      prefetch_l2(A + (size_t)(ch + 2) * NPIX + tid);
+      prefetch_l2(A + (size_t)(ch + 2) * NPIX + 512 + tid);
+      if (ch + 3 < NCH) {
+        prefetch_l2(A + (size_t)(ch + 3) * NPIX + tid);
+        prefetch_l2(A + (size_t)(ch + 3) * NPIX + 512 + tid);
+      }
+    }
     build_plane2(s, tb, ch, two ? ch + 1 : -1);
     fft2_64(s.plane, tb, false);
-    for (int i = tid; i < NPIX; i += kThreads) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = tid + k * kThreads;
       float2 fa, fb;
-      split_spectra(s, i, fa, fb);
-      const float2 g = s.acc[i];
-      const float2 ga = cmul(g, fa);
+      split_spectra(s, ybase + 8 * k, xcol, fa, fb);
+      const float2 ga = cmul(g[k], fa);
       float2 a = A[(size_t)ch * NPIX + i];
       a.x = om * a.x + nu * ga.x;
       a.y = om * a.y + nu * ga.y;
       A[(size_t)ch * NPIX + i] = a;
       if (two) {
-        const float2 gb = cmul(g, fb);
+        const float2 gb = cmul(g[k], fb);
         float2 b2 = A[(size_t)(ch + 1) * NPIX + i];
         b2.x = om * b2.x + nu * gb.x;
         b2.y = om * b2.y + nu * gb.y;
@@ -446,7 +523,6 @@ __global__ void __launch_bounds__(kThreads) tracker_kernel(BankParams p, const _
     }
     __syncthreads();
   }
-  for (int i = tid; i < NPIX; i += kThreads) B[i] = om * B[i] + nu * s.bsum[i];
 }
 
 
@@ -485,25 +561,35 @@ struct ScaleParams {
 
 __device__ __forceinline__ int rev5(int v) { return (int)(__brev((unsigned)v) >> 27); }
 
+constexpr int SG = 4;                  // scales built per round (32 scales = 8 rounds)
+constexpr int SPX = SW * SW;           // 529 pixels per scale chip
+constexpr int SROWS = SF / 2;          // two real features share one complex row: 248 rows
+constexpr int NBIN = SCELLS * SCELLS * 18;
+
+// Two changes against the first version (ncu: 1 CTA / SM at 131 KB, 224 block barriers around 529-pixel loops):
+//  * the 32 scale chips are built SG = 4 at a time, so the seven barriers of a round are amortised over 2116 pixels;
+//  * features 2r and 2r+1 (both real) are the real and imaginary part of ONE complex row, the 248 row transforms give
+//    both spectra, Fa[k] = (Z[k] + conj(Z[-k])) / 2, Fb[k] = (Z[k] - conj(Z[-k])) / (2i): half the transforms and 66 KB
+//    instead of 131 KB of shared memory, i.e. two tracks per SM.
 template <bool START>
-__global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, const __grid_constant__ ScaleTables tbc) {
+__global__ void __launch_bounds__(kThreads, 2) tracker_scale_kernel(ScaleParams p, const __grid_constant__ ScaleTables tbc) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ ScaleTables tb;        // per-lane indexed tables: shared memory, not the constant bank (see tracker_kernel)
   for (int i = threadIdx.x; i < (int)(sizeof(ScaleTables) / 4); i += kThreads)
     reinterpret_cast<uint32_t*>(&tb)[i] = reinterpret_cast<const uint32_t*>(&tbc)[i];
   __syncthreads();
-  float2* Z = reinterpret_cast<float2*>(smem_raw);                 // [SF][ZP]
-  float* s_mag = reinterpret_cast<float*>(Z + SF * ZP);             // [SW*SW]
-  float* s_hist = s_mag + SW * SW;                                  // [36*18]
-  float* s_nrm = s_hist + SCELLS * SCELLS * 18;                     // [36]
-  float* s_red = s_nrm + SCELLS * SCELLS;                           // [kGroups*64 + 64]
-  uint8_t* s_chip = reinterpret_cast<uint8_t*>(s_red + kGroups * 64 + 64);  // [SW*SW*3]
-  uint8_t* s_ori = s_chip + SW * SW * 3 + 3;                        // [SW*SW]
+  float2* Z = reinterpret_cast<float2*>(smem_raw);                  // [SROWS][ZP]
+  float* s_mag = reinterpret_cast<float*>(Z + SROWS * ZP);           // [SG][SPX]
+  float* s_hist = s_mag + SG * SPX;                                  // [SG][36*18]
+  unsigned* s_histi = reinterpret_cast<unsigned*>(s_hist + SG * NBIN);   // [SG][36*18] fixed-point scatter target
+  float* s_nrm = reinterpret_cast<float*>(s_histi + SG * NBIN);      // [SG][36]
+  float* s_red = s_nrm + SG * SCELLS * SCELLS;                       // [kGroups*64 + 64]
+  uint8_t* s_chip = reinterpret_cast<uint8_t*>(s_red + kGroups * 64 + 64);  // [SG][SPX*3]
+  uint8_t* s_ori = s_chip + SG * SPX * 3 + 4;                        // [SG][SPX]
   __shared__ double s_gre[NS], s_gim[NS];   // conj(FFT(target))
   __shared__ double s_rre[NS], s_rim[NS];
   __shared__ float s_resp[NS];
   __shared__ float s_peak;
-  __shared__ unsigned s_histi[SCELLS * SCELLS * 18];   // fixed-point cell histograms (scatter target)
   __shared__ int s_cwi[SW];                 // FHOG cell-4 bilinear weights of pixel coordinate c:
   __shared__ float s_cw0[SW], s_cw1[SW];    //   cp = (c + 0.5)/4 - 0.5, s_cwi = floor(cp), s_cw0 = cp - floor(cp), s_cw1 = 1 - s_cw0
   const int tid = threadIdx.x;
@@ -524,13 +610,15 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
   const float cx = __fmul_rn(__fadd_rn(l, r), 0.5f), cy = __fmul_rn(__fadd_rn(t, b), 0.5f);
   const float hw0 = __fmul_rn(__fsub_rn(r, l), 0.5f), hh0 = __fmul_rn(__fsub_rn(b, t), 0.5f);
 
-  for (int k = 0; k < NS; ++k) {
-    // ---- chip of scale k ----
-    const float hw = __fmul_rn(hw0, tb.factor[k]), hh = __fmul_rn(hh0, tb.factor[k]);
-    const float lk = __fsub_rn(cx, hw), rk = __fadd_rn(cx, hw), tk = __fsub_rn(cy, hh), bk = __fadd_rn(cy, hh);
-    const float sx = __fdiv_rn(__fsub_rn(rk, lk), (float)(SW - 1)), sy = __fdiv_rn(__fsub_rn(bk, tk), (float)(SW - 1));
-    for (int i = tid; i < SW * SW; i += kThreads) {
-      const int y = i / SW, x = i - y * SW;
+  for (int k0 = 0; k0 < NS; k0 += SG) {
+    // ---- chips of scales k0 .. k0+SG-1 ----
+    for (int i = tid; i < SG * SPX; i += kThreads) {
+      const int g = i / SPX, pix = i - g * SPX;
+      const int k = k0 + g;
+      const float hw = __fmul_rn(hw0, tb.factor[k]), hh = __fmul_rn(hh0, tb.factor[k]);
+      const float lk = __fsub_rn(cx, hw), rk = __fadd_rn(cx, hw), tk = __fsub_rn(cy, hh), bk = __fadd_rn(cy, hh);
+      const float sx = __fdiv_rn(__fsub_rn(rk, lk), (float)(SW - 1)), sy = __fdiv_rn(__fsub_rn(bk, tk), (float)(SW - 1));
+      const int y = pix / SW, x = pix - y * SW;
       const float fx = __fadd_rn(lk, __fmul_rn((float)x, sx)), fy = __fadd_rn(tk, __fmul_rn((float)y, sy));
       const int left = (int)floorf(fx), top = (int)floorf(fy);
       uint8_t o[3] = {0, 0, 0};
@@ -549,48 +637,37 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
       }
       s_chip[3 * i] = o[0]; s_chip[3 * i + 1] = o[1]; s_chip[3 * i + 2] = o[2];
     }
+    for (int bi = tid; bi < SG * NBIN; bi += kThreads) s_histi[bi] = 0u;
     __syncthreads();
-    // ---- gradient magnitude / snapped orientation ----
-    for (int i = tid; i < SW * SW; i += kThreads) {
-      const int y = i / SW, x = i - y * SW;
-      float m = 0.f;
-      int bo = 0;
-      if (y > 0 && y < SW - 1 && x > 0 && x < SW - 1) {
-        float gx = 0.f, gy = 0.f, best = -1.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float dx = __fsub_rn((float)s_chip[3 * (i + 1) + c], (float)s_chip[3 * (i - 1) + c]);
-          const float dy = __fsub_rn((float)s_chip[3 * (i + SW) + c], (float)s_chip[3 * (i - SW) + c]);
-          const float v = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-          if (v > best) { best = v; gx = dx; gy = dy; }
-        }
-        m = sqrtf(best);
-        float best_dot = 0.f;
-#pragma unroll
-        for (int o = 0; o < 9; ++o) {
-          const float dot = __fadd_rn(__fmul_rn(tb.uu[o], gx), __fmul_rn(tb.vv[o], gy));
-          if (dot > best_dot) { best_dot = dot; bo = o; }
-          else if (-dot > best_dot) { best_dot = -dot; bo = o + 9; }
-        }
-      }
-      s_mag[i] = m;
-      s_ori[i] = (uint8_t)bo;
-    }
-    __syncthreads();
-    // ---- cell histograms: every pixel SCATTERS its magnitude into the (up to) 2 x 2 cells it overlaps ----
-    // A gather (one thread per (cell, orientation) bin scanning its 8 x 8 support) visited 41 k pixels per scale to use
-    // 1.8 k of them and was 2/3 of this kernel (ncu, profiles/README.md).  The scatter adds 17-bit fixed point with
+    // ---- gradient magnitude / snapped orientation, scattered straight into the cell histograms ----
+    // every pixel SCATTERS its magnitude into the (up to) 2 x 2 cells it overlaps, as 17-bit fixed point with
     // shared-memory integer atomics: integer addition is associative, so the result does not depend on the order of
     // arrival (deterministic), at a resolution of 2^-17 on sums < 2^15 — finer than float32 at these magnitudes.
-    for (int bi = tid; bi < SCELLS * SCELLS * 18; bi += kThreads) s_histi[bi] = 0u;
-    __syncthreads();
-    for (int i = tid; i < SW * SW; i += kThreads) {
-      const int y = i / SW, x = i - y * SW;
+    for (int i = tid; i < SG * SPX; i += kThreads) {
+      const int g = i / SPX, pix = i - g * SPX;
+      const int y = pix / SW, x = pix - y * SW;
       if (y < 1 || y > SW - 2 || x < 1 || x > SW - 2) continue;
-      const float m = s_mag[i];
-      const int o = s_ori[i];
+      const uint8_t* ch = s_chip + 3 * (size_t)(g * SPX);
+      float gx = 0.f, gy = 0.f, best = -1.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float dx = __fsub_rn((float)ch[3 * (pix + 1) + c], (float)ch[3 * (pix - 1) + c]);
+        const float dy = __fsub_rn((float)ch[3 * (pix + SW) + c], (float)ch[3 * (pix - SW) + c]);
+        const float v = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (v > best) { best = v; gx = dx; gy = dy; }
+      }
+      const float m = sqrtf(best);
+      float best_dot = 0.f;
+      int o = 0;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        const float dot = __fadd_rn(__fmul_rn(tb.uu[q], gx), __fmul_rn(tb.vv[q], gy));
+        if (dot > best_dot) { best_dot = dot; o = q; }
+        else if (-dot > best_dot) { best_dot = -dot; o = q + 9; }
+      }
       const int iyp = s_cwi[y], ixp = s_cwi[x];
       const float wy[2] = {s_cw1[y], s_cw0[y]}, wx[2] = {s_cw1[x], s_cw0[x]};   // cell iyp gets 1 - frac, cell iyp + 1 gets frac
+      unsigned* hist = s_histi + g * NBIN;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy) {
         const int cyi = iyp + dy;
@@ -600,36 +677,40 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
           const int cxi = ixp + dx;
           if (cxi < 0 || cxi >= SCELLS) continue;
           const float v = __fmul_rn(__fmul_rn(wx[dx], wy[dy]), m);
-          atomicAdd(&s_histi[(cyi * SCELLS + cxi) * 18 + o], (unsigned)__float2uint_rn(__fmul_rn(v, 131072.0f)));
+          atomicAdd(&hist[(cyi * SCELLS + cxi) * 18 + o], (unsigned)__float2uint_rn(__fmul_rn(v, 131072.0f)));
         }
       }
     }
     __syncthreads();
-    for (int bi = tid; bi < SCELLS * SCELLS * 18; bi += kThreads) s_hist[bi] = __fmul_rn((float)s_histi[bi], 1.0f / 131072.0f);   // [cell][o]
+    for (int bi = tid; bi < SG * NBIN; bi += kThreads) s_hist[bi] = __fmul_rn((float)s_histi[bi], 1.0f / 131072.0f);   // [g][cell][o]
     __syncthreads();
-    if (tid < SCELLS * SCELLS) {
+    if (tid < SG * SCELLS * SCELLS) {
+      const float* h = s_hist + tid * 18;      // (g, cell) flattened: g * 36 + cell
       float n = 0.f;
       for (int o = 0; o < 9; ++o) {
-        const float sv = __fadd_rn(s_hist[tid * 18 + o], s_hist[tid * 18 + o + 9]);
+        const float sv = __fadd_rn(h[o], h[o + 9]);
         n = __fadd_rn(n, __fmul_rn(sv, sv));
       }
       s_nrm[tid] = n;
     }
     __syncthreads();
-    // ---- 496 features of this scale ----
-    for (int j = tid; j < SF; j += kThreads) {
+    // ---- 496 features of each of the SG scales ----
+    for (int jj = tid; jj < SG * SF; jj += kThreads) {
+      const int g = jj / SF, j = jj - g * SF;
+      const int k = k0 + g;
       const int plane = j / (SOUT * SOUT), rem = j - plane * SOUT * SOUT;
       const int y = rem / SOUT, x = rem - y * SOUT;
       const int Y = y + 1, X = x + 1;
+      const float* nrm = s_nrm + g * SCELLS * SCELLS;
       float ns[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int yy = Y - 1 + (q >> 1), xx = X - 1 + (q & 1);
-        const float blk = __fadd_rn(__fadd_rn(__fadd_rn(s_nrm[yy * SCELLS + xx], s_nrm[yy * SCELLS + xx + 1]),
-                                              s_nrm[(yy + 1) * SCELLS + xx]), s_nrm[(yy + 1) * SCELLS + xx + 1]);
+        const float blk = __fadd_rn(__fadd_rn(__fadd_rn(nrm[yy * SCELLS + xx], nrm[yy * SCELLS + xx + 1]),
+                                              nrm[(yy + 1) * SCELLS + xx]), nrm[(yy + 1) * SCELLS + xx + 1]);
         ns[q] = __fdiv_rn(1.0f, sqrtf(__fadd_rn(blk, 0.0001f)));
       }
-      const float* h = s_hist + (Y * SCELLS + X) * 18;
+      const float* h = s_hist + g * NBIN + (Y * SCELLS + X) * 18;
       float v;
       if (plane < 27) {
         const float hv = plane < 18 ? h[plane] : __fadd_rn(h[plane - 18], h[plane - 18 + 9]);
@@ -642,13 +723,15 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
         for (int o = 0; o < 18; ++o) tsum = __fadd_rn(tsum, fminf(__fmul_rn(h[o], ns[q]), 0.2f));
         v = __fmul_rn(0.2357f, tsum);
       }
-      Z[j * ZP + rev5(k)] = make_float2(__fmul_rn(v, tb.hann[k]), 0.f);
+      // feature j -> row j >> 1, real part for even j, imaginary part for odd j; stored bit-reversed over scales
+      float* zz = reinterpret_cast<float*>(Z + (j >> 1) * ZP + rev5(k));
+      zz[j & 1] = __fmul_rn(v, tb.hann[k]);
     }
     __syncthreads();
   }
 
-  // ---- length-32 FFT over scales for every feature row (input stored bit-reversed) ----
-  for (int j = tid; j < SF; j += kThreads) {
+  // ---- length-32 FFT over scales for every row (input stored bit-reversed) ----
+  for (int j = tid; j < SROWS; j += kThreads) {
     float2* z = Z + j * ZP;
     for (int s = 1; s <= 5; ++s) {
       const int half = 1 << (s - 1);
@@ -666,15 +749,20 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
   __syncthreads();
 
   const int k = tid & 31, grp = tid >> 5;   // kGroups row groups
+  const int km = (NS - k) & (NS - 1);
   float peak = 0.5f * NS;
   if (!START) {
-    // response R^[k] = sum_j Z[j][k] conj(As[j][k]) / (Bs[k] + lambda)
+    // response R^[k] = sum_j F_j[k] conj(As[j][k]) / (Bs[k] + lambda)
     float re = 0.f, im = 0.f;
-    for (int j = grp; j < SF; j += kGroups) {
-      const float2 f = Z[j * ZP + k];
-      const float2 a = As[(size_t)j * NS + k];
-      re += f.x * a.x + f.y * a.y;
-      im += f.y * a.x - f.x * a.y;
+    for (int rr = grp; rr < SROWS; rr += kGroups) {
+      const float2 z = Z[rr * ZP + k], zm = Z[rr * ZP + km];
+      const float2 fa = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
+      const float2 fb = make_float2(0.5f * (z.y + zm.y), 0.5f * (zm.x - z.x));
+      const float2 a = As[(size_t)(2 * rr) * NS + k], a2 = As[(size_t)(2 * rr + 1) * NS + k];
+      re += fa.x * a.x + fa.y * a.y;
+      im += fa.y * a.x - fa.x * a.y;
+      re += fb.x * a2.x + fb.y * a2.y;
+      im += fb.y * a2.x - fb.x * a2.y;
     }
     s_red[grp * 64 + k] = re;
     s_red[grp * 64 + 32 + k] = im;
@@ -737,17 +825,24 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
   {
     const float gre = (float)s_gre[k], gim = (float)s_gim[k];
     float bsum = 0.f;
-    for (int j = grp; j < SF; j += kGroups) {
-      const float2 f = Z[j * ZP + k];
-      const float2 gf = make_float2(gre * f.x - gim * f.y, gre * f.y + gim * f.x);
-      bsum += f.x * f.x + f.y * f.y;
-      if (START) {
-        As[(size_t)j * NS + k] = gf;
-      } else {
-        float2 a = As[(size_t)j * NS + k];
-        a.x = (1.0f - tb.nu) * a.x + tb.nu * gf.x;
-        a.y = (1.0f - tb.nu) * a.y + tb.nu * gf.y;
-        As[(size_t)j * NS + k] = a;
+    for (int rr = grp; rr < SROWS; rr += kGroups) {
+      const float2 z = Z[rr * ZP + k], zm = Z[rr * ZP + km];
+      float2 f[2];
+      f[0] = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
+      f[1] = make_float2(0.5f * (z.y + zm.y), 0.5f * (zm.x - z.x));
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 gf = make_float2(gre * f[h].x - gim * f[h].y, gre * f[h].y + gim * f[h].x);
+        bsum += f[h].x * f[h].x + f[h].y * f[h].y;
+        float2* ap = As + (size_t)(2 * rr + h) * NS + k;
+        if (START) {
+          *ap = gf;
+        } else {
+          float2 a = *ap;
+          a.x = (1.0f - tb.nu) * a.x + tb.nu * gf.x;
+          a.y = (1.0f - tb.nu) * a.y + tb.nu * gf.y;
+          *ap = a;
+        }
       }
     }
     __syncthreads();
@@ -760,8 +855,9 @@ __global__ void __launch_bounds__(kThreads) tracker_scale_kernel(ScaleParams p, 
     }
   }
 }
-constexpr size_t kScaleSmem = (size_t)SF * ZP * 8 + (SW * SW) * 4 + (SCELLS * SCELLS * 18) * 4 + SCELLS * SCELLS * 4 +
-                              (kGroups * 64 + 64) * 4 + SW * SW * 3 + 3 + SW * SW + 64;
+constexpr size_t kScaleSmem = (size_t)SROWS * ZP * 8 + (size_t)SG * SPX * 4 + 2 * (size_t)SG * NBIN * 4 + SG * SCELLS * SCELLS * 4 +
+                              (kGroups * 64 + 64) * 4 + SG * SPX * 3 + 4 + SG * SPX + 64;
+static_assert(2 * (kScaleSmem + 4096) <= 227 * 1024, "two CTAs per SM");
 
 struct Bank {
   int capacity;

@@ -5,9 +5,9 @@
   EmbedNet     dlib face_recognition_resnet_model_v1: 150x150 chip -> 29 convs -> 128-d
                (replaces compute_face_descriptor, pyannote/video/face/face.py:74-75)
 
-Every convolution is one launch of the tcgen05 srgemm kernel with the dlib `affine` (frozen BN),
-bias, residual add and ReLU fused into its epilogue; the remaining layers are the small kernels of
-csrc/layers.cu and csrc/detect.cu.  All buffers are allocated once; nothing here touches the CPU
+Every convolution is one tcgen05 kernel launch with the dlib `affine` (frozen BN), bias, residual add and
+ReLU fused into its epilogue — `conv1_fused` + `rsconv` (row streaming) for the detector, `srgemm` (shifted-row
+GEMM) for the embedder; the remaining layers are the small kernels of csrc/layers.cu and csrc/detect.cu.  All buffers are allocated once; nothing here touches the CPU
 oracle.
 """
 import ctypes as C
@@ -422,11 +422,12 @@ class DetectorNet:
                                       C.c_float(self.score_bias), _lib.ptr(self.scores), st), "pv_det_shift_sum")
         return self.scores[:M]
 
-    def decode(self, M):
+    def decode(self, M, threshold=None):
         L = _lib.lib()
         st = _lib.stream_ptr()
         m = self.model
-        _lib.check(L.pv_det_candidates(_lib.ptr(self.scores), M, self.OH * self.OW, C.c_float(float(m["adjust_threshold"])),
+        thr = float(m["adjust_threshold"]) if threshold is None else max(float(threshold), float(m["adjust_threshold"]))
+        _lib.check(L.pv_det_candidates(_lib.ptr(self.scores), M, self.OH * self.OW, C.c_float(thr),
                                        _lib.ptr(self.counts), _lib.ptr(self.cand_score), _lib.ptr(self.cand_cell),
                                        self.MAX_CAND, st), "pv_det_candidates")
         _lib.check(L.pv_det_nms(_lib.ptr(self.counts), _lib.ptr(self.cand_score), _lib.ptr(self.cand_cell), self.MAX_CAND,

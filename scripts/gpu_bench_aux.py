@@ -69,15 +69,61 @@ def bench_cluster(n):
                 pdist_flop=2.0 * X.shape[0] ** 2 * 128 * 1.5)
 
 
+def bench_embed(batch):
+    """embed-only: chips -> 29 convs -> 128-d at a large face batch, CUDA events around every conv launch"""
+    from pyannote_video_b200 import weights as W
+    from pyannote_video_b200.nets import EmbedNet
+    dev = torch.device("cuda:0")
+    net = EmbedNet(W.make_embedder(seed=3), batch, dev)
+    net.chips.copy_(torch.randint(0, 256, net.chips.shape, dtype=torch.uint8, device=dev))
+    for _ in range(3):
+        net.forward_chips(batch)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 10
+    for _ in range(reps):
+        net.forward_chips(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    # per-layer
+    evs = []
+    convs = [a[0] for k, a in net.ops if k == "conv"]
+    orig = [op.run for op in convs]
+    for i, op in enumerate(convs):
+        def timed(q=None, _r=op.run, _i=i):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); _r(q); b.record()
+            evs.append((_i, a, b))
+        op.run = timed
+    net.forward_chips(batch); torch.cuda.synchronize(); evs.clear()
+    net.forward_chips(batch); torch.cuda.synchronize()
+    for op, r in zip(convs, orig):
+        op.run = r
+    layers = []
+    for (i, a, b), op in zip(evs, convs):
+        cp = op.cp
+        cin = cp.lin.C if cp.lin.kind != "gathered" else 3
+        fl = 2.0 * batch * cp.OH * cp.OW * cp.Cout * cin * cp.KH * cp.KW
+        t = a.elapsed_time(b)
+        layers.append(dict(i=i, out="%dx%dx%d" % (cp.OH, cp.OW, cp.Cout), k=cp.KH, us=round(t * 1e3, 1), tflops=round(fl / t / 1e9, 1)))
+    conv_ms = sum(a.elapsed_time(b) for _, a, b in evs)
+    fl = batch * net.flops_per_face
+    return dict(bench="embed-only", batch=batch, ms=ms, faces_per_s=batch / ms * 1e3, tflops=fl / ms / 1e9,
+                frac_of_1442=fl / ms / 1e9 / 1442.3, conv_ms=conv_ms, conv_tflops=fl / conv_ms / 1e9, layers=layers)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=200)
     ap.add_argument("--n", type=int, default=100000)
-    ap.add_argument("--only", default="", help="tracker | cluster")
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--only", default="", help="tracker | cluster | embed")
     a = ap.parse_args()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "aux_bench.jsonl"), "a") as f:
-        for fn, arg in ((bench_tracker, a.frames), (bench_cluster, a.n)):
+        for fn, arg in ((bench_tracker, a.frames), (bench_cluster, a.n), (bench_embed, a.batch)):
             if a.only and a.only not in fn.__name__:
                 continue
             try:

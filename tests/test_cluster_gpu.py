@@ -78,4 +78,11 @@ def test_face_clustering_file_roundtrip(cuda, tmp_path):
     starting_point, features = clustering.model.preprocess(str(path))
     result = clustering(starting_point, features=features)
     ref = ohac.greedy_hac(features["X"], features["track"], threshold=0.6)
-    assert ohac.partition_of(result) == ohac.partition_of({k: v for k, v in ref.items() if k in starting_point})
+    from pyannote_video_b200.annotation import Annotation
+    assert isinstance(starting_point, Annotation) and isinstance(result, Annotation)
+    kept = set(t for _, t in starting_point.itertracks())
+    assert ohac.partition_of(result.to_dict()) == ohac.partition_of({k: v for k, v in ref.items() if k in kept})
+    # the notebook's loop (doc/getting_started.ipynb cell 21): itertracks(yield_label=True), label = a surviving track id
+    for segment, track, label in result.itertracks(yield_label=True):
+        assert label in kept and segment.end > segment.start
+    assert FaceClustering(threshold=0.6, force=True)(starting_point, features=features) == result

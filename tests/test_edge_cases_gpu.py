@@ -26,7 +26,7 @@ def test_frame_without_detections_yields_nothing(cuda):
     assert boxes.shape == (0, 4) and fidx.numel() == 0 and scores.numel() == 0
 
 
-def test_candidate_overflow_is_reported_not_truncated_silently(cuda):
+def test_candidate_overflow_is_reported_and_degrades_to_the_best_candidates(cuda):
     det = W.make_detector(seed=2, score_bias=50.0)            # every cell is a candidate
     face = _face(cuda, detector=det)
     rgb = make_frames(1, 160, 200, seed=3)[0].numpy()
@@ -34,8 +34,15 @@ def test_candidate_overflow_is_reported_not_truncated_silently(cuda):
     assert net.OH * net.OW > net.MAX_CAND
     _, _, counts = net.detect(torch.from_numpy(rgb)[None].to(cuda))
     assert int(counts[0]) < 0                                  # include/pv_b200.h: out_counts < 0 reports the overflow
-    with pytest.raises(RuntimeError):
-        face.detect_batch(rgb)
+    # the public API keeps the MAX_CAND best cells of the frame and warns instead of aborting the video
+    with pytest.warns(UserWarning):
+        boxes, fidx, scores = face.detect_batch(rgb)
+    assert boxes.shape[0] > 0 and boxes.shape[0] <= net.MAX_DET
+    from oracle import pyramid as opyr
+    sc = net.scores[0].cpu().numpy()
+    kth = float(np.sort(sc.reshape(-1))[-net.MAX_CAND])
+    ref = opyr.decode(sc, net.geo, det["window"], kth, det["iou_thresh"], det["covered_thresh"])
+    assert [tuple(b) for b in boxes.cpu().tolist()] == [r[:4] for r in ref][:boxes.shape[0]]
 
 
 def test_constant_frames_are_finite_and_deterministic(cuda):
