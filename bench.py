@@ -142,56 +142,64 @@ class CpuPath(object):
 
 
 def cpu_sample(models, threads, n_frames, seed=0):
-    """times n_frames frames of ONE stream through the C++ path; returns (seconds, threads used)"""
+    """times n_frames frames through the C++ path; returns (seconds, threads used).  threads > 1 = frame-level
+    parallelism (BASELINE.md §2 "B-cpu-N": `threads` independent streams, one host thread each, every stream doing the
+    same per-frame work as one stream of the GPU step); threads == 1 = one stream on one thread ("B-cpu-1")."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cpu_ref
     from pyannote_video_b200.synth import make_frames, make_boxes
     frames = make_frames(N_TIMES, H, W, seed=seed, shift_per_frame=SHIFT).numpy()
     boxes, fidx = make_boxes(N_TIMES, FACES_PER_FRAME, H, W, seed=1)
     boxes = boxes.numpy().reshape(N_TIMES, FACES_PER_FRAME, 4)
-    path = CpuPath(models, threads)
-    path.start_tracks(frames[0])
-    path.frame(frames[1], boxes[1])                       # warm-up (page faults, thread pool)
-    t0 = time.perf_counter()
-    for i in range(n_frames):
-        t = time_index(i + 2)
-        path.frame(frames[t], boxes[t])
-    return time.perf_counter() - t0, path.threads
+    threads = max(1, int(threads))
+    per = max(1, n_frames // threads)
+    cpu_ref.lib()                                   # (build and) load the library before the worker threads start
+
+    def worker(k, timed):
+        cpu_ref.set_threads(1)                      # OpenMP's thread count is per host thread: every worker runs serial code
+        if k not in paths:
+            paths[k] = CpuPath(models, 1)
+            paths[k].start_tracks(frames[0])
+            paths[k].frame(frames[1], boxes[1])     # warm-up (page faults, block pool)
+        if timed:
+            for i in range(per):
+                t = time_index(i + 2)
+                paths[k].frame(frames[t], boxes[t])
+
+    paths = {}
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(lambda k: worker(k, False), range(threads)))
+        t0 = time.perf_counter()
+        list(ex.map(lambda k: worker(k, True), range(threads)))
+        el = time.perf_counter() - t0
+    return el, threads, per * threads
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the C++ restatement of the reference's dlib path with all usable host cores (rank 0 only)."""
+    """--impl reference: the C++ restatement of the reference's dlib path with all usable host cores (rank 0 only):
+    frame-level parallelism, one stream per core.  Each timed step = one frame per core."""
     if rank != 0:
         return
     from oracle import cpu_ref
-    from pyannote_video_b200.synth import make_frames, make_boxes
     models = make_models()
     cores = cpu_ref.host_cores()
-    frames_per_step = 2
-    frames = make_frames(N_TIMES, H, W, seed=0, shift_per_frame=SHIFT).numpy()
-    boxes, _ = make_boxes(N_TIMES, FACES_PER_FRAME, H, W, seed=1)
-    boxes = boxes.numpy().reshape(N_TIMES, FACES_PER_FRAME, 4)
-    path = CpuPath(models, cores)
-    path.start_tracks(frames[0])
-    k = 0
-    for _ in range(max(1, min(args.warmup, 3)) * frames_per_step):
-        k += 1
-        path.frame(frames[time_index(k)], boxes[time_index(k)])
-    steps = max(1, min(args.steps, 40))
-    t0 = time.perf_counter()
-    for _ in range(steps * frames_per_step):
-        k += 1
-        path.frame(frames[time_index(k)], boxes[time_index(k)])
-    el = time.perf_counter() - t0
-    fps = steps * frames_per_step / el
-    sample = "%d steps x %d 1080p frames of one stream (same per-frame work as the GPU step)" % (steps, frames_per_step)
-    line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 3),
+    steps = max(1, min(args.steps, 30))
+    el, used, n = cpu_sample(models, cores, steps * cores)
+    fps = n / el
+    frames_per_step = cores
+    sample = ("%d steps x %d 1080p frames (%d independent streams, one host thread each; same per-frame work as one stream "
+              "of the GPU step)" % (steps, frames_per_step, used))
+    line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=steps, warmup=1,
                 ms_per_step=1000.0 * el / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
                 config=dict(workload=WORKLOAD, frames_per_step=frames_per_step, faces_per_frame=FACES_PER_FRAME,
                             tracker_updates_per_frame=2 * TRACKS_PER_STREAM, sample=sample,
                             implementation="restated dlib-style CPU baseline: C++ -O3 -march=native, fp32 blocked direct "
-                                           "convolutions, OpenMP (oracle/cpu); not dlib itself (absent here)"),
-                cpu_baseline=dict(value=fps, unit="frames/s", cores=path.threads, kind="port", sample=sample,
-                                  host_threads_visible=os.cpu_count()),
+                                           "convolutions (oracle/cpu), frame-level parallelism over all usable cores; not dlib "
+                                           "itself (absent here)"),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=used, kind="port", sample=sample,
+                                  host_threads_visible=os.cpu_count(),
+                                  cores_note="usable cores = min(online CPUs, cgroup cpu.max quota)"),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -521,14 +529,15 @@ def main():
         from oracle import cpu_ref
         models = (det_m, sp_m, emb_m)
         cores = cpu_ref.host_cores()
-        el1, _ = cpu_sample(models, 1, 2)
-        n_all = max(4, min(40, int(2 * cores * 0.5)))
-        el_n, used = cpu_sample(models, cores, n_all)
+        el1, _, n1 = cpu_sample(models, 1, 2)
+        el_n, used, n_all = cpu_sample(models, cores, 4 * cores)
         cpu = dict(value=n_all / el_n, unit="frames/s", cores=used, kind="port",
-                   sample="%d x 1080p frames of one stream (detect + %d tracker updates + %d faces) through the C++ restatement "
-                          "oracle/cpu (-O3 -march=native, OpenMP), %.1f s" % (n_all, 2 * TRACKS_PER_STREAM, FACES_PER_FRAME, el_n),
-                   single_thread=dict(value=2 / el1, cores=1, sample="2 frames, %.1f s" % el1),
-                   core_scaling=round((n_all / el_n) / (2 / el1), 2), host_threads_visible=os.cpu_count())
+                   sample="%d x 1080p frames (%d independent streams, one host thread each: detect + %d tracker updates + %d "
+                          "faces per frame) through the C++ restatement oracle/cpu (-O3 -march=native), %.1f s"
+                          % (n_all, used, 2 * TRACKS_PER_STREAM, FACES_PER_FRAME, el_n),
+                   single_thread=dict(value=n1 / el1, cores=1, sample="%d frames, %.1f s" % (n1, el1)),
+                   core_scaling=round((n_all / el_n) / (n1 / el1), 2), host_threads_visible=os.cpu_count(),
+                   cores_note="usable cores = min(online CPUs, cgroup cpu.max quota)")
 
     line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",

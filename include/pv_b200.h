@@ -273,6 +273,12 @@ int pv_chip_extract(const void* frames, int H, int W, const int* parts, const in
  * ------------------------------------------------------------------------------------------ */
 /* D[i][j] = ||x_i - x_j|| (metric 0, scipy pdist 'euclidean') or 1 - cos (metric 1); X f32 [n,128] */
 int pv_pdist(const float* X, int64_t n, int dim, int metric, float* D, void* stream);
+/* the same matrix from the tensor cores (csrc/gram.cu): <x_i, x_j> as a bf16 x 3 split GEMM with fp32 TMEM accumulation
+ * (six products, error ~2^-24), distance epilogue fused.  Workspaces: xs_ws = 3 * npad * 128 bf16, norms_ws = npad floats,
+ * npad = pv_gram_npad(n); err_flag: device int set by a pipeline timeout (may be NULL). */
+int64_t pv_gram_npad(int64_t n);
+int pv_gram_dist(const float* X, int64_t n, int dim, int metric, float* D, void* xs_ws, float* norms_ws, int* err_flag,
+                 void* stream);
 /* S' = P S P^T in two passes; CSR (offs i32 [tout+1], memb i32) lists the old clusters of each new one */
 int pv_pool_rows(const float* S, int64_t tin, const int* offs, const int* memb, float* R, int64_t tout, void* stream);
 int pv_pool_cols(const float* R, int64_t tin, const int* offs, const int* memb, float* Sout, int64_t tout, void* stream);

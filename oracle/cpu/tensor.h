@@ -48,7 +48,7 @@ struct BlockPool {
   }
   void give(size_t bytes, char* p) {
     std::lock_guard<std::mutex> g(mu);
-    if (held + bytes > ((size_t)6 << 30)) {   // keep at most 6 GiB parked
+    if (held + bytes > ((size_t)48 << 30)) {   // keep at most 48 GiB parked (16 concurrent 1080p frames hold ~24 GiB)
       free(p);
       return;
     }

@@ -13,6 +13,7 @@ import ctypes as C
 import hashlib
 import os
 import subprocess
+import threading
 
 import numpy as np
 
@@ -48,9 +49,13 @@ def lib_path():
 def ensure_built():
     path = lib_path()
     if not os.path.exists(path):
-        r = subprocess.run(["make", "-s", "-C", _HERE, "LIB=" + os.path.basename(path)], capture_output=True, text=True)
-        if r.returncode != 0 or not os.path.exists(path):
+        # build under a private name, then rename: another process / thread never sees a half-written library
+        tmp = "tmp%d_%s" % (os.getpid(), os.path.basename(path))
+        r = subprocess.run(["make", "-s", "-C", _HERE, "LIB=" + tmp], capture_output=True, text=True)
+        tmp_path = os.path.join(_HERE, "_build", tmp)
+        if r.returncode != 0 or not os.path.exists(tmp_path):
             raise RuntimeError("building the C++ CPU oracle failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp_path, path)
     return path
 
 
@@ -71,13 +76,18 @@ def host_cores():
     return n
 
 
+_lib_lock = threading.Lock()
+
+
 def lib():
     global _lib
     if _lib is None:
-        l = C.CDLL(ensure_built())
-        l.pvc_net_create.restype = C.c_void_p
-        l.pvc_trackers_create.restype = C.c_void_p
-        _lib = l
+        with _lib_lock:
+            if _lib is None:
+                l = C.CDLL(ensure_built())
+                l.pvc_net_create.restype = C.c_void_p
+                l.pvc_trackers_create.restype = C.c_void_p
+                _lib = l
     return _lib
 
 

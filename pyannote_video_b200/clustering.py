@@ -23,6 +23,31 @@ def _i32(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
 
 
+def pairwise_distances(X, metric="euclidean", impl="tcgen05"):
+    """D float32 [N,N] on X's device: scipy pdist+squareform (clustering.py:101).  impl 'tcgen05' = csrc/gram.cu (bf16 x 3
+    split Gram on the tensor cores, fused distance epilogue), 'fp32' = the CUDA-core difference kernel (kept as the
+    cross-check: it is exact for duplicate points, the Gram form has |dD| <= ~2e-7 / D)."""
+    if metric not in ("euclidean", "cosine"):
+        raise ValueError("metric must be 'euclidean' or 'cosine'")
+    m = 0 if metric == "euclidean" else 1
+    L = _lib.lib()
+    st = _lib.stream_ptr()
+    N = X.shape[0]
+    dev = X.device
+    D = torch.empty(N, N, dtype=torch.float32, device=dev)
+    if impl == "fp32":
+        _lib.check(L.pv_pdist(_lib.ptr(X), C.c_int64(N), 128, m, _lib.ptr(D), st), "pv_pdist")
+        return D
+    L.pv_gram_npad.restype = C.c_int64
+    npad = int(L.pv_gram_npad(C.c_int64(N)))
+    xs = torch.empty(3 * npad, 128, dtype=torch.bfloat16, device=dev)
+    norms = torch.empty(npad, dtype=torch.float32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(L.pv_gram_dist(_lib.ptr(X), C.c_int64(N), 128, m, _lib.ptr(D), _lib.ptr(xs), _lib.ptr(norms), _lib.ptr(err), st),
+               "pv_gram_dist")
+    return D
+
+
 def cluster(emb, track_id, threshold=0.6, metric="euclidean", strict=False, device=None, max_rounds=10000,
             return_stats=False):
     """Threshold-stopped average-linkage clustering of tracks.
@@ -48,8 +73,7 @@ def cluster(emb, track_id, threshold=0.6, metric="euclidean", strict=False, devi
     m = 0 if metric == "euclidean" else 1
     if metric not in ("euclidean", "cosine"):
         raise ValueError("metric must be 'euclidean' or 'cosine'")
-    D = torch.empty(N, N, dtype=torch.float32, device=dev)
-    _lib.check(L.pv_pdist(_lib.ptr(X), C.c_int64(N), 128, m, _lib.ptr(D), st), "pv_pdist")
+    D = pairwise_distances(X, metric)
     # members of current clusters, in terms of the rows/cols of the current matrix
     sizes = np.diff(np.append(start, N)).astype(np.int64)            # embeddings per track
 

@@ -190,8 +190,8 @@ __global__ void hac_members_kernel(const int* __restrict__ keep, const int* __re
 
 // S2[A][B] = sum over the (at most 2 x 2) old clusters: rows pooled first, then columns (same order as pool_rows + pool_cols)
 __global__ void hac_contract_kernel(const float* __restrict__ S, long long t, const int* __restrict__ m0, const int* __restrict__ m1,
-                                    float* __restrict__ S2, long long tout) {
-  const long long A = blockIdx.y;
+                                    float* __restrict__ S2, long long tout, long long row0) {
+  const long long A = row0 + blockIdx.y;
   const long long B = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (A >= tout || B >= tout) return;
   const int a0 = m0[A], a1 = m1[A], b0 = m0[B], b1 = m1[B];
@@ -243,8 +243,7 @@ extern "C" int pv_hac_contract(const float* S, int64_t t, const int* m0, const i
   const long long maxy = 65535;
   for (long long a0 = 0; a0 < tout; a0 += maxy) {
     const long long na = (tout - a0 < maxy) ? tout - a0 : maxy;
-    hac_contract_kernel<<<dim3((unsigned)((tout + 255) / 256), (unsigned)na), 256, 0, s>>>(S, t, m0 + a0, m1 + a0, S2 + a0 * tout,
-                                                                                          tout);
+    hac_contract_kernel<<<dim3((unsigned)((tout + 255) / 256), (unsigned)na), 256, 0, s>>>(S, t, m0, m1, S2, tout, a0);
     g_pv_launches.fetch_add(1);
   }
   PV_CUDA_CHECK(cudaGetLastError());

@@ -42,6 +42,28 @@ def test_pdist_matches_scipy(cuda, metric):
     assert np.allclose(D.cpu().numpy(), ref, atol=2e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+@pytest.mark.parametrize("n", [300, 1000, 1343])
+def test_tcgen05_gram_distances_match_scipy(cuda, metric, n):
+    """csrc/gram.cu (bf16 x 3 split Gram on the tensor cores + fused distance epilogue) against scipy's float64 pdist —
+    the reference's own call — and against the fp32 CUDA-core kernel; n not a multiple of 128 / 8 exercises the tails"""
+    from scipy.spatial.distance import pdist, squareform
+    from pyannote_video_b200.clustering import pairwise_distances
+    rng = np.random.default_rng(n)
+    cent = rng.standard_normal((12, 128)) * 0.35
+    X = (cent[rng.integers(0, 12, n)] + 0.03 * rng.standard_normal((n, 128))).astype(np.float32)
+    Xd = torch.from_numpy(X).to(cuda)
+    D = pairwise_distances(Xd, metric).cpu().numpy()
+    ref = squareform(pdist(X.astype(np.float64), metric=metric))
+    assert D.shape == ref.shape and (np.diag(D) == 0).all()
+    err = np.abs(D - ref)
+    print("gram %s n=%d: max |dD| %.2e (D range %.3f..%.3f)" % (metric, n, err.max(), ref[ref > 0].min(), ref.max()))
+    assert err.max() < 2e-5
+    D32 = pairwise_distances(Xd, metric, impl="fp32").cpu().numpy()
+    assert np.abs(D - D32).max() < 2e-5
+    assert np.abs(D - D.T).max() < 1e-6
+
+
 @pytest.mark.parametrize("seed,metric,thr", [(1, "euclidean", 0.6), (2, "euclidean", 0.6), (3, "cosine", 0.05)])
 def test_cluster_matches_greedy_oracle(cuda, seed, metric, thr):
     from pyannote_video_b200.clustering import cluster

@@ -5,6 +5,8 @@ Plane: bit-exact against the numpy oracle AND the C++ oracle.  Scores: max |d| <
 C++ oracle in bf16-faithful mode (it stores bf16 where the CUDA path stores bf16).  Decode: the CUDA decode of the CUDA
 scores equals the oracle's decode of the same scores, exactly.  Landmarks / chips: bit-exact.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -37,8 +39,8 @@ def _detector_frame(cuda, H, Wd, seed):
     rng = max(1.0, float(np.abs(ref_scores).max()))
     print("%dx%d: scores max|d| %.4f (range %.2f, std %.3f), plane %s" % (Wd, H, d.max(), rng, ref_scores.std(), plane.shape))
     assert d.max() <= 0.03 * rng
-    # decode with a threshold that keeps a few hundred candidate cells
-    thr = float(np.quantile(scores, 1 - 400.0 / scores.size))
+    # decode with a threshold that keeps ~200 candidate cells (the kept boxes must fit the MAX_DET = 256 output rows)
+    thr = float(np.quantile(scores, 1 - 200.0 / scores.size))
     m2 = dict(model)
     m2["adjust_threshold"] = thr
     net.model = m2
@@ -46,9 +48,12 @@ def _detector_frame(cuda, H, Wd, seed):
     n = int(counts[0])
     ref = opyr.decode(scores, geo, model["window"], thr, model["iou_thresh"], model["covered_thresh"])
     ref_cpp = det.decode(scores, geo, threshold=thr)
-    assert n == len(ref) and n > 20
+    assert n == len(ref) and 20 < n <= net.MAX_DET
     got = [tuple(int(v) for v in b) for b in boxes[0, :n].cpu().numpy()]
-    assert got == [r[:4] for r in ref] == [r[:4] for r in ref_cpp]
+    if [r[:4] for r in ref] != [r[:4] for r in ref_cpp] and os.path.isdir("gpurun_out"):
+        np.savez_compressed("gpurun_out/decode_mismatch_%d.npz" % H, scores=scores, thr=thr)
+    assert got == [r[:4] for r in ref], "CUDA decode differs from the numpy oracle's decode of the same scores"
+    assert [r[:4] for r in ref] == [r[:4] for r in ref_cpp], "C++ and numpy oracle decodes disagree"
     assert np.allclose(bsc[0, :n].cpu().numpy(), [r[4] for r in ref])
     # boxes lie in the image (up to half a window) and come from more than one pyramid level
     sizes = set((r[2] - r[0]) for r in ref)
