@@ -420,7 +420,7 @@ def main():
     if rank == 0 and args.profile_convs > 0:
         net = face.face_recognition_
         det_names = ["conv%d" % (i + 1) for i in range(len(det0.convs))]
-        conv_ops = [(n, op) for n, (op, _) in zip(det_names, det0.convs)] + [("embed", a[0]) for k, a in net.ops if k == "conv"]
+        conv_ops = [(n, op) for n, (op, _) in zip(det_names, det0.convs)] + [("embed", op) for op, _ in net.conv_ops()]
         evs = []
         orig = {}
         for name, op in conv_ops:

@@ -79,7 +79,9 @@ typedef struct PvSrEntry {
 
 /* maps an output grid position (n, y, x) to a row of a destination / residual matrix */
 typedef struct PvRowMap {
-  int32_t kind;        /* 0: padded NHWC  row = n*img + (y+py)*w + (x+px)
+  int32_t kind;        /* 2: faces side by side ("packed rows", embedder levels 4 / 3): image g = n / img holds img faces at
+                             column pitch px, py rows per image:  row = (g*py + y)*w + (n - g*img)*px + x
+                          0: padded NHWC  row = n*img + (y+py)*w + (x+px)
                           1: parity split row = plane*plane_rows + n*img + ((y+py)>>1)*w + ((x+px)>>1),
                              plane = ((y+py)&1)*2 + ((x+px)&1)                               */
   int32_t cols;        /* row length in elements                                              */
@@ -156,6 +158,10 @@ typedef struct PvDetconvDesc {
   int32_t relu;
   void* out;             /* bf16 (or f32 when out_f32) [B, OH, out_pitch, out_cs]               */
   int32_t out_pitch, out_cs;
+  /* rsconv only (embedder levels 4 / 3, faces side by side in one image row): */
+  const void* resid;     /* optional bf16, same geometry as `out`: added before the ReLU (dlib add_prev)      */
+  int32_t gap_period;    /* > 0: output columns x with x % gap_period == gap_pos are written as zeros         */
+  int32_t gap_pos;       /*      (the zero column between two faces = the padding of both)                    */
 } PvDetconvDesc;
 
 int pv_detconv_create(const PvDetconvDesc* desc, void** out_handle);
@@ -209,6 +215,10 @@ int pv_conv1_fused(const void* plane_rgba, int B, int Hp, int Wp, const void* w_
  * cycles summed over CTAs {MMA: wait accumulator, wait pixels, issue, tiles; converter: wait raw, wait slot, work;
  * epilogue: wait} */
 int pv_conv1_debug(long long* out8);
+/* packed-rows tensors [G][H][Wp][C] (F faces per image row at pitch W+1): dlib avg_pool<2,2,2,2> per face, channels
+ * zero-extended Cin -> Cout (ares_down skip path), and the hand-over to a PvRowMap layout */
+int pv_pr_avgpool(const void* in, int G, int F, int H, int W, int Wp, int Cin, void* out, int OWp, int Cout, void* stream);
+int pv_pr_unpack(const void* in, int B, int F, int H, int W, int Wp, int C, void* out, const PvRowMap* dst, void* stream);
 /* dlib max_pool<3,3,2,2> (pad 0) on bf16 NHWC [B,H,W,C] -> rows of `dst` */
 int pv_maxpool3x3s2(const void* in, void* out, int B, int H, int W, int C, const PvRowMap* dst, void* stream);
 /* dlib avg_pool<2,2,2,2> skip path of ares_down: parity-layout input -> skip (zero-extended to Cout)

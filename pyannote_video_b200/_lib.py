@@ -92,6 +92,8 @@ class PvDetconvDesc(C.Structure):
         ("relu", C.c_int32),
         ("out", C.c_void_p),
         ("out_pitch", C.c_int32), ("out_cs", C.c_int32),
+        ("resid", C.c_void_p),
+        ("gap_period", C.c_int32), ("gap_pos", C.c_int32),
     ]
 
 

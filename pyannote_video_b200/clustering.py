@@ -101,6 +101,8 @@ def cluster(emb, track_id, threshold=0.6, metric="euclidean", strict=False, devi
     sz = torch.from_numpy(sizes.astype(np.float32)).to(dev)           # embeddings per cluster
     cl = torch.arange(T, dtype=torch.int32, device=dev)               # cluster index of every track
     rounds = 0
+    S_store = (S._base if S._base is not None else S).reshape(-1)     # flat storage behind the current matrix
+    spare = None
     while t > 1 and rounds < max_rounds:
         nn = torch.empty(t, dtype=torch.int32, device=dev)
         nnd = torch.empty(t, dtype=torch.float32, device=dev)
@@ -122,10 +124,15 @@ def cluster(emb, track_id, threshold=0.6, metric="euclidean", strict=False, devi
         _lib.check(L.pv_hac_members(_lib.ptr(keep), _lib.ptr(partner), _lib.ptr(newidx), _lib.ptr(nn), _lib.ptr(sz),
                                     C.c_int64(t), _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(sz2), _lib.ptr(mp), st),
                    "pv_hac_members")
-        S2 = torch.empty(tout, tout, dtype=torch.float32, device=dev)
+        # the contracted matrix goes into the OTHER of two flat buffers (the distance matrix's storage and one more block
+        # of the first contraction's size): no allocation and no free of multi-gigabyte blocks inside the loop
+        if spare is None:
+            spare = torch.empty(tout * tout, dtype=torch.float32, device=dev)
+        S2 = spare[:tout * tout].view(tout, tout)
         _lib.check(L.pv_hac_contract(_lib.ptr(S), C.c_int64(t), _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(S2), C.c_int64(tout), st),
                    "pv_hac_contract")
         _lib.check(L.pv_hac_relabel(_lib.ptr(cl), C.c_int64(T), _lib.ptr(mp), st), "pv_hac_relabel")
+        spare, S_store = S_store, spare
         S, sz, t = S2, sz2, tout
         del S2
         rounds += 1

@@ -26,3 +26,8 @@ DET_CONV1 = os.environ.get("PV_DET_CONV1", "fused")
 #              UMMA descriptor into the patch (1.9 input pixels read per output), compile-time MMA sequence
 #   "srgemm"   the generic 1-D shifted-row GEMM (5.3 input rows read per output, table-driven issue loop)
 DET_CONVS = os.environ.get("PV_DET_CONVS", "rsconv")
+
+# embedder convs of levels 4 / 3 (32 and 64 channels, 14 of the 29 convs, 54 % of the FLOPs):
+#   "rs"      csrc/rsconv.cu, faces packed side by side in an image row (N = 3 x Cout per MMA)          [default]
+#   "srgemm"  the shifted-row GEMM for every conv (round-1 path; N = Cout <= 64 is shared-memory-bound)
+EMBED_IMPL = os.environ.get("PV_EMBED_IMPL", "rs")

@@ -10,11 +10,17 @@
 // are accumulated in fp32 TMEM:  hi.hi + hi.mid + mid.hi + hi.lo + lo.hi + mid.mid   (error ~ 2^-24 of the product).
 // That is a GEMM with K = 6 x 128 on operands that stay in L2 (100 k embeddings x 3 parts x 256 B = 77 MB).
 //
-// One persistent CTA per SM; warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue.
-// Work item = one 128-row block of i (its three parts, 96 KB, stay resident in shared memory) x a run of 128-column
-// blocks of j streamed through a 3-stage ring, one part (32 KB) per stage.  Accumulators: a ring of four 128 x 128 fp32
-// tiles in TMEM (all 512 columns), so the epilogue of one tile (tcgen05.ld -> norms -> sqrt -> 256-bit row stores)
-// overlaps the 48 MMAs of the next ones.  The output is the roofline: 4 N^2 bytes are written once.
+// One persistent CTA per SM; warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..9 = epilogue (two per
+// TMEM lane quarter, 64 columns each).  Work item = one 128-row block of i (its three parts, 96 KB, stay resident in
+// shared memory) x a run of 128-column blocks of j streamed through a 3-stage ring, one part (32 KB) per stage.
+// Accumulators: two tiles in flight, each two 128 x 128 fp32 accumulators in TMEM (all 512 columns), so the epilogue of
+// one tile (tcgen05.ld -> norms -> sqrt -> 256-bit row stores) overlaps the 48 MMAs of the next one.  The output is the
+// roofline: 4 N^2 bytes are written once.
+//
+// Accumulation order matters: the tensor core adds into the fp32 accumulator with truncation, i.e. every accumulating
+// MMA costs up to an ulp OF THE ACCUMULATOR'S MAGNITUDE (measured: 48 adds into a sum of 16 gave |dG| ~ 6e-5, 1.3e-4 on D).
+// So the five small products go first, while the accumulator is ~2^-8 of the final value, hi.hi goes last, and its
+// second K half goes into a second accumulator that the epilogue adds in fp32: 4 + 4 adds at half magnitude.
 #include <cuda.h>
 #include <atomic>
 #include "../../include/pv_b200.h"
@@ -27,8 +33,9 @@ namespace {
 constexpr int kDim = 128;
 constexpr int kBlk = 128;            // rows per i block = columns per j block
 constexpr int kStages = 3;
-constexpr int kAcc = 4;
-constexpr int kThreads = 192;
+constexpr int kAcc = 2;              // tiles in flight in TMEM; a tile owns TWO 128-column accumulators (see the MMA order below)
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kPartBytes = kBlk * kDim * 2;      // 32 KB: one part of one block (two 64-column swizzle-128B halves)
 constexpr int kHalfBytes = kPartBytes / 2;
 
@@ -90,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
     pv_mbar_init(bar_a_full, 1);
     pv_mbar_init(bar_a_empty, 1);
     for (int i = 0; i < kStages; ++i) { pv_mbar_init(&bar_b_full[i], 1); pv_mbar_init(&bar_b_empty[i], 1); }
-    for (int i = 0; i < kAcc; ++i) { pv_mbar_init(&bar_acc_full[i], 1); pv_mbar_init(&bar_acc_empty[i], 4); }
+    for (int i = 0; i < kAcc; ++i) { pv_mbar_init(&bar_acc_full[i], 1); pv_mbar_init(&bar_acc_empty[i], kEpiWarps); }
     pv_fence_mbar_init();
   }
   if (warp == 1) pv_tmem_alloc(s_tmem, 512);
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
             pv_tma_load_2d(a_sm + part * kPartBytes + h * kHalfBytes, &p.xs, bar_a_full, h * 64, part * p.npad + ib * kBlk);
         a_phase ^= 1u;
         for (int jb = jb0; jb < jb1; ++jb)
-          for (int part = 0; part < 3; ++part) {
+          for (int part = 2; part >= 0; --part) {                 // lo, mid, hi: small products first
             pv_mbar_wait(&bar_b_empty[stage], phase ^ 1u, p.err, 2);
             pv_mbar_arrive_expect_tx(&bar_b_full[stage], (uint32_t)kPartBytes);
             for (int h = 0; h < 2; ++h)
@@ -139,20 +146,24 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
         for (int jb = jb0; jb < jb1; ++jb) {
           const uint32_t slot = acc_cnt % kAcc;
           pv_mbar_wait(&bar_acc_empty[slot], ((acc_cnt / kAcc) & 1u) ^ 1u, p.err, 4);
-          const uint32_t d = tmem_base + slot * kBlk;
+          const uint32_t d0 = tmem_base + slot * (2 * kBlk), d1 = d0 + kBlk;
           uint32_t first = 1;
-          for (int bp = 0; bp < 3; ++bp) {                     // B part: hi, mid, lo
+          for (int bp = 2; bp >= 0; --bp) {                     // B part: lo, mid, hi
             pv_mbar_wait(&bar_b_full[stage], phase, p.err, 5);
             pv_tc_fence_after();
             const int n_ap = 3 - bp;                            // A parts whose product with this B part is kept
-            for (int ap = 0; ap < n_ap; ++ap)
+            for (int ap = n_ap - 1; ap >= 0; --ap)              // smallest product first; hi.hi is the very last one
 #pragma unroll
               for (int k = 0; k < 8; ++k) {                     // K = 128 in steps of 16: half k >> 2, 32-byte step inside the atom
                 const uint32_t off = (uint32_t)((k >> 2) * kHalfBytes + (k & 3) * 32);
                 const uint64_t da = pv_umma_desc(a_addr + ap * kPartBytes + off, 1024, 2, 0);
                 const uint64_t db = pv_umma_desc(b_addr + stage * kPartBytes + off, 1024, 2, 0);
-                pv_umma_bf16(d, da, db, idesc, first ? 0u : 1u);
-                first = 0;
+                if (bp == 0 && ap == 0 && k >= 4) {
+                  pv_umma_bf16(d1, da, db, idesc, k == 4 ? 0u : 1u);   // second K half of hi.hi: its own accumulator
+                } else {
+                  pv_umma_bf16(d0, da, db, idesc, first ? 0u : 1u);
+                  first = 0;
+                }
               }
             pv_umma_commit(&bar_b_empty[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -164,10 +175,11 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue: row i = TMEM lane, 128 columns of j =====================
+    // ===================== epilogue: row i = TMEM lane; warps 2..5 take columns 0..63, warps 6..9 columns 64..127 =====
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;                            // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64;                            // 0..255 among the epilogue threads
+    const int grp = (warp - 2) >> 2;                            // column half
     const bool vec_ok = (p.n % 8) == 0;
     uint32_t acc_cnt = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -179,37 +191,45 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
       for (int jb = jb0; jb < jb1; ++jb) {
         const uint32_t slot = acc_cnt % kAcc;
         float* nj = s_nj + slot * kBlk;
-        nj[et] = p.norms[jb * kBlk + et];
+        if (et < kBlk) nj[et] = p.norms[jb * kBlk + et];
         pv_mbar_wait(&bar_acc_full[slot], (acc_cnt / kAcc) & 1u, p.err, 6);
         pv_tc_fence_after();
-        asm volatile("bar.sync 1, 128;" ::: "memory");           // nj[] of this slot written by all four warps
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * kBlk;
-        const long long j0 = (long long)jb * kBlk;
+        asm volatile("bar.sync 1, 256;" ::: "memory");           // nj[] of this slot is complete
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * (2 * kBlk) + grp * 64;
+        const long long j0 = (long long)jb * kBlk + grp * 64;
         float* drow = p.D + i * p.n + j0;
+        const int diag = (ib == jb) ? m - grp * 64 : -1;         // column of this thread's diagonal element, if in range
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-          uint32_t v[4][16];
+          uint32_t v0[2][16], v1[2][16];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) pv_tmem_ld16(taddr + half * 64 + c * 16, v[c]);
+          for (int c = 0; c < 2; ++c) {
+            pv_tmem_ld16(taddr + half * 32 + c * 16, v0[c]);
+            pv_tmem_ld16(taddr + kBlk + half * 32 + c * 16, v1[c]);
+          }
           pv_tmem_ld_wait();
           if (half == 1) {
             pv_tc_fence_before();
             __syncwarp();
-            if (lane == 0) pv_mbar_arrive(&bar_acc_empty[slot]);   // the whole accumulator row is in registers
+            if (lane == 0) pv_mbar_arrive(&bar_acc_empty[slot]);   // this warp's part of both accumulators is in registers
           }
           if (i < p.n) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int col = half * 64 + c * 16;
+            for (int c = 0; c < 2; ++c) {
+              const int col = half * 32 + c * 16;
               float f[16];
 #pragma unroll
               for (int k = 0; k < 16; ++k) {
-                const float g = __uint_as_float(v[c][k]);
-                const float njk = nj[col + k];
+                const float g = __uint_as_float(v0[c][k]) + __uint_as_float(v1[c][k]);
+                const float njk = nj[grp * 64 + col + k];
                 float dv;
-                if (p.metric == 0) dv = sqrtf(fmaxf(ni + njk - 2.0f * g, 0.f));
-                else dv = 1.f - g / fmaxf(sni * sqrtf(njk), 1e-30f);
-                if (j0 + col + k == i) dv = 0.f;
+                if (p.metric == 0) {
+                  const float d2 = fmaxf(ni + njk - 2.0f * g, 0.f);
+                  asm("sqrt.approx.f32 %0, %1;" : "=f"(dv) : "f"(d2));
+                } else {
+                  dv = 1.f - g / fmaxf(sni * sqrtf(njk), 1e-30f);
+                }
+                if (col + k == diag) dv = 0.f;
                 f[k] = dv;
               }
               if (vec_ok && j0 + col + 16 <= p.n) {
@@ -226,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");           // nj[] of this slot may be overwritten 4 tiles later
+        asm volatile("bar.sync 1, 256;" ::: "memory");           // nj[] of this slot may be overwritten two tiles later
         ++acc_cnt;
       }
     }

@@ -14,6 +14,10 @@ extern std::atomic<long long> g_pv_launches;
 namespace {
 
 __device__ __forceinline__ long long row_of(const PvRowMap& m, uint32_t n, uint32_t y, uint32_t x) {
+  if (m.kind == 2) {   // faces side by side: image g = n / F holds faces g*F .. g*F+F-1 at column pitch px; py = rows per image
+    const uint32_t F = (uint32_t)m.img, g = n / F, f = n - g * F;
+    return ((long long)g * m.py + y) * m.w + (long long)f * m.px + x;
+  }
   const uint32_t Y = y + m.py, X = x + m.px;
   if (m.kind == 0) return (long long)n * m.img + (long long)Y * m.w + X;
   const uint32_t plane = ((Y & 1u) << 1) | (X & 1u);
@@ -185,6 +189,71 @@ __global__ void avgpool_skip_kernel(const __nv_bfloat16* __restrict__ in, int Ci
 }
 
 // ---------------------------------------------------------------------------------------------
+// "packed rows" tensors of the embedder's levels 4 / 3 (csrc/rsconv.cu): [G images][H][Wp][C] bf16, an image row holds F
+// faces side by side at column pitch P = W + 1 (one zero column between neighbours = the 3x3 convs' padding).
+//   pr_avgpool: dlib avg_pool<2,2,2,2> of every face (the ares_down skip path): in [G,H,Wp,Cin] -> out [G,OH,OWp,Cout],
+//               channels >= Cin written as zeros (add_prev zero-extends), gap columns untouched (they stay zero).
+//   pr_unpack:  packed rows -> rows of a PvRowMap (hand-over to the srgemm layers of level 2).
+// ---------------------------------------------------------------------------------------------
+__global__ void pr_avgpool_kernel(const __nv_bfloat16* __restrict__ in, int H, int Wp, int Cin, int P, __nv_bfloat16* __restrict__ out,
+                                  int G, int F, int OH, int OW, int OWp, int OP, int Cout) {
+  const int c8 = Cout / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)G * F * OH * OW * c8;
+  if (idx >= total) return;
+  const int cc = (int)(idx % c8);
+  long long r = idx / c8;
+  const int ox = (int)(r % OW);
+  r /= OW;
+  const int oy = (int)(r % OH);
+  r /= OH;
+  const int f = (int)(r % F);
+  const int g = (int)(r / F);
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
+  if (cc * 8 < Cin) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int y = 2 * oy + (t >> 1), x = f * P + 2 * ox + (t & 1);
+      const uint4 q = *reinterpret_cast<const uint4*>(in + (((long long)g * H + y) * Wp + x) * Cin + cc * 8);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        a[2 * k] = __fadd_rn(a[2 * k], __bfloat162float(h.x));
+        a[2 * k + 1] = __fadd_rn(a[2 * k + 1], __bfloat162float(h.y));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = __fmul_rn(a[k], 0.25f);
+  }
+  uint4 o;
+  o.x = pv_pack_bf16x2(a[0], a[1]);
+  o.y = pv_pack_bf16x2(a[2], a[3]);
+  o.z = pv_pack_bf16x2(a[4], a[5]);
+  o.w = pv_pack_bf16x2(a[6], a[7]);
+  *reinterpret_cast<uint4*>(out + (((long long)g * OH + oy) * OWp + f * OP + ox) * Cout + cc * 8) = o;
+}
+
+__global__ void pr_unpack_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int Wp, int P, int F, int C, int B,
+                                 __nv_bfloat16* __restrict__ out, PvRowMap dst) {
+  const int c8 = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * W * c8;
+  if (idx >= total) return;
+  const int cc = (int)(idx % c8);
+  long long r = idx / c8;
+  const int x = (int)(r % W);
+  r /= W;
+  const int y = (int)(r % H);
+  const int n = (int)(r / H);
+  const int g = n / F, f = n - g * F;
+  const uint4 q = *reinterpret_cast<const uint4*>(in + (((long long)g * H + y) * Wp + f * P + x) * C + cc * 8);
+  *reinterpret_cast<uint4*>(out + row_of(dst, n, y, x) * dst.cols + cc * 8) = q;
+}
+
+// ---------------------------------------------------------------------------------------------
 // embed head: global average over HxW (padded layout pad 0), then y = fc[128,256] . g
 // one CTA of 256 threads per face
 // ---------------------------------------------------------------------------------------------
@@ -273,6 +342,32 @@ extern "C" int pv_avgpool_skip(const void* in, int Cin, int64_t in_plane_rows, i
   avgpool_skip_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in), Cin, in_plane_rows, in_hq, in_wq, static_cast<__nv_bfloat16*>(skip),
       static_cast<__nv_bfloat16*>(out), B, OH, OW, Cout, *dst);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_pr_avgpool(const void* in, int G, int F, int H, int W, int Wp, int Cin, void* out, int OWp, int Cout,
+                             void* stream) {
+  PV_REQUIRE(in && out, "pv_pr_avgpool: null argument");
+  PV_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cout >= Cin && (W + 1) % 2 == 0, "pv_pr_avgpool: channels / face pitch");
+  const int OH = (H - 2) / 2 + 1, OW = (W - 2) / 2 + 1, P = W + 1, OP = P / 2;
+  PV_REQUIRE(F * P <= Wp && F * OP <= OWp, "pv_pr_avgpool: pitches");
+  const long long total = (long long)G * F * OH * OW * (Cout / 8);
+  pr_avgpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), H, Wp, Cin, P, static_cast<__nv_bfloat16*>(out), G, F, OH, OW, OWp, OP, Cout);
+  g_pv_launches.fetch_add(1);
+  PV_CUDA_CHECK(cudaGetLastError());
+  return PV_OK;
+}
+
+extern "C" int pv_pr_unpack(const void* in, int B, int F, int H, int W, int Wp, int C, void* out, const PvRowMap* dst,
+                            void* stream) {
+  PV_REQUIRE(in && out && dst, "pv_pr_unpack: null argument");
+  PV_REQUIRE(C % 8 == 0 && dst->cols >= C && F * (W + 1) <= Wp, "pv_pr_unpack: geometry");
+  const long long total = (long long)B * H * W * (C / 8);
+  pr_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), H, W, Wp, W + 1, F, C, B, static_cast<__nv_bfloat16*>(out), *dst);
   g_pv_launches.fetch_add(1);
   PV_CUDA_CHECK(cudaGetLastError());
   return PV_OK;

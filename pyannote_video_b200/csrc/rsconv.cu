@@ -56,6 +56,11 @@ struct RsParams {
   int n_stages;
   int* err;
   long long* dbg;   // optional [grid][8] cycle counters (role timing), nullptr = off
+  // embedder extensions: residual added before the ReLU (same geometry as `out`), and "gap" columns — images that hold
+  // several faces side by side, every gap_period-th column (gap_pos) is the zero column between two faces and must
+  // stay zero in the output (it is the padding of both neighbours)
+  const __nv_bfloat16* resid;
+  int gap_period, gap_pos;
 };
 
 __host__ __device__ constexpr int rs_align1k(int v) { return (v + 1023) & ~1023; }
@@ -348,6 +353,7 @@ __global__ void __launch_bounds__(kThreads, (NC <= 32 ? 2 : 1)) rsconv_kernel(co
       const int rb = min(ra + p.seg_rows, p.OH);
       const int ox = strip * kTileW + m;
       const bool xvalid = ox < p.OW;
+      const bool gap = p.gap_period > 0 && (ox % p.gap_period) == p.gap_pos;
       for (int r = ra; r < rb; ++r) {
         const uint32_t rel = cnt + (uint32_t)(r - ra);
         const uint32_t slot = rel % NSLOT;
@@ -369,9 +375,21 @@ __global__ void __launch_bounds__(kThreads, (NC <= 32 ? 2 : 1)) rsconv_kernel(co
           for (int j = 0; j < NC / 16; ++j) {
             float f[16];
 #pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = fmaf(__uint_as_float(v[j][k]), s_scale[j * 16 + k], s_shift[j * 16 + k]);
+            if (!F32 && p.resid) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.out_cs + j * 16);
+              const uint4 ra4 = __ldg(rp), rb4 = __ldg(rp + 1);
+              const uint32_t rw[8] = {ra4.x, ra4.y, ra4.z, ra4.w, rb4.x, rb4.y, rb4.z, rb4.w};
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                f[2 * k] += __uint_as_float(rw[k] << 16);
+                f[2 * k + 1] += __uint_as_float(rw[k] & 0xFFFF0000u);
+              }
+            }
+#pragma unroll
             for (int k = 0; k < 16; ++k) {
-              f[k] = fmaf(__uint_as_float(v[j][k]), s_scale[j * 16 + k], s_shift[j * 16 + k]);
               if (p.relu) f[k] = fmaxf(f[k], 0.f);
+              if (gap) f[k] = 0.f;
             }
             if (F32) {
               float* dp = reinterpret_cast<float*>(p.out) + pix * p.out_cs + j * 16;
@@ -442,6 +460,9 @@ constexpr RsInstance kRsInstances[] = {
     {32, 48, 5, 5, 1, 0},   // conv4
     {48, 48, 5, 5, 1, 0},   // conv5, conv6
     {48, 16, 9, 1, 1, 1},   // conv7 as 9x1 (filter columns as output channels), fp32 rows
+    {32, 32, 3, 3, 1, 0},   // embedder level 4 (35 x 35, faces side by side)
+    {32, 64, 3, 3, 2, 0},   // embedder level 3 entry (stride 2)
+    {64, 64, 3, 3, 1, 0},   // embedder level 3 (17 x 17)
 };
 constexpr int kNumRsInstances = sizeof(kRsInstances) / sizeof(kRsInstances[0]);
 
@@ -496,7 +517,10 @@ extern "C" int pv_rsconv_create(const PvDetconvDesc* d, void** out_handle) {
     case 1: rs_geometry<32, 32, 5, 5, 2>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
     case 2: rs_geometry<32, 48, 5, 5, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
     case 3: rs_geometry<48, 48, 5, 5, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
-    default: rs_geometry<48, 16, 9, 1, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
+    case 4: rs_geometry<48, 16, 9, 1, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
+    case 5: rs_geometry<32, 32, 3, 3, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
+    case 6: rs_geometry<32, 64, 3, 3, 2>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
+    default: rs_geometry<64, 64, 3, 3, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
   }
   PV_REQUIRE(d->w_bytes == (int64_t)w_bytes, "pv_rsconv_create: weight image is %lld bytes, expected %d", (long long)d->w_bytes, w_bytes);
   const size_t fixed = (2 * kMaxStages + 2 * kMaxSlots + 1) * sizeof(uint64_t) + 2 * in.N * sizeof(float) + 64;
@@ -587,6 +611,10 @@ extern "C" int pv_rsconv_create(const PvDetconvDesc* d, void** out_handle) {
     p.segs = (OH + best_rows - 1) / best_rows;
   }
   p.relu = d->relu;
+  p.resid = static_cast<const __nv_bfloat16*>(d->resid);
+  p.gap_period = d->gap_period;
+  p.gap_pos = d->gap_pos;
+  PV_REQUIRE(!d->resid || (reinterpret_cast<uintptr_t>(d->resid) & 31) == 0, "pv_rsconv_create: residual must be 32-byte aligned");
   p.n_stages = n_stages;
   p.err = plan->d_err;
   plan->kind = kind;
@@ -615,7 +643,10 @@ extern "C" int pv_rsconv_run(void* handle, int B, void* stream) {
     case 1: e = rs_launch<32, 32, 5, 5, 2, false>(plan, p, grid, st); break;
     case 2: e = rs_launch<32, 48, 5, 5, 1, false>(plan, p, grid, st); break;
     case 3: e = rs_launch<48, 48, 5, 5, 1, false>(plan, p, grid, st); break;
-    default: e = rs_launch<48, 16, 9, 1, 1, true>(plan, p, grid, st); break;
+    case 4: e = rs_launch<48, 16, 9, 1, 1, true>(plan, p, grid, st); break;
+    case 5: e = rs_launch<32, 32, 3, 3, 1, false>(plan, p, grid, st); break;
+    case 6: e = rs_launch<32, 64, 3, 3, 2, false>(plan, p, grid, st); break;
+    default: e = rs_launch<64, 64, 3, 3, 1, false>(plan, p, grid, st); break;
   }
   g_pv_launches.fetch_add(1);
   PV_CUDA_CHECK(e);

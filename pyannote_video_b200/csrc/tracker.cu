@@ -2,11 +2,11 @@
 // ONE launch.  Replaces dlib.correlation_tracker.start_track / update / get_position called per
 // tracker per frame from Python (pyannote/video/tracking.py:203,231,250-251).
 //
-// Per track state in HBM (float32): A[31][64x64] complex numerators, B[64x64] denominator,
-// position (l,t,r,b).  update = chip (bilinear, rect*1.4 -> 64x64) -> FHOG-31 (cell 1) x cosine
-// window -> 31 2-D FFTs (shared memory, radix-2) -> response = ifft2(sum F_i conj(A_i)/(B+lambda))
-// -> argmax / sub-pixel / PSR (warp-shuffle + shared reductions) -> position -> filter update
-// (features are recomputed rather than spilled: 1 MB of state is read twice and written once).
+// Per track state in HBM (float32): A[31][33x64] complex numerators (half plane: the spectra of real features are
+// Hermitian), B[33x64] denominator, position (l,t,r,b).  update = chip (bilinear, rect*1.4 -> 64x64) -> FHOG-31 (cell 1)
+// x cosine window -> 16 packed 2-D FFTs (shared memory, radix-8) -> response = ifft2(sum F_i conj(A_i)/(B+lambda))
+// -> argmax / sub-pixel / PSR (warp-shuffle + shared reductions) -> position -> filter update from the spectra that
+// pass 1 spilled to a scratch plane (0.5 MB per track, re-read by the thread that wrote it).
 // A second kernel runs the 1-D scale filter (32 scales, FHOG cell 4).  Mirrors oracle/dsst.py step by step.
 #include <atomic>
 #include "../../include/pv_b200.h"
@@ -28,8 +28,9 @@ struct TrackerTables {
 };
 
 struct BankParams {
-  float2* A;        // [cap][31][4096]
-  float* B;         // [cap][4096]
+  float2* A;        // [cap][31][2112]  numerators, half plane ky <= 32 (Hermitian spectra of real features)
+  float2* F;        // [cap][31][2112]  scratch: the spectra of the current update, written by pass 1, read by pass 2
+  float* B;         // [cap][2112]
   float* pos;       // [cap][4]
   float* psr;       // [cap]
   const int* ids;   // [n] slots handled by this launch
@@ -39,6 +40,9 @@ struct BankParams {
   int H, W;
   float padding, lambda, nu;
 };
+
+// u8 -> f32 without the conversion unit (I2F runs at a quarter of the FP32 rate): (2^23 | b) - 2^23 is exact
+__device__ __forceinline__ float u8f(uint32_t b) { return __fsub_rn(__uint_as_float(0x4B000000u | b), 8388608.0f); }
 
 __device__ __forceinline__ int rev6(int v) { return (int)(__brev((unsigned)v) >> 26); }
 
@@ -161,8 +165,8 @@ __device__ void features_prepare(const BankParams& p, const TrackerTables& tb, c
       const uint8_t* pbl = ptl + (long long)p.W * 3;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float a = __fadd_rn(__fmul_rn(omlr, (float)ptl[c]), __fmul_rn(lr, (float)ptl[3 + c]));
-        const float bb = __fadd_rn(__fmul_rn(omlr, (float)pbl[c]), __fmul_rn(lr, (float)pbl[3 + c]));
+        const float a = __fadd_rn(__fmul_rn(omlr, u8f(ptl[c])), __fmul_rn(lr, u8f(ptl[3 + c])));
+        const float bb = __fadd_rn(__fmul_rn(omlr, u8f(pbl[c])), __fmul_rn(lr, u8f(pbl[3 + c])));
         float v = __fadd_rn(__fmul_rn(omtb, a), __fmul_rn(tbv, bb));
         v = fminf(fmaxf(floorf(__fadd_rn(v, 0.5f)), 0.f), 255.f);
         o[c] = (uint8_t)v;
@@ -181,8 +185,8 @@ __device__ void features_prepare(const BankParams& p, const TrackerTables& tb, c
       float gx = 0.f, gy = 0.f, best = -1.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float dx = __fsub_rn((float)s.chip[3 * (i + 1) + c], (float)s.chip[3 * (i - 1) + c]);
-        const float dy = __fsub_rn((float)s.chip[3 * (i + FS) + c], (float)s.chip[3 * (i - FS) + c]);
+        const float dx = __fsub_rn(u8f(s.chip[3 * (i + 1) + c]), u8f(s.chip[3 * (i - 1) + c]));
+        const float dy = __fsub_rn(u8f(s.chip[3 * (i + FS) + c]), u8f(s.chip[3 * (i - FS) + c]));
         const float v = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
         if (v > best) { best = v; gx = dx; gy = dy; }
       }
@@ -288,9 +292,15 @@ __device__ void target_hat(Smem& s, const TrackerTables& tb, float px, float py,
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Every thread owns the 8 spectrum bins i = tid + 512 k for the whole kernel: the response accumulator and conj(G^) live
-// in registers, so that the CTA needs 103 KB of shared memory and two CTAs (two tracks) share an SM — 256 tracks are one
-// wave on 148 SMs and one track's transforms overlap the other's state traffic.
+// The features are REAL, so every spectrum is Hermitian, F[-k] = conj(F[k]): only the half plane ky <= 32 (33 x 64 = 2112
+// bins) is stored and processed — numerators A, denominator B, and the per-update spectra F that pass 1 spills so that
+// pass 2 (the filter update, which needs the peak found by pass 1) streams them back instead of redoing 16 transforms.
+// Every thread owns the same bins (h = tid + 512 k, k < 4, plus h = 2048 + tid for tid < 64) for the whole kernel: the
+// response accumulator and conj(G^) live in registers, the spilled spectra are re-read by the thread that wrote them (no
+// synchronisation), the CTA needs 95 KB of shared memory and two CTAs (two tracks) share an SM.
+constexpr int NHB = 33 * FS;          // stored half-plane bins per channel
+constexpr int NB = 5;                 // bins per thread (the fifth only for tid < 64)
+
 template <bool START>
 __global__ void __launch_bounds__(kThreads, 2) tracker_kernel(BankParams p, const __grid_constant__ TrackerTables tbc) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -306,8 +316,9 @@ __global__ void __launch_bounds__(kThreads, 2) tracker_kernel(BankParams p, cons
   const int tid = threadIdx.x;
   const int slot = p.ids[blockIdx.x];
   if (p.frame_idx) p.frame += (size_t)p.frame_idx[blockIdx.x] * p.H * p.W * 3;
-  float2* A = p.A + (size_t)slot * NCH * NPIX;
-  float* B = p.B + (size_t)slot * NPIX;
+  float2* A = p.A + (size_t)slot * NCH * NHB;
+  float2* F = p.F + (size_t)slot * NCH * NHB;
+  float* B = p.B + (size_t)slot * NHB;
   float rect[4];
   if (START) {
 #pragma unroll
@@ -315,89 +326,95 @@ __global__ void __launch_bounds__(kThreads, 2) tracker_kernel(BankParams p, cons
   } else {
 #pragma unroll
     for (int k = 0; k < 4; ++k) rect[k] = p.pos[slot * 4 + k];
-    if ((tid & 15) == 0) prefetch_l2(A + tid), prefetch_l2(A + NPIX + tid);
+    if ((tid & 15) == 0) prefetch_l2(A + tid), prefetch_l2(A + NHB + tid);
   }
   features_prepare(p, tb, rect, s, tf);
   features_osum(s);
-  const int ybase = tid >> 6, xcol = tid & 63;    // bin k of this thread: row ybase + 8 k, column xcol
+  const int ybase = tid >> 6, xcol = tid & 63;    // bin k of this thread: row ybase + 8 k (k < 4) or row 32 (k = 4), column xcol
+  const int nb = tid < FS ? NB : NB - 1;
 
   if (START) {
     float2 g[8];
     target_hat(s, tb, 0.5f * (FS - 1), 0.5f * (FS - 1), g);
-    for (int i = tid; i < NPIX; i += kThreads) s.bsum[i] = 0.f;
+    // g[k] holds rows ybase + 8 k, k < 8; row 32 of the threads tid < 64 is g[4] (ybase = 0)
+    for (int i = tid; i < NHB; i += kThreads) s.bsum[i] = 0.f;
     __syncthreads();
     for (int ch = 0; ch < NCH; ch += 2) {
       const bool two = ch + 1 < NCH;
       build_plane2(s, tb, ch, two ? ch + 1 : -1);
       fft2_64(s.plane, tb, false);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int i = tid + k * kThreads;
+      for (int k = 0; k < nb; ++k) {
+        const int h = tid + k * kThreads;
         float2 fa, fb;
         split_spectra(s, ybase + 8 * k, xcol, fa, fb);
-        A[(size_t)ch * NPIX + i] = cmul(g[k], fa);
+        A[(size_t)ch * NHB + h] = cmul(g[k], fa);
         float bs = fa.x * fa.x + fa.y * fa.y;
         if (two) {
-          A[(size_t)(ch + 1) * NPIX + i] = cmul(g[k], fb);
+          A[(size_t)(ch + 1) * NHB + h] = cmul(g[k], fb);
           bs += fb.x * fb.x + fb.y * fb.y;
         }
-        s.bsum[i] += bs;
+        s.bsum[h] += bs;
       }
       __syncthreads();
     }
-    for (int i = tid; i < NPIX; i += kThreads) B[i] = s.bsum[i];
+    for (int i = tid; i < NHB; i += kThreads) B[i] = s.bsum[i];
     if (tid < 4) p.pos[slot * 4 + tid] = rect[tid];
     if (tid == 0) p.psr[slot] = 0.f;
     return;
   }
 
-  // ---- pass 1: response ----
-  float2 acc[8];
+  // ---- pass 1: response; the spectra go to the scratch plane F ----
+  float2 acc[NB];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
-  for (int i = tid; i < NPIX; i += kThreads) s.bsum[i] = 0.f;
+  for (int k = 0; k < NB; ++k) acc[k] = make_float2(0.f, 0.f);
+  for (int i = tid; i < NHB; i += kThreads) s.bsum[i] = 0.f;
   __syncthreads();
   for (int ch = 0; ch < NCH; ch += 2) {
     const bool two = ch + 1 < NCH;
     if (ch + 2 < NCH && (tid & 15) == 0) {   // the next pair's numerators travel to L2 under this pair's transform
-      prefetch_l2(A + (size_t)(ch + 2) * NPIX + tid);
-      prefetch_l2(A + (size_t)(ch + 2) * NPIX + 512 + tid);
-      if (ch + 3 < NCH) {
-        prefetch_l2(A + (size_t)(ch + 3) * NPIX + tid);
-        prefetch_l2(A + (size_t)(ch + 3) * NPIX + 512 + tid);
-      }
+      prefetch_l2(A + (size_t)(ch + 2) * NHB + tid);
+      if (ch + 3 < NCH) prefetch_l2(A + (size_t)(ch + 3) * NHB + tid);
     }
     build_plane2(s, tb, ch, two ? ch + 1 : -1);
     fft2_64(s.plane, tb, false);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = tid + k * kThreads;
-      float2 fa, fb;
-      split_spectra(s, ybase + 8 * k, xcol, fa, fb);
-      const float2 a = A[(size_t)ch * NPIX + i];
-      acc[k].x += fa.x * a.x + fa.y * a.y;   // f * conj(a)
-      acc[k].y += fa.y * a.x - fa.x * a.y;
-      float bs = fa.x * fa.x + fa.y * fa.y;
-      if (two) {
-        const float2 b2 = A[(size_t)(ch + 1) * NPIX + i];
-        acc[k].x += fb.x * b2.x + fb.y * b2.y;
-        acc[k].y += fb.y * b2.x - fb.x * b2.y;
-        bs += fb.x * fb.x + fb.y * fb.y;
+    for (int k = 0; k < NB; ++k) {
+      if (k < nb) {
+        const int h = tid + k * kThreads;
+        float2 fa, fb;
+        split_spectra(s, ybase + 8 * k, xcol, fa, fb);
+        const float2 a = A[(size_t)ch * NHB + h];
+        F[(size_t)ch * NHB + h] = fa;
+        acc[k].x += fa.x * a.x + fa.y * a.y;   // f * conj(a)
+        acc[k].y += fa.y * a.x - fa.x * a.y;
+        float bs = fa.x * fa.x + fa.y * fa.y;
+        if (two) {
+          const float2 b2 = A[(size_t)(ch + 1) * NHB + h];
+          F[(size_t)(ch + 1) * NHB + h] = fb;
+          acc[k].x += fb.x * b2.x + fb.y * b2.y;
+          acc[k].y += fb.y * b2.x - fb.x * b2.y;
+          bs += fb.x * fb.x + fb.y * fb.y;
+        }
+        s.bsum[h] += bs;
       }
-      s.bsum[i] += bs;
     }
     __syncthreads();
   }
   {
     const float nu = p.nu, om = 1.0f - p.nu;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = tid + k * kThreads;
-      const int y = ybase + 8 * k;
-      const float bold = B[i];
-      const float d = 1.0f / (bold + p.lambda);
-      s.plane[rev6(y) * PS + rev6(xcol)] = make_float2(acc[k].x * d, acc[k].y * d);
-      B[i] = om * bold + nu * s.bsum[i];     // the denominator's running update needs nothing from pass 2
+    for (int k = 0; k < NB; ++k) {
+      if (k < nb) {
+        const int h = tid + k * kThreads;
+        const int y = ybase + 8 * k;
+        const float bold = B[h];
+        const float d = 1.0f / (bold + p.lambda);
+        const float2 v = make_float2(acc[k].x * d, acc[k].y * d);
+        s.plane[rev6(y) * PS + rev6(xcol)] = v;
+        if (y >= 1 && y <= 31)               // the other half plane: R^[-k] = conj(R^[k]) (the response is real)
+          s.plane[rev6(FS - y) * PS + rev6((FS - xcol) & (FS - 1))] = make_float2(v.x, -v.y);
+        B[h] = om * bold + nu * s.bsum[h];     // the denominator's running update needs nothing from pass 2
+      }
     }
   }
   __syncthreads();
@@ -487,41 +504,26 @@ __global__ void __launch_bounds__(kThreads, 2) tracker_kernel(BankParams p, cons
   }
   __syncthreads();
 
-  // ---- pass 2: filter update (features are recomputed rather than spilled: the state is read twice, written once) ----
+  // ---- pass 2: filter update A <- (1 - nu) A + nu conj(G^) F, streaming the spilled spectra back (no transforms) ----
   float2 g[8];
   target_hat(s, tb, peak[0], peak[1], g);
   const float nu = p.nu, om = 1.0f - p.nu;
-  for (int ch = 0; ch < NCH; ch += 2) {
-    const bool two = ch + 1 < NCH;
-    if (ch + 2 < NCH && (tid & 15) == 0) {
-      prefetch_l2(A + (size_t)(ch + 2) * NPIX + tid);
-      prefetch_l2(A + (size_t)(ch + 2) * NPIX + 512 + tid);
-      if (ch + 3 < NCH) {
-        prefetch_l2(A + (size_t)(ch + 3) * NPIX + tid);
-        prefetch_l2(A + (size_t)(ch + 3) * NPIX + 512 + tid);
-      }
-    }
-    build_plane2(s, tb, ch, two ? ch + 1 : -1);
-    fft2_64(s.plane, tb, false);
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    float2* Ac = A + (size_t)ch * NHB;
+    const float2* Fc = F + (size_t)ch * NHB;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = tid + k * kThreads;
-      float2 fa, fb;
-      split_spectra(s, ybase + 8 * k, xcol, fa, fb);
-      const float2 ga = cmul(g[k], fa);
-      float2 a = A[(size_t)ch * NPIX + i];
-      a.x = om * a.x + nu * ga.x;
-      a.y = om * a.y + nu * ga.y;
-      A[(size_t)ch * NPIX + i] = a;
-      if (two) {
-        const float2 gb = cmul(g[k], fb);
-        float2 b2 = A[(size_t)(ch + 1) * NPIX + i];
-        b2.x = om * b2.x + nu * gb.x;
-        b2.y = om * b2.y + nu * gb.y;
-        A[(size_t)(ch + 1) * NPIX + i] = b2;
+    for (int k = 0; k < NB; ++k) {
+      if (k < nb) {
+        const int h = tid + k * kThreads;
+        const float2 f = Fc[h];
+        float2 a = Ac[h];
+        const float2 gf = cmul(g[k], f);
+        a.x = om * a.x + nu * gf.x;
+        a.y = om * a.y + nu * gf.y;
+        Ac[h] = a;
       }
     }
-    __syncthreads();
   }
 }
 
@@ -629,8 +631,8 @@ __global__ void __launch_bounds__(kThreads, 2) tracker_scale_kernel(ScaleParams 
         const uint8_t* pbl = ptl + (long long)p.W * 3;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float a = __fadd_rn(__fmul_rn(omlr, (float)ptl[c]), __fmul_rn(lr, (float)ptl[3 + c]));
-          const float bb = __fadd_rn(__fmul_rn(omlr, (float)pbl[c]), __fmul_rn(lr, (float)pbl[3 + c]));
+          const float a = __fadd_rn(__fmul_rn(omlr, u8f(ptl[c])), __fmul_rn(lr, u8f(ptl[3 + c])));
+          const float bb = __fadd_rn(__fmul_rn(omlr, u8f(pbl[c])), __fmul_rn(lr, u8f(pbl[3 + c])));
           float v = __fadd_rn(__fmul_rn(omtb, a), __fmul_rn(tbv, bb));
           o[c] = (uint8_t)fminf(fmaxf(floorf(__fadd_rn(v, 0.5f)), 0.f), 255.f);
         }
@@ -651,8 +653,8 @@ __global__ void __launch_bounds__(kThreads, 2) tracker_scale_kernel(ScaleParams 
       float gx = 0.f, gy = 0.f, best = -1.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float dx = __fsub_rn((float)ch[3 * (pix + 1) + c], (float)ch[3 * (pix - 1) + c]);
-        const float dy = __fsub_rn((float)ch[3 * (pix + SW) + c], (float)ch[3 * (pix - SW) + c]);
+        const float dx = __fsub_rn(u8f(ch[3 * (pix + 1) + c]), u8f(ch[3 * (pix - 1) + c]));
+        const float dy = __fsub_rn(u8f(ch[3 * (pix + SW) + c]), u8f(ch[3 * (pix - SW) + c]));
         const float v = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
         if (v > best) { best = v; gx = dx; gy = dy; }
       }
@@ -866,6 +868,7 @@ struct Bank {
   ScaleTables stb;
   bool has_scale = false;
   float2* A;
+  float2* F = nullptr;
   float* B;
   float* pos;
   float* psr;
@@ -890,8 +893,9 @@ extern "C" int pv_tracker_create(int capacity, const float* hann64_host, const f
   b->padding = padding;
   b->lambda = lambda;
   b->nu = nu;
-  cudaError_t e = cudaMalloc(&b->A, sizeof(float2) * (size_t)capacity * NCH * NPIX);
-  if (e == cudaSuccess) e = cudaMalloc(&b->B, sizeof(float) * (size_t)capacity * NPIX);
+  cudaError_t e = cudaMalloc(&b->A, sizeof(float2) * (size_t)capacity * NCH * NHB);
+  if (e == cudaSuccess) e = cudaMalloc(&b->F, sizeof(float2) * (size_t)capacity * NCH * NHB);
+  if (e == cudaSuccess) e = cudaMalloc(&b->B, sizeof(float) * (size_t)capacity * NHB);
   if (e == cudaSuccess) e = cudaMalloc(&b->pos, sizeof(float) * (size_t)capacity * 4);
   if (e == cudaSuccess) e = cudaMalloc(&b->psr, sizeof(float) * (size_t)capacity);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tracker_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
@@ -909,6 +913,7 @@ extern "C" int pv_tracker_destroy(void* handle) {
   if (!handle) return PV_OK;
   Bank* b = static_cast<Bank*>(handle);
   cudaFree(b->A);
+  cudaFree(b->F);
   cudaFree(b->B);
   cudaFree(b->pos);
   cudaFree(b->psr);
@@ -923,6 +928,7 @@ static int launch(Bank* b, bool start, const void* frame, const int* frame_idx, 
   if (n == 0) return PV_OK;
   BankParams p;
   p.A = b->A;
+  p.F = b->F;
   p.B = b->B;
   p.pos = b->pos;
   p.psr = b->psr;

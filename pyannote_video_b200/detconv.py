@@ -14,6 +14,8 @@ from . import _lib
 
 INSTANCES = {  # (c_in, n_out, kh, kw, stride, out_f32)
     (16, 32, 5, 5, 2, 0), (32, 32, 5, 5, 2, 0), (32, 48, 5, 5, 1, 0), (48, 48, 5, 5, 1, 0), (48, 16, 9, 1, 1, 1)}
+# rsconv additionally serves the embedder's 3x3 layers of levels 4 and 3 (faces packed side by side in an image row)
+INSTANCES_RS = INSTANCES | {(32, 32, 3, 3, 1, 0), (32, 64, 3, 3, 2, 0), (64, 64, 3, 3, 1, 0)}
 
 
 def even(n):
@@ -64,12 +66,15 @@ class DetConv:
     def _pack(weight, c_in, n_out, stride):
         return pack_weight_image(weight, c_in, n_out)
 
-    def __init__(self, x, H, W, weight, stride, scale, shift, relu, c_in, n_out, out_f32=False, out_cs=None):
+    _instances = INSTANCES
+
+    def __init__(self, x, H, W, weight, stride, scale, shift, relu, c_in, n_out, out_f32=False, out_cs=None, out=None,
+                 resid=None, gap=None):
         dev = x.device
         Cout, Cin, KH, KW = weight.shape
         key = (c_in, n_out, KH, KW, stride, int(out_f32))
-        if key not in INSTANCES:
-            raise _lib.PvError("detconv: no kernel instance for %r" % (key,))
+        if key not in self._instances:
+            raise _lib.PvError("%s: no kernel instance for %r" % (type(self).__name__, key))
         B, Hx, pitch, Cx = x.shape
         assert x.dtype == torch.bfloat16 and x.is_contiguous() and (Hx, Cx) == (H, c_in) and pitch == even(W)
         pad_y, pad_x = (KH // 2, KW // 2) if stride == 1 else (0, 0)
@@ -77,8 +82,14 @@ class DetConv:
         self.OW = (W + 2 * pad_x - KW) // stride + 1
         self.out_pitch = even(self.OW)
         self.out_cs = out_cs or n_out
-        self.out = torch.zeros(B, self.OH, self.out_pitch, self.out_cs, dtype=torch.float32 if out_f32 else torch.bfloat16,
-                               device=dev)
+        if out is None:
+            out = torch.zeros(B, self.OH, self.out_pitch, self.out_cs, dtype=torch.float32 if out_f32 else torch.bfloat16,
+                              device=dev)
+        assert tuple(out.shape) == (B, self.OH, self.out_pitch, self.out_cs) and out.is_contiguous()
+        self.out = out
+        self.resid = resid
+        if resid is not None:
+            assert tuple(resid.shape) == tuple(out.shape) and resid.dtype == torch.bfloat16 and resid.is_contiguous()
         self.w_img = self._pack(weight, c_in, n_out, stride).to(dev)
         sc = torch.zeros(n_out, dtype=torch.float32)
         sh = torch.zeros(n_out, dtype=torch.float32)
@@ -96,6 +107,8 @@ class DetConv:
         d.relu = int(relu)
         d.out = self.out.data_ptr()
         d.out_pitch, d.out_cs = self.out_pitch, self.out_cs
+        d.resid = resid.data_ptr() if resid is not None else None
+        d.gap_period, d.gap_pos = (int(gap[0]), int(gap[1])) if gap else (0, 0)
         h = C.c_void_p()
         _lib.check(getattr(_lib.lib(), self._create)(C.byref(d), C.byref(h)), self._create)
         self.h = h
@@ -175,6 +188,7 @@ class RsConv(DetConv):
     """Same layer contract as DetConv on the row-streaming kernel (csrc/rsconv.cu)."""
 
     _create, _run, _check, _destroy = "pv_rsconv_create", "pv_rsconv_run", "pv_rsconv_check", "pv_rsconv_destroy"
+    _instances = INSTANCES_RS
 
     @staticmethod
     def _pack(weight, c_in, n_out, stride):

@@ -37,11 +37,27 @@ def _mean3():
     return (C.c_float * 3)(*W.PIXEL_MEAN)
 
 
+def _packed_rowmap(F, H, Wp, P, C):
+    """PvRowMap kind 2: faces side by side in an image row (csrc/layers.cu row_of)"""
+    rm = _lib.PvRowMap()
+    rm.kind, rm.cols, rm.w, rm.py, rm.px, rm.img, rm.plane_rows = 2, C, Wp, H, P, F, 0
+    return rm
+
+
 class EmbedNet:
-    def __init__(self, model, max_batch, device, group=None):
+    """face_recognition_resnet_model_v1 (29 convs).  impl 'rs' (default): the 3x3 layers of levels 4 and 3 (14 convs,
+    54 % of the FLOPs, 32 / 64 channels) run on the row-streaming kernel csrc/rsconv.cu with FACES_PER_ROW faces packed
+    side by side in one image row (one zero column between neighbours = the convs' padding), so that one MMA multiplies
+    an input row against the three filter rows at once (N = 96 / 192 instead of 32 / 64); conv1 and levels 2..0 stay on
+    the shifted-row GEMM csrc/srgemm.cu.  impl 'srgemm': every conv on srgemm (the round-1 path, kept as cross-check)."""
+
+    FACES_PER_ROW = 7          # 7 x (35 + 1) = 252 columns = two 128-column strips (126 used each); 7 x 18 = 126 at level 3
+
+    def __init__(self, model, max_batch, device, group=None, impl=None):
         if model.get("kind") != "resnet_v1_embedder":
             raise RuntimeError("EmbedNet: not an embedder model")
         group = config.SRGEMM_GROUP if group is None else group
+        self.impl = impl = (config.EMBED_IMPL if impl is None else impl)
         self.B = B = int(max_batch)
         self.dev = device
         S = W.EMB_CHIP
@@ -60,11 +76,17 @@ class EmbedNet:
         # max_pool 3x3 s2
         H = (cp.OH - 3) // 2 + 1
         blocks = model["blocks"]
-        lcur = RowLayout("parity" if blocks[0]["type"] == "ares_down" else "padded", B, H, H, 32,
-                         pad=0 if blocks[0]["type"] == "ares_down" else 1)
-        cur = lcur.alloc(device)
-        self.ops.append(("maxpool", (b1, cur, l1.H, l1.W, 32, lcur.rowmap())))
+        first = 0
+        if impl == "rs":
+            cur, lcur, first = self._build_rs(model, b1, l1, H, device)
+        else:
+            lcur = RowLayout("parity" if blocks[0]["type"] == "ares_down" else "padded", B, H, H, 32,
+                             pad=0 if blocks[0]["type"] == "ares_down" else 1)
+            cur = lcur.alloc(device)
+            self.ops.append(("maxpool", (b1, cur, l1.H, l1.W, 32, lcur.rowmap())))
         for i, blk in enumerate(blocks):
+            if i < first:
+                continue
             nxt = blocks[i + 1]["type"] if i + 1 < len(blocks) else None
             ch = blk["a"]["w"].shape[0]
             wa, wb = _t(blk["a"]["w"]), _t(blk["b"]["w"])
@@ -107,11 +129,82 @@ class EmbedNet:
         self.ops.append(("head", (cur, lcur.H * lcur.W, lcur.C)))
         self.final_layout = lcur
 
+    # ---- levels 4 and 3 on rsconv, faces packed side by side ----
+    def _build_rs(self, model, b1, l1, H, device):
+        """returns (tensor, layout, index of the first block that is NOT handled here)"""
+        B, F = self.B, self.FACES_PER_ROW
+        G = (B + F - 1) // F
+        self.G, blocks = G, model["blocks"]
+
+        def pr(h, w, c):
+            P = w + 1
+            wp = even(F * P)
+            return torch.zeros(G, h, wp, c, dtype=torch.bfloat16, device=device), wp, P
+
+        def rs(x, h, wp, conv, stride, c_in, n_out, gap, out=None, resid=None, face=None):
+            sc, sh = _affine(conv)
+            op = RsConv(x, h, wp, _t(conv["w"]), stride, sc, sh, True, c_in, n_out, out=out, resid=resid, gap=gap)
+            fh, fw = face
+            cout, cin = conv["w"].shape[0], conv["w"].shape[1]
+            fl = 2 * fh * fw * cout * cin * 9
+            self.ops.append(("rsconv", (op, fl)))
+            self.flops_per_face += fl
+            return op.out
+
+        # max_pool: conv1 output rows -> level-4 packed tensor
+        x, wp, P = pr(H, H, 32)
+        self.ops.append(("maxpool", (b1, x, l1.H, l1.W, 32, _packed_rowmap(F, H, wp, P, 32))))
+        h, w, c = H, H, 32
+        i = 0
+        while i < len(blocks):
+            blk = blocks[i]
+            ch = blk["a"]["w"].shape[0]
+            if ch > 64:
+                break
+            if blk["type"] == "ares":
+                gap = (P, w)
+                t = rs(x, h, wp, blk["a"], 1, c, ch, gap, face=(h, w))
+                x = rs(t, h, wp, blk["b"], 1, ch, ch, gap, resid=x, face=(h, w))
+            else:
+                oh, ow = (h - 3) // 2 + 1, (w - 3) // 2 + 1
+                skip, owp, OP = pr(oh, ow, ch)
+                assert OP * 2 == P and (oh, ow) == ((h - 2) // 2 + 1, (w - 2) // 2 + 1)
+                gap = (OP, ow)
+                t = rs(x, h, wp, blk["a"], 2, c, ch, gap, face=(oh, ow))
+                assert tuple(t.shape) == tuple(skip.shape), (t.shape, skip.shape)
+                self.ops.append(("pr_avgpool", (x, G, F, h, w, wp, c, skip, owp, ch)))
+                x = rs(t, oh, owp, blk["b"], 1, ch, ch, gap, resid=skip, face=(oh, ow))
+                h, w, c, wp, P = oh, ow, ch, owp, OP
+            i += 1
+        # hand over to the srgemm layers: the layout the next block reads
+        nxt = blocks[i]["type"] if i < len(blocks) else None
+        if nxt is None:
+            lo = RowLayout("padded", B, h, w, c, pad=0)
+        elif nxt == "ares_down":
+            lo = RowLayout("parity", B, h, w, c, pad=0)
+        else:
+            lo = RowLayout("padded", B, h, w, c, pad=1)
+        o = lo.alloc(device)
+        self.ops.append(("pr_unpack", (x, F, h, w, wp, c, o, lo.rowmap())))
+        return o, lo, i
+
     def _add_conv(self, cp, x, out, lout, sc, sh, relu, resid, lres):
         op = Srgemm(cp, x, out, lout, sc, sh, relu, resid=resid, lres=lres)
         self.ops.append(("conv", (op, cp.lin.img)))
         Cin = cp.lin.C if cp.lin.kind != "gathered" else 3
         self.flops_per_face += 2 * cp.OH * cp.OW * cp.Cout * Cin * cp.KH * cp.KW
+
+    def conv_ops(self):
+        """[(op, flops per face)] of every tensor-core conv launch, in execution order (bench / probes patch op.run)"""
+        out = []
+        for kind, a in self.ops:
+            if kind == "conv":
+                cp = a[0].cp
+                cin = cp.lin.C if cp.lin.kind != "gathered" else 3
+                out.append((a[0], 2 * cp.OH * cp.OW * cp.Cout * cin * cp.KH * cp.KW))
+            elif kind == "rsconv":
+                out.append(a)
+        return out
 
     def forward_chips(self, M):
         """Run the network on self.chips[:M] (RGBA u8).  Returns self.out[:M] (float32 [M,128])."""
@@ -119,12 +212,15 @@ class EmbedNet:
         L = _lib.lib()
         st = _lib.stream_ptr()
         S = W.EMB_CHIP
+        Gm = (M + self.FACES_PER_ROW - 1) // self.FACES_PER_ROW
         _lib.check(L.pv_pack_gathered(_lib.ptr(self.chips), _lib.ptr(self.xg), M, S, S, 7,
                                       C.c_int64(self.lg.plane_rows), _mean3(), st), "pv_pack_gathered")
         for kind, a in self.ops:
             if kind == "conv":
                 op, img = a
                 op.run(M * img)
+            elif kind == "rsconv":
+                a[0].run(Gm)
             elif kind == "maxpool":
                 src, dst, h, w, c, rm = a
                 _lib.check(L.pv_maxpool3x3s2(_lib.ptr(src), _lib.ptr(dst), M, h, w, c, C.byref(rm), st), "pv_maxpool3x3s2")
@@ -133,6 +229,12 @@ class EmbedNet:
                 _lib.check(L.pv_avgpool_skip(_lib.ptr(src), lsrc.C, C.c_int64(lsrc.plane_rows), lsrc.Hq, lsrc.Wq,
                                              _lib.ptr(skip), _lib.ptr(o), M, ph, pw, ch, C.byref(rm), st),
                            "pv_avgpool_skip")
+            elif kind == "pr_avgpool":
+                src, G, F, h, w, wp, c, skip, owp, ch = a
+                _lib.check(L.pv_pr_avgpool(_lib.ptr(src), Gm, F, h, w, wp, c, _lib.ptr(skip), owp, ch, st), "pv_pr_avgpool")
+            elif kind == "pr_unpack":
+                src, F, h, w, wp, c, o, rm = a
+                _lib.check(L.pv_pr_unpack(_lib.ptr(src), M, F, h, w, wp, c, _lib.ptr(o), C.byref(rm), st), "pv_pr_unpack")
             else:
                 src, hw, c = a
                 _lib.check(L.pv_embed_head(_lib.ptr(src), M, hw, c, _lib.ptr(self.fc), _lib.ptr(self.out),
@@ -141,7 +243,7 @@ class EmbedNet:
 
     def check(self):
         for kind, a in self.ops:
-            if kind == "conv":
+            if kind in ("conv", "rsconv"):
                 a[0].check()
 
 

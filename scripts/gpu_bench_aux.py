@@ -52,29 +52,54 @@ def bench_tracker(n_frames):
 
 
 def bench_cluster(n):
-    from pyannote_video_b200.clustering import cluster
+    """C5: 100k x 128-d embeddings around 2000 centroids; input (a) singleton tracks, input (b) 10 embeddings per track
+    (SURVEY.md §8d).  Also times the distance matrix alone (tcgen05 Gram vs the fp32 CUDA-core kernel)."""
+    from pyannote_video_b200.clustering import cluster, pairwise_distances
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(3)
     n_cent = 2000
     cent = torch.randn(n_cent, 128, generator=g)
     cent = cent / cent.norm(dim=1, keepdim=True) * 0.9
     X = (cent[:, None, :] + 0.02 * torch.randn(n_cent, n // n_cent, 128, generator=g)).reshape(-1, 128)
-    X = X[torch.randperm(X.shape[0], generator=g)].contiguous().to(dev)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    tracks, labels, stats = cluster(X, np.arange(X.shape[0]), threshold=0.6, device=dev, return_stats=True)
-    torch.cuda.synchronize()
-    el = time.perf_counter() - t0
-    return dict(bench="C5 clustering", n=int(X.shape[0]), seconds=el, rounds=stats["rounds"], clusters=stats["n_clusters"],
-                pdist_flop=2.0 * X.shape[0] ** 2 * 128 * 1.5)
+    perm = torch.randperm(X.shape[0], generator=g)
+    X = X[perm].contiguous().to(dev)
+    N = int(X.shape[0])
+    out = dict(bench="C5 clustering", n=N)
+    for impl in ("tcgen05", "fp32"):
+        D = pairwise_distances(X, "euclidean", impl=impl)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        del D
+        e0.record()
+        D = pairwise_distances(X, "euclidean", impl=impl)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out["pdist_%s_ms" % impl] = round(ms, 2)
+        if impl == "tcgen05":
+            out["gram_tflops_6term"] = round(6 * 2.0 * N * N * 128 / ms / 1e9, 1)
+            out["gram_write_gbs"] = round(4.0 * N * N / ms / 1e6, 1)
+        del D
+    torch.cuda.empty_cache()
+    # tracks of 10: ten embeddings of the SAME centroid per track (row r of the shuffled matrix was row perm[r] before)
+    orig = perm.numpy()
+    for name, ids in (("singletons", np.arange(N)), ("tracks_of_10", orig // 10)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tracks, labels, stats = cluster(X, ids, threshold=0.6, device=dev, return_stats=True)
+        torch.cuda.synchronize()
+        out[name] = dict(seconds=round(time.perf_counter() - t0, 4), rounds=stats["rounds"], clusters=stats["n_clusters"],
+                         tracks=int(len(tracks)))
+        torch.cuda.empty_cache()
+    return out
 
 
-def bench_embed(batch):
+def bench_embed(batch, impl=None):
     """embed-only: chips -> 29 convs -> 128-d at a large face batch, CUDA events around every conv launch"""
     from pyannote_video_b200 import weights as W
     from pyannote_video_b200.nets import EmbedNet
     dev = torch.device("cuda:0")
-    net = EmbedNet(W.make_embedder(seed=3), batch, dev)
+    net = EmbedNet(W.make_embedder(seed=3), batch, dev, impl=impl)
     net.chips.copy_(torch.randint(0, 256, net.chips.shape, dtype=torch.uint8, device=dev))
     for _ in range(3):
         net.forward_chips(batch)
@@ -89,7 +114,8 @@ def bench_embed(batch):
     ms = e0.elapsed_time(e1) / reps
     # per-layer
     evs = []
-    convs = [a[0] for k, a in net.ops if k == "conv"]
+    conv_fl = net.conv_ops()
+    convs = [op for op, _ in conv_fl]
     orig = [op.run for op in convs]
     for i, op in enumerate(convs):
         def timed(q=None, _r=op.run, _i=i):
@@ -102,15 +128,13 @@ def bench_embed(batch):
     for op, r in zip(convs, orig):
         op.run = r
     layers = []
-    for (i, a, b), op in zip(evs, convs):
-        cp = op.cp
-        cin = cp.lin.C if cp.lin.kind != "gathered" else 3
-        fl = 2.0 * batch * cp.OH * cp.OW * cp.Cout * cin * cp.KH * cp.KW
+    for (i, a, b), (op, flf) in zip(evs, conv_fl):
+        fl = float(batch) * flf
         t = a.elapsed_time(b)
-        layers.append(dict(i=i, out="%dx%dx%d" % (cp.OH, cp.OW, cp.Cout), k=cp.KH, us=round(t * 1e3, 1), tflops=round(fl / t / 1e9, 1)))
+        layers.append(dict(i=i, kernel=type(op).__name__, us=round(t * 1e3, 1), tflops=round(fl / t / 1e9, 1)))
     conv_ms = sum(a.elapsed_time(b) for _, a, b in evs)
     fl = batch * net.flops_per_face
-    return dict(bench="embed-only", batch=batch, ms=ms, faces_per_s=batch / ms * 1e3, tflops=fl / ms / 1e9,
+    return dict(bench="embed-only", impl=net.impl, batch=batch, ms=ms, faces_per_s=batch / ms * 1e3, tflops=fl / ms / 1e9,
                 frac_of_1442=fl / ms / 1e9 / 1442.3, conv_ms=conv_ms, conv_tflops=fl / conv_ms / 1e9, layers=layers)
 
 

@@ -61,7 +61,7 @@ def test_tcgen05_gram_distances_match_scipy(cuda, metric, n):
     assert err.max() < 2e-5
     D32 = pairwise_distances(Xd, metric, impl="fp32").cpu().numpy()
     assert np.abs(D - D32).max() < 2e-5
-    assert np.abs(D - D.T).max() < 1e-6
+    assert np.abs(D - D.T).max() < 2e-5          # D[i][j] and D[j][i] accumulate the six products in different orders
 
 
 @pytest.mark.parametrize("seed,metric,thr", [(1, "euclidean", 0.6), (2, "euclidean", 0.6), (3, "cosine", 0.05)])

@@ -20,15 +20,17 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-12))
 
 
-def test_embed_net_matches_oracle(cuda):
+@pytest.mark.parametrize("impl,M,cap", [("rs", 5, 8), ("rs", 23, 30), ("srgemm", 5, 8)])
+def test_embed_net_matches_oracle(cuda, impl, M, cap):
+    """impl 'rs': levels 4 / 3 on csrc/rsconv.cu with 7 faces packed per image row (M = 23 crosses image rows and leaves the
+    last one partly filled); 'srgemm': every conv on the shifted-row GEMM"""
     from oracle import nets as onets
     from pyannote_video_b200.nets import EmbedNet
     model = W.make_embedder(seed=3)
-    M = 5
     g = torch.Generator().manual_seed(11)
     chips = torch.randint(0, 256, (M, 150, 150, 3), generator=g, dtype=torch.uint8)
     chips = (torch.nn.functional.avg_pool2d(chips.permute(0, 3, 1, 2).float(), 5, 1, 2)).permute(0, 2, 3, 1).to(torch.uint8)
-    net = EmbedNet(model, max_batch=8, device=cuda)
+    net = EmbedNet(model, max_batch=cap, device=cuda, impl=impl)
     net.chips[:M, :, :, :3] = chips.to(cuda)
     net.chips[:M, :, :, 3] = 255
     out = net.forward_chips(M).cpu()
