@@ -301,6 +301,15 @@ int pv_hac_members(const int* keep, const int* partner, const int* newidx, const
                    int* m0, int* m1, float* sizes2, int* map, void* stream);
 int pv_hac_contract(const float* S, int64_t t, const int* m0, const int* m1, float* S2, int64_t tout, void* stream);
 int pv_hac_relabel(int* cl, int64_t n, const int* map, void* stream);
+/* whole-stage form for one-embedding-per-track inputs (what a non-Python consumer binds instead of the Python loop in
+ * clustering.py): X f32 [n][128] (device) -> labels i32 [n] (device), label = smallest row index of the row's cluster.
+ * Allocates its work space (2 n^2 floats + the Gram operands) and synchronises the stream once per round.
+ * rounds_out: HOST int or NULL. */
+int pv_hac_threshold(const float* X, int64_t n, int dim, int metric, float threshold, int strict, int* labels, int* rounds_out,
+                     void* stream);
+/* TrackingByDetection._match (pyannote/video/tracking.py:129-134), HOST function on (l,t,r,b) doubles in dlib drectangle
+ * arithmetic: intersection area, or 0 unless it covers at least `ratio` of both rectangles */
+double pv_rect_overlap(const double* a_ltrb, const double* b_ltrb, double ratio);
 
 /* ------------------------------------------------------------------------------------------
  * correlation-tracker bank (csrc/tracker.cu) — dlib.correlation_tracker start_track / update /

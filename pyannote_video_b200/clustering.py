@@ -77,11 +77,8 @@ def cluster(emb, track_id, threshold=0.6, metric="euclidean", strict=False, devi
     # members of current clusters, in terms of the rows/cols of the current matrix
     sizes = np.diff(np.append(start, N)).astype(np.int64)            # embeddings per track
 
-    def contract(S, tin, member_lists):
-        tout = len(member_lists)
-        offs = np.zeros(tout + 1, np.int32)
-        offs[1:] = np.cumsum([len(g) for g in member_lists])
-        memb = np.concatenate([np.asarray(g, np.int32) for g in member_lists])
+    def contract_csr(S, tin, offs, memb):
+        tout = len(offs) - 1
         offs_d, memb_d = _i32(offs, dev), _i32(memb, dev)
         R = torch.empty(tout, tin, dtype=torch.float32, device=dev)
         _lib.check(L.pv_pool_rows(_lib.ptr(S), C.c_int64(tin), _lib.ptr(offs_d), _lib.ptr(memb_d), _lib.ptr(R),
@@ -94,7 +91,8 @@ def cluster(emb, track_id, threshold=0.6, metric="euclidean", strict=False, devi
     if T == N:
         S = D if np.array_equal(order, np.arange(N)) else D[torch.from_numpy(order).to(dev)][:, torch.from_numpy(order).to(dev)].contiguous()
     else:
-        S = contract(D, N, [order[start[t]:start[t] + sizes[t]].tolist() for t in range(T)])
+        # rows are grouped by track through `order`: the CSR of the first contraction is (start, order) as they stand
+        S = contract_csr(D, N, np.append(start, N).astype(np.int32), order.astype(np.int32))
         del D
     # ---- agglomeration rounds, entirely on the device: the host only learns how many clusters are left ----
     t = T

@@ -259,6 +259,159 @@ extern "C" int pv_hac_relabel(int* cl, int64_t n, const int* map, void* stream) 
   return PV_OK;
 }
 
+// ---- whole-stage entry points (what a non-Python consumer binds) ---------------------------------------------------
+namespace {
+__global__ void hac_iota_kernel(int* a, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (int)i;
+}
+__global__ void hac_count_scan_kernel(const int* __restrict__ keep, int* __restrict__ newidx, long long t, int* __restrict__ total) {
+  // single-CTA exclusive scan of keep[0..t) (t <= a few 10^5: one pass of 1024 threads with a running carry)
+  __shared__ int s_part[1024];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < t; base += 1024) {
+    const long long i = base + threadIdx.x;
+    const int v = i < t ? keep[i] : 0;
+    s_part[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int add = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_part[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < t) newidx[i] = s_carry + s_part[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry += s_part[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_carry;
+}
+__global__ void hac_first_kernel(const int* __restrict__ cl, long long n, int* __restrict__ first) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMin(&first[cl[i]], (int)i);
+}
+__global__ void hac_label_kernel(const int* __restrict__ cl, const int* __restrict__ first, long long n, int* __restrict__ labels) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) labels[i] = first[cl[i]];
+}
+__global__ void hac_fill_kernel(int* a, long long n, int v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+__global__ void hac_ones_kernel(float* a, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = 1.0f;
+}
+}  // namespace
+
+extern "C" int pv_gram_dist(const float* X, int64_t n, int dim, int metric, float* D, void* xs_ws, float* norms_ws, int* err_flag,
+                            void* stream);
+extern "C" int64_t pv_gram_npad(int64_t n);
+
+/* FaceClustering as one call for embeddings that are one-per-track (pyannote/video/face/clustering.py:92-148 with
+ * singleton tracks): X f32 [n][128] (device) -> labels i32 [n] (device): label = smallest row index of the row's cluster.
+ * Average-linkage agglomeration stopped at `threshold` (strict: stop at >=).  Allocates its work space (2 n^2 floats + the
+ * Gram operands) with cudaMalloc and synchronises the stream once per round (it reads how many clusters are left).
+ * rounds_out (HOST, may be NULL) receives the number of rounds. */
+extern "C" int pv_hac_threshold(const float* X, int64_t n, int dim, int metric, float threshold, int strict, int* labels,
+                                int* rounds_out, void* stream) {
+  PV_REQUIRE(X && labels, "pv_hac_threshold: null argument");
+  PV_REQUIRE(dim == kDim, "pv_hac_threshold: dim=%d (must be 128)", dim);
+  if (rounds_out) *rounds_out = 0;
+  if (n == 0) return PV_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long npad = pv_gram_npad(n);
+  float *bufA = nullptr, *bufB = nullptr, *norms = nullptr, *sz = nullptr, *sz2 = nullptr, *nnd = nullptr;
+  void* xs = nullptr;
+  int *nn = nullptr, *keep = nullptr, *partner = nullptr, *newidx = nullptr, *m0 = nullptr, *m1 = nullptr, *map = nullptr, *cl = nullptr,
+      *first = nullptr, *d_total = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(bufA); cudaFree(bufB); cudaFree(norms); cudaFree(sz); cudaFree(sz2); cudaFree(nnd); cudaFree(xs); cudaFree(nn);
+    cudaFree(keep); cudaFree(partner); cudaFree(newidx); cudaFree(m0); cudaFree(m1); cudaFree(map); cudaFree(cl); cudaFree(first);
+    cudaFree(d_total);
+  };
+#define PV_TRY(expr)                                                          \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) {                                                  \
+      pv_set_error("pv_hac_threshold: %s -> %s", #expr, cudaGetErrorString(_e)); \
+      cleanup();                                                              \
+      return PV_ERR_CUDA;                                                     \
+    }                                                                         \
+  } while (0)
+  PV_TRY(cudaMalloc(&bufA, sizeof(float) * (size_t)n * n));
+  PV_TRY(cudaMalloc(&xs, (size_t)3 * npad * kDim * 2));
+  PV_TRY(cudaMalloc(&norms, sizeof(float) * npad));
+  PV_TRY(cudaMalloc(&sz, sizeof(float) * n));
+  PV_TRY(cudaMalloc(&sz2, sizeof(float) * n));
+  PV_TRY(cudaMalloc(&nnd, sizeof(float) * n));
+  PV_TRY(cudaMalloc(&nn, sizeof(int) * n));
+  PV_TRY(cudaMalloc(&keep, sizeof(int) * n));
+  PV_TRY(cudaMalloc(&partner, sizeof(int) * n));
+  PV_TRY(cudaMalloc(&newidx, sizeof(int) * n));
+  PV_TRY(cudaMalloc(&m0, sizeof(int) * n));
+  PV_TRY(cudaMalloc(&m1, sizeof(int) * n));
+  PV_TRY(cudaMalloc(&map, sizeof(int) * n));
+  PV_TRY(cudaMalloc(&cl, sizeof(int) * n));
+  PV_TRY(cudaMalloc(&first, sizeof(int) * n));
+  PV_TRY(cudaMalloc(&d_total, sizeof(int)));
+  const unsigned gb = (unsigned)((n + 255) / 256);
+  int rc = pv_gram_dist(X, n, dim, metric, bufA, xs, norms, nullptr, stream);
+  if (rc != PV_OK) { cleanup(); return rc; }
+  hac_iota_kernel<<<gb, 256, 0, st>>>(cl, n);
+  hac_ones_kernel<<<gb, 256, 0, st>>>(sz, n);
+  float* S = bufA;
+  float* other = nullptr;      // allocated at the first contraction (its size is known then)
+  long long t = n;
+  int rounds = 0;
+  while (t > 1) {
+    rc = pv_row_argmin(S, t, sz, nn, nnd, stream);
+    if (rc == PV_OK) rc = pv_hac_plan(nn, nnd, t, threshold, strict, keep, partner, stream);
+    if (rc != PV_OK) { cleanup(); return rc; }
+    hac_count_scan_kernel<<<1, 1024, 0, st>>>(keep, newidx, t, d_total);
+    int tout = 0;
+    PV_TRY(cudaMemcpyAsync(&tout, d_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PV_TRY(cudaStreamSynchronize(st));
+    if (tout == t) break;
+    if (!other) {
+      PV_TRY(cudaMalloc(&bufB, sizeof(float) * (size_t)tout * tout));
+      other = bufB;
+    }
+    rc = pv_hac_members(keep, partner, newidx, nn, sz, t, m0, m1, sz2, map, stream);
+    if (rc == PV_OK) rc = pv_hac_contract(S, t, m0, m1, other, tout, stream);
+    if (rc == PV_OK) rc = pv_hac_relabel(cl, n, map, stream);
+    if (rc != PV_OK) { cleanup(); return rc; }
+    float* tmp = S; S = other; other = tmp;
+    float* ts = sz; sz = sz2; sz2 = ts;
+    t = tout;
+    ++rounds;
+  }
+  hac_fill_kernel<<<gb, 256, 0, st>>>(first, n, 0x7fffffff);
+  hac_first_kernel<<<gb, 256, 0, st>>>(cl, n, first);
+  hac_label_kernel<<<gb, 256, 0, st>>>(cl, first, n, labels);
+  PV_TRY(cudaStreamSynchronize(st));
+  PV_TRY(cudaGetLastError());
+#undef PV_TRY
+  if (rounds_out) *rounds_out = rounds;
+  cleanup();
+  return PV_OK;
+}
+
+/* TrackingByDetection._match (pyannote/video/tracking.py:129-134): area of the intersection of two (l,t,r,b) rectangles in
+ * dlib drectangle arithmetic (width = r - l), or 0 unless it covers at least `ratio` of BOTH rectangles.  Host function. */
+extern "C" double pv_rect_overlap(const double* a, const double* b, double ratio) {
+  const double l = a[0] > b[0] ? a[0] : b[0], t = a[1] > b[1] ? a[1] : b[1];
+  const double r = a[2] < b[2] ? a[2] : b[2], bo = a[3] < b[3] ? a[3] : b[3];
+  if (r <= l || bo <= t) return 0.0;
+  const double inter = (r - l) * (bo - t);
+  const double a1 = (a[2] - a[0]) * (a[3] - a[1]), a2 = (b[2] - b[0]) * (b[3] - b[1]);
+  if (inter >= ratio * a1 && inter >= ratio * a2) return inter;
+  return 0.0;
+}
+
 extern "C" int pv_pdist(const float* X, int64_t n, int dim, int metric, float* D, void* stream) {
   PV_REQUIRE(X && D, "pv_pdist: null argument");
   PV_REQUIRE(dim == kDim, "pv_pdist: dim=%d (must be 128)", dim);

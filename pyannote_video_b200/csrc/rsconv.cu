@@ -357,6 +357,19 @@ __global__ void __launch_bounds__(kThreads, (NC <= 32 ? 2 : 1)) rsconv_kernel(co
       for (int r = ra; r < rb; ++r) {
         const uint32_t rel = cnt + (uint32_t)(r - ra);
         const uint32_t slot = rel % NSLOT;
+        const long long pix = ((long long)b * p.OH + r) * p.out_pitch + ox;
+        // the residual row does not depend on the accumulator: its loads are issued BEFORE the wait for the row's MMAs
+        // (behind the wait they doubled the epilogue time of the embedder's second conv of every block)
+        uint4 res[NC / 16][2];
+        const bool has_res = !F32 && p.resid != nullptr && xvalid;
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < NC / 16; ++j) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.out_cs + j * 16);
+            res[j][0] = __ldg(rp);
+            res[j][1] = __ldg(rp + 1);
+          }
+        }
         const long long e0 = p.dbg ? clock64() : 0;
         pv_mbar_wait(&bar_rfull[slot], (rel / NSLOT) & 1u, p.err, 4);
         pv_tc_fence_after();
@@ -370,16 +383,13 @@ __global__ void __launch_bounds__(kThreads, (NC <= 32 ? 2 : 1)) rsconv_kernel(co
         __syncwarp();
         if (lane == 0) pv_mbar_arrive(&bar_rempty[slot]);      // accumulator row is in registers: release the slot
         if (xvalid) {
-          const long long pix = ((long long)b * p.OH + r) * p.out_pitch + ox;
 #pragma unroll
           for (int j = 0; j < NC / 16; ++j) {
             float f[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) f[k] = fmaf(__uint_as_float(v[j][k]), s_scale[j * 16 + k], s_shift[j * 16 + k]);
-            if (!F32 && p.resid) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.out_cs + j * 16);
-              const uint4 ra4 = __ldg(rp), rb4 = __ldg(rp + 1);
-              const uint32_t rw[8] = {ra4.x, ra4.y, ra4.z, ra4.w, rb4.x, rb4.y, rb4.z, rb4.w};
+            if (has_res) {
+              const uint32_t rw[8] = {res[j][0].x, res[j][0].y, res[j][0].z, res[j][0].w, res[j][1].x, res[j][1].y, res[j][1].z, res[j][1].w};
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 f[2 * k] += __uint_as_float(rw[k] << 16);

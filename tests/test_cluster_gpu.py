@@ -108,3 +108,26 @@ def test_face_clustering_file_roundtrip(cuda, tmp_path):
     for segment, track, label in result.itertracks(yield_label=True):
         assert label in kept and segment.end > segment.start
     assert FaceClustering(threshold=0.6, force=True)(starting_point, features=features) == result
+
+
+def test_whole_stage_c_entry_point_matches_the_python_loop(cuda):
+    """pv_hac_threshold (one C call: tcgen05 Gram -> rounds of argmin / plan / contract on the device) gives the partition
+    of the Python-driven loop and of scipy's average linkage cut"""
+    from scipy.cluster.hierarchy import linkage, fcluster
+    from pyannote_video_b200 import _lib
+    from pyannote_video_b200.clustering import cluster
+    rng = np.random.default_rng(5)
+    cent = rng.standard_normal((30, 128)) * 0.35
+    X = np.concatenate([c + 0.02 * rng.standard_normal((20, 128)) for c in cent]).astype(np.float32)
+    X = X[rng.permutation(len(X))]
+    n = len(X)
+    Xd = torch.from_numpy(X).to(cuda)
+    labels = torch.empty(n, dtype=torch.int32, device=cuda)
+    rounds = C.c_int(0)
+    _lib.check(_lib.lib().pv_hac_threshold(_lib.ptr(Xd), C.c_int64(n), 128, 0, C.c_float(0.6), 0, _lib.ptr(labels),
+                                           C.byref(rounds), _lib.stream_ptr()), "pv_hac_threshold")
+    got = dict(enumerate(labels.cpu().tolist()))
+    tracks, lab = cluster(X, np.arange(n), threshold=0.6, device=cuda)
+    assert got == dict(zip(tracks.tolist(), lab.tolist())) and rounds.value > 0
+    Z = fcluster(linkage(X.astype(np.float64), "average"), t=0.6, criterion="distance")
+    assert ohac.partition_of(got) == ohac.partition_of(dict(enumerate(Z.tolist())))

@@ -223,3 +223,26 @@ def test_fhog_known_answers():
     assert inner[18].max() > 0 and inner[19:27].max() == 0
     f4 = fhog_cell4(ramp[:23, :23])
     assert f4.shape == (31, 4, 4) and f4[0].min() > 0 and f4[1:18].max() == 0
+
+
+def test_rect_overlap_c_entry_point_matches_the_python_rule():
+    """pv_rect_overlap (host function of the C ABI) == geometry.match_overlap == TrackingByDetection._match
+    (pyannote/video/tracking.py:129-134) on random and degenerate rectangles"""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "pyannote_video_b200", "libpvb200.so"))
+    lib.pv_rect_overlap.restype = ctypes.c_double
+    rng = np.random.default_rng(0)
+    cases = [((0, 0, 10, 10), (5, 5, 15, 15)), ((0, 0, 10, 10), (10, 0, 20, 10)), ((0, 0, 10, 10), (2, 2, 8, 8)),
+             ((0, 0, 4, 4), (0, 0, 4, 4))]
+    for _ in range(200):
+        a = rng.uniform(0, 100, 2)
+        b = rng.uniform(0, 100, 2)
+        cases.append(((a[0], a[1], a[0] + rng.uniform(1, 60), a[1] + rng.uniform(1, 60)),
+                      (b[0], b[1], b[0] + rng.uniform(1, 60), b[1] + rng.uniform(1, 60))))
+    for ra, rb in cases:
+        for ratio in (0.3, 0.5):
+            A = (ctypes.c_double * 4)(*ra)
+            B = (ctypes.c_double * 4)(*rb)
+            got = lib.pv_rect_overlap(A, B, ctypes.c_double(ratio))
+            ref = match_overlap(DRect(*ra), DRect(*rb), ratio)
+            assert abs(got - ref) < 1e-9, (ra, rb, ratio, got, ref)
