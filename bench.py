@@ -214,6 +214,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tracker", action="store_true", help="leave the tracker updates out of the step (C2 without tracking)")
     ap.add_argument("--profile-convs", type=int, default=2, help="instrumented steps for the roofline leg")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="after the warm-up, run ONE serialised step between cudaProfilerStart/Stop and exit (for `ncu "
+                         "--profile-from-start off`: the launch list / --set full capture of exactly one step)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -362,6 +365,13 @@ def main():
     for s in range(args.warmup):
         step_resident(s)
     sync_all()
+    if args.ncu_step:
+        overlap[0] = False
+        torch.cuda.profiler.start()
+        step_resident(args.warmup)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
