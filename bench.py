@@ -429,7 +429,7 @@ def main():
     roof = None
     if rank == 0 and args.profile_convs > 0:
         net = face.face_recognition_
-        det_names = ["conv%d" % (i + 1) for i in range(len(det0.convs))]
+        det_names = list(det0.layer_names)           # "conv1+2" = conv1 and conv2 in one launch (csrc/c12.cu)
         conv_ops = [(n, op) for n, (op, _) in zip(det_names, det0.convs)] + [("embed", op) for op, _ in net.conv_ops()]
         evs = []
         orig = {}
@@ -485,13 +485,13 @@ def main():
         layer_ms = {}
         for name, a, b in evs:
             layer_ms[name] = layer_ms.get(name, 0.0) + a.elapsed_time(b) / P
-        layer_flops = {n: B * f for n, f in zip(det_names, det0.algorithmic_flops_per_layer)}   # per pyramid pixel, padding excluded
+        layer_flops = {n: B * f for n, f in zip(det_names, det0.algorithmic_flops_per_op)}   # per pyramid pixel, padding excluded
         layer_flops["embed"] = B * FACES_PER_FRAME * net.flops_per_face
         peaks = load_peaks()
         peak = peaks["tf_sustained"]
         layers = {n: dict(ms=round(layer_ms[n], 4), tflops=round(layer_flops[n] / (layer_ms[n] * 1e-3) / 1e12, 1),
                           frac=round(layer_flops[n] / (layer_ms[n] * 1e-3) / 1e12 / peak, 4)) for n in layer_ms}
-        dom = det_names[1:]
+        dom = [n for n in det_names if n not in ("conv1", "conv1+2")]      # the rsconv_kernel launches
         dom_ms = sum(layer_ms[n] for n in dom)
         dom_fl = sum(layer_flops[n] for n in dom)
         all_ms = sum(layer_ms.values())
@@ -501,7 +501,9 @@ def main():
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            if tj.get("plane") == [det0.geo.plane_h, det0.geo.plane_w] and tj.get("impl", "detconv") == det0.conv_impl:
+            tj_layers = tj.get("layers", ["conv%d" % i for i in range(2, 8)])
+            if (tj.get("plane") == [det0.geo.plane_h, det0.geo.plane_w] and tj.get("impl", "detconv") == det0.conv_impl
+                    and tj_layers == dom):
                 traffic = tj["detconv_dram_bytes_per_frame"] * B
                 traffic_source = ("static: dram__bytes_read+write of the six rsconv launches from the committed ncu --set full "
                                   "capture (profiles/ncu_traffic.json: %s), x frames per step; not measured in this run"
@@ -509,7 +511,7 @@ def main():
         achieved = dom_fl / (dom_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
                     traffic_source=traffic_source, peak_source=peaks["source"],
-                    kernel="rsconv_kernel (detector convs 2..7, %d launches/step)" % len(dom),
+                    kernel="rsconv_kernel (detector %s, %d launches/step)" % ("convs " + dom[0][4:] + "..7", len(dom)),
                     kernel_ms_per_step=round(dom_ms, 4), algorithmic_flops_per_step=dom_fl,
                     all_convs=dict(ms_per_step=round(all_ms, 4), tflops=round(all_fl / (all_ms * 1e-3) / 1e12, 1),
                                    frac=round(all_fl / (all_ms * 1e-3) / 1e12 / peak, 4), launches_per_step=len(evs) // P),

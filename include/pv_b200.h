@@ -192,6 +192,44 @@ int pv_rsconv_check(void* handle, void* stream);
 int pv_rsconv_debug(void* handle, long long* out8);
 
 /* ------------------------------------------------------------------------------------------
+ * c12: detector conv1 (5x5 s2, RGB -> 16) + conv2 (5x5 s2, 16 -> 32), each with affine + ReLU, as ONE strip kernel
+ * (csrc/c12.cu): the conv1 activations stay in shared memory / TMEM (232 MB per 1080p frame less HBM traffic each
+ * way).  Replaces pv_conv1_fused + the first pv_rsconv launch behind face_detector_(rgb, 1),
+ * pyannote/video/face/face.py:66.  plane: RGBA u8 [B,Hp,Wp,4] (A = 0: padding), Wp % 4 == 0.
+ * w1_img (4096 B): eight blocks of 16 output channels x 16 k, 32-byte rows with the 32-byte swizzle (element (nn,k) of a
+ * tile at nn*32 + (((k>>3) ^ ((nn>>2)&1))*16) + (k&7)*2, nn counted from the tile's first block):
+ *   tile M0 = blocks [kh4, kh2, kh0], tile M1 = [kh3, kh1] with k = kw*4 + c (kw 0..3, c 0..2, c = 3 zero);
+ *   tile P  = blocks [(kh4|0), (kh2|kh3), (kh0|kh1)] with k < 8: (kw 4, c = k) of the even plane row (k 3..7 zero),
+ *             k >= 8: the same of the odd plane row.
+ * w2_img (25600 B): the rsconv weight image of a (16 -> 32, 5x5, stride 2) layer.
+ * out: bf16 [B, OH2, out_pitch, 32], OH1 = (Hp-5)/2+1, OH2 = (OH1-5)/2+1 (same for W).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct PvC12Desc {
+  const void* plane;
+  int32_t B, Hp, Wp;
+  const void* w1_img;
+  int64_t w1_bytes;
+  const void* w2_img;
+  int64_t w2_bytes;
+  const float* scale1;   /* [16] */
+  const float* shift1;
+  const float* scale2;   /* [32] */
+  const float* shift2;
+  void* out;
+  int32_t out_pitch;
+  const float* mean_host; /* 3 floats (HOST): pixel mean; input = (v - mean)/256 */
+} PvC12Desc;
+int pv_c12_create(const PvC12Desc* desc, void** out_handle);
+int pv_c12_run(void* handle, int B, void* stream);
+int pv_c12_destroy(void* handle);
+int pv_c12_info(void* handle, int* smem_bytes, int* strips, int* segs, int* seg_rows, int* oh2, int* ow2);
+int pv_c12_check(void* handle, void* stream);
+/* role timing of the last launch when the plan was created with PV_C12_DEBUG set: out16 (HOST) = cycles summed over CTAs
+ * {conv1 MMA: wait pixels, issue + slot waits (tile 1), issue + slot waits (tile 0), quads; conv2 MMA: wait A rows, wait slot, issue, rows; converter: wait raw,
+ * wait slot, work; conv1 epilogue: wait row, wait A slot, work; conv2 epilogue: wait row, work} */
+int pv_c12_debug(void* handle, long long* out16);
+
+/* ------------------------------------------------------------------------------------------
  * first-layer packing and the small layers of the embedder (csrc/layers.cu)
  * ------------------------------------------------------------------------------------------ */
 /* RGBA u8 [B,H,W,4] (A==0: pyramid padding) -> "gathered" bf16 rows for a kw x kw stride-2 first conv:

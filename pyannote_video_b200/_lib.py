@@ -97,6 +97,20 @@ class PvDetconvDesc(C.Structure):
     ]
 
 
+class PvC12Desc(C.Structure):
+    _fields_ = [
+        ("plane", C.c_void_p),
+        ("B", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32),
+        ("w1_img", C.c_void_p), ("w1_bytes", C.c_int64),
+        ("w2_img", C.c_void_p), ("w2_bytes", C.c_int64),
+        ("scale1", C.c_void_p), ("shift1", C.c_void_p),
+        ("scale2", C.c_void_p), ("shift2", C.c_void_p),
+        ("out", C.c_void_p),
+        ("out_pitch", C.c_int32),
+        ("mean_host", C.POINTER(C.c_float)),
+    ]
+
+
 _lib = None
 
 

@@ -11,12 +11,15 @@ SRGEMM_GROUP = "row"   # validated on B200 (gpurun #1): descriptors at arbitrary
 # first detector conv input:
 #   "fused"    conv1_fused.cu reads the RGBA u8 plane by TMA, normalises every pixel once into a
 #              shared-memory pixel-row buffer and lets tcgen05.mma read OVERLAPPING A rows from it
-#              (no im2col in HBM or in shared memory).  8 frames 1080p: 1.36 ms            [default]
+#              (no im2col in HBM or in shared memory).  8 frames 1080p: 1.36 ms
 #   "gathered" pack kernel writes kw*3-wide bf16 rows (16 B/pixel), generic srgemm reads them back:
 #              1.15 + 1.73 ms
 #   "pixrows"  pack kernel writes a bf16 RGBX plane (8 B/pixel), srgemm reads 8-pixel runs through an
 #              overlapping-row tensor map (row stride 16 B): slower than "gathered" (L2-bound re-reads)
-DET_CONV1 = os.environ.get("PV_DET_CONV1", "fused")
+#   "c12"      csrc/c12.cu: conv1 AND conv2 in one row-streaming strip kernel — the conv1 activations go from TMEM to
+#              shared memory in conv2's operand layout and never reach HBM (464 MB per 1080p frame less traffic)
+#              [default with DET_CONVS = "rsconv"; any other conv back-end falls back to "fused"]
+DET_CONV1 = os.environ.get("PV_DET_CONV1", "c12")    # measured (8 frames 1080p): c12 1.05 ms vs conv1_fused 0.875 + conv2 0.473 ms
 
 # detector conv layers 2..7:
 #   "rsconv"   csrc/rsconv.cu: row streaming — every input row is loaded once and multiplied against all filter rows

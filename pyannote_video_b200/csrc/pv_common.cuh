@@ -215,6 +215,18 @@ __device__ __forceinline__ void pv_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) 
         "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+// whole warp: write zeros to 32 lanes x 16 consecutive 32-bit columns (accumulator rows that are handed back cleared, so
+// that every MMA can accumulate)
+__device__ __forceinline__ void pv_tmem_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void pv_tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void pv_tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }

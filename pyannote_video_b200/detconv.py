@@ -198,3 +198,120 @@ class RsConv(DetConv):
         a, b, c, e, f = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _lib.check(_lib.lib().pv_rsconv_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(e), C.byref(f)), "pv_rsconv_info")
         return dict(n_stages=a.value, smem_bytes=b.value, strips=c.value, segs=e.value, seg_rows=f.value)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# c12: detector conv1 + conv2 in one strip kernel (csrc/c12.cu)
+# ---------------------------------------------------------------------------------------------------------------
+C12_W1_TILES = (("M0", (4, 2, 0)), ("M1", (3, 1)), ("P", ((4, None), (2, 3), (0, 1))))
+
+
+def _c12_block(w, kind, spec):
+    """one 16 x 16 block (output channel n, k) of the conv1 weight image; w float [16,3,5,5]"""
+    blk = torch.zeros(16, 16)
+    if kind in ("M0", "M1"):
+        kh = spec
+        for kw in range(4):
+            blk[:, kw * 4:kw * 4 + 3] = w[:, :, kh, kw]            # k = kw*4 + c, c = 3 stays zero
+    else:
+        for half, kh in enumerate(spec):                           # k < 8: even plane row, k >= 8: odd plane row
+            if kh is not None:
+                blk[:, half * 8:half * 8 + 3] = w[:, :, kh, 4]     # kw = 4; k 3..7 of the half stay zero (kw = 5 does not exist)
+    return blk
+
+
+def pack_c12_w1(w):
+    """conv1 weight image of csrc/c12.cu (include/pv_b200.h, PvC12Desc): tiles M0 / M1 / P, blocks of 16 output channels,
+    32-byte K-major rows with the 32-byte swizzle counted from the tile's first row."""
+    w = torch.as_tensor(w).float()
+    assert tuple(w.shape) == (16, 3, 5, 5)
+    parts = []
+    for kind, specs in C12_W1_TILES:
+        tile = torch.cat([_c12_block(w, kind, sp) for sp in specs], dim=0).reshape(-1, 2, 8)      # [nn, chunk, 8]
+        nn = torch.arange(tile.shape[0])
+        swap = ((nn >> 2) & 1).bool()
+        t = tile.clone()
+        t[swap] = tile[swap].flip(1)
+        parts.append(t.reshape(-1))
+    img = torch.cat(parts).to(torch.bfloat16).view(torch.uint8).reshape(-1)
+    assert img.numel() == 4096
+    return img
+
+
+def unpack_c12_w1(img):
+    """inverse of pack_c12_w1 with the element-address formula written out (CPU test): returns {tile: [blocks][16][16]}"""
+    v = img.view(torch.bfloat16).float().numpy()
+    out, base = {}, 0
+    for kind, specs in C12_W1_TILES:
+        nb = len(specs)
+        t = np.zeros((nb, 16, 16), np.float32)
+        for b in range(nb):
+            for n in range(16):
+                nn = b * 16 + n
+                for k in range(16):
+                    off = base + nn * 32 + (((k >> 3) ^ ((nn >> 2) & 1)) * 16) + (k & 7) * 2
+                    t[b, n, k] = v[off // 2]
+        out[kind] = t
+        base += nb * 512
+    return out
+
+
+class FusedC12:
+    """Detector conv1 (5x5 s2, RGB -> 16) + conv2 (5x5 s2, 16 -> 32), affine + ReLU each, in one launch reading the RGBA u8
+    pyramid plane (csrc/c12.cu).  out: bf16 [B, OH2, even(OW2), 32].  Same run(B) / check() protocol as DetConv."""
+
+    def __init__(self, plane, Hp, Wp, w1, scale1, shift1, w2, scale2, shift2, mean, out=None):
+        dev = plane.device
+        B = plane.shape[0]
+        assert plane.dtype == torch.uint8 and tuple(plane.shape) == (B, Hp, Wp, 4) and plane.is_contiguous()
+        self.OH1, self.OW1 = (Hp - 5) // 2 + 1, (Wp - 5) // 2 + 1
+        self.OH, self.OW = (self.OH1 - 5) // 2 + 1, (self.OW1 - 5) // 2 + 1
+        self.out_pitch = even(self.OW)
+        if out is None:
+            out = torch.zeros(B, self.OH, self.out_pitch, 32, dtype=torch.bfloat16, device=dev)
+        assert tuple(out.shape) == (B, self.OH, self.out_pitch, 32) and out.is_contiguous()
+        self.out, self.plane, self.Bmax = out, plane, B
+        self.w1_img = pack_c12_w1(w1).to(dev)
+        self.w2_img = pack_weight_image_rs(w2, 16, 32, 2).to(dev)
+        f = lambda a: torch.as_tensor(a).float().contiguous().to(dev)
+        self.scale1, self.shift1, self.scale2, self.shift2 = f(scale1), f(shift1), f(scale2), f(shift2)
+        self._mean = (C.c_float * 3)(*[float(m) for m in mean])
+        d = _lib.PvC12Desc()
+        d.plane = plane.data_ptr()
+        d.B, d.Hp, d.Wp = B, Hp, Wp
+        d.w1_img, d.w1_bytes = self.w1_img.data_ptr(), self.w1_img.numel()
+        d.w2_img, d.w2_bytes = self.w2_img.data_ptr(), self.w2_img.numel()
+        d.scale1, d.shift1 = self.scale1.data_ptr(), self.shift1.data_ptr()
+        d.scale2, d.shift2 = self.scale2.data_ptr(), self.shift2.data_ptr()
+        d.out, d.out_pitch = out.data_ptr(), self.out_pitch
+        d.mean_host = self._mean
+        h = C.c_void_p()
+        _lib.check(_lib.lib().pv_c12_create(C.byref(d), C.byref(h)), "pv_c12_create")
+        self.h = h
+        self.flops_per_image = 2 * (self.OH1 * self.OW1 * 16 * 3 * 25 + self.OH * self.OW * 32 * 16 * 25)
+
+    def info(self):
+        v = [C.c_int() for _ in range(6)]
+        _lib.check(_lib.lib().pv_c12_info(self.h, *[C.byref(x) for x in v]), "pv_c12_info")
+        return dict(zip(("smem_bytes", "strips", "segs", "seg_rows", "oh2", "ow2"), [x.value for x in v]))
+
+    def debug(self):
+        out = (C.c_longlong * 16)()
+        _lib.check(_lib.lib().pv_c12_debug(self.h, out), "pv_c12_debug")
+        names = ("c1_wait_px", "c1_issue_tile1", "c1_issue", "c1_quads", "c2_wait_a", "c2_wait_slot", "c2_issue", "c2_rows",
+                 "cv_wait_raw", "cv_wait_slot", "cv_work", "e1_wait_row", "e1_wait_a", "e1_work", "e2_wait_row", "e2_work")
+        return dict(zip(names, [int(x) for x in out]))
+
+    def run(self, B=None):
+        _lib.check(_lib.lib().pv_c12_run(self.h, int(B or self.Bmax), _lib.stream_ptr()), "pv_c12_run")
+
+    def check(self):
+        _lib.check(_lib.lib().pv_c12_check(self.h, _lib.stream_ptr()), "pv_c12_check")
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.lib().pv_c12_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

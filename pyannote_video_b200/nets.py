@@ -18,7 +18,7 @@ import torch
 from . import _lib, config
 from . import weights as W
 from .plan import ConvPlan, RowLayout, Srgemm
-from .detconv import DetConv, RsConv, even
+from .detconv import DetConv, RsConv, FusedC12, even
 from .pyrgeom import pyramid_geometry, det_cell_to_plane
 
 
@@ -297,6 +297,8 @@ class DetectorNet:
         self.planes = [self.plane]        # a second plane (enable_double_buffer) lets the next batch's pyramid be built early
         self.conv1_mode = config.DET_CONV1 if conv1_mode is None else conv1_mode
         self.conv_impl = config.DET_CONVS if conv_impl is None else conv_impl
+        if self.conv1_mode == "c12" and self.conv_impl != "rsconv":
+            self.conv1_mode = "fused"            # the conv1+conv2 strip kernel feeds the rsconv layers only
         if self.conv_impl in ("detconv", "rsconv"):
             self._init_detconv(model, device)
         else:
@@ -311,6 +313,11 @@ class DetectorNet:
             cum *= s
             self.algorithmic_flops_per_layer.append(2.0 * P / (cum * cum) * cout * cin * k * k)
         self.algorithmic_flops_per_frame = sum(self.algorithmic_flops_per_layer)
+        # the same, per launch of self.convs (conv1 + conv2 share one launch in "c12" mode)
+        names = getattr(self, "layer_names", None) or ["conv%d" % (i + 1) for i in range(len(self.convs))]
+        self.layer_names = names
+        af = list(self.algorithmic_flops_per_layer)
+        self.algorithmic_flops_per_op = ([af[0] + af[1]] + af[2:]) if names[0] == "conv1+2" else af
 
     def _init_detconv(self, model, device):
         """layers 2..7 on csrc/rsconv.cu (row streaming) or csrc/detconv.cu (2-D tiles): plain NHWC activations
@@ -322,27 +329,26 @@ class DetectorNet:
         self.convs = []
         self.flops_per_frame = 0
         self.flops_per_layer = []
-        # conv1 (5x5 s2, RGB -> 16) writes straight into the NHWC tensor through a row map
-        cout, cin, k, s = W.DET_CONVS[0]
-        OH1, OW1 = (Hp - k) // s + 1, (Wp - k) // s + 1
-        l1 = RowLayout("padded", B, OH1, even(OW1), 16, pad=0)
-        a1 = l1.alloc(device)
-        if self.conv1_mode == "fused":
+        self.layer_names = []
+        first = 1
+        if self.conv_impl == "rsconv" and self.conv1_mode == "c12":
+            # conv1 + conv2 in ONE strip kernel (csrc/c12.cu): the conv1 activations never reach HBM
             self.lg, self.xg = None, None
-            op = FusedConv1(self.plane, Hp, Wp, convs[0], a1, l1, device)
-            img1 = op.img
-        else:
-            lg = RowLayout(self.conv1_mode, B, Hp, Wp, 3, kw=5)
-            self.lg, self.xg = lg, lg.alloc(device)
-            cp = ConvPlan(lg, _t(convs[0]["w"]), s, 0, group=config.SRGEMM_GROUP)
-            sc, sh = _affine(convs[0])
-            op = Srgemm(cp, self.xg, a1, l1, sc, sh, relu=True)
-            img1 = lg.img
-        self.convs.append((op, img1))
-        self.flops_per_layer.append(2 * OH1 * OW1 * cout * cin * k * k)
-        x, h, w = a1.view(B, OH1, even(OW1), 16), OH1, OW1
+            (sc1, sh1), (sc2, sh2) = _affine(convs[0]), _affine(convs[1])
+            op = FusedC12(self.plane, Hp, Wp, _t(convs[0]["w"]), sc1, sh1, _t(convs[1]["w"]), sc2, sh2, W.PIXEL_MEAN)
+            self._c12_args = (Hp, Wp, _t(convs[0]["w"]), sc1, sh1, _t(convs[1]["w"]), sc2, sh2, W.PIXEL_MEAN)
+            self.convs.append((op, 1))
+            self.layer_names.append("conv1+2")
+            for i in range(2):
+                cout, cin, k, s = W.DET_CONVS[i]
+                oh, ow = (op.OH1, op.OW1) if i == 0 else (op.OH, op.OW)
+                self.flops_per_layer.append(2 * oh * ow * cout * cin * k * k)
+            x, h, w = op.out, op.OH, op.OW
+            first = 2
+        if first == 1:
+            x, h, w = self._init_conv1(model, device, B, Hp, Wp)
         n = len(convs)
-        for i in range(1, n):
+        for i in range(first, n):
             cout, cin, k, s = W.DET_CONVS[i]
             c = convs[i]
             last = i == n - 1
@@ -365,7 +371,31 @@ class DetectorNet:
                 self.flops_per_layer.append(2 * op.OH * op.OW * cout * cin * k * k)
                 x, h, w = op.out, op.OH, op.OW
             self.convs.append((op, 1))
+            self.layer_names.append("conv%d" % (i + 1))
         self.flops_per_frame = sum(self.flops_per_layer)
+
+    def _init_conv1(self, model, device, B, Hp, Wp):
+        """conv1 (5x5 s2, RGB -> 16) as its own launch: writes straight into the NHWC tensor through a row map"""
+        convs = model["convs"]
+        cout, cin, k, s = W.DET_CONVS[0]
+        OH1, OW1 = (Hp - k) // s + 1, (Wp - k) // s + 1
+        l1 = RowLayout("padded", B, OH1, even(OW1), 16, pad=0)
+        a1 = l1.alloc(device)
+        if self.conv1_mode == "fused":
+            self.lg, self.xg = None, None
+            op = FusedConv1(self.plane, Hp, Wp, convs[0], a1, l1, device)
+            img1 = op.img
+        else:
+            lg = RowLayout(self.conv1_mode, B, Hp, Wp, 3, kw=5)
+            self.lg, self.xg = lg, lg.alloc(device)
+            cp = ConvPlan(lg, _t(convs[0]["w"]), s, 0, group=config.SRGEMM_GROUP)
+            sc, sh = _affine(convs[0])
+            op = Srgemm(cp, self.xg, a1, l1, sc, sh, relu=True)
+            img1 = lg.img
+        self.convs.append((op, img1))
+        self.flops_per_layer.append(2 * OH1 * OW1 * cout * cin * k * k)
+        self.layer_names.append("conv1")
+        return a1.view(B, OH1, even(OW1), 16), OH1, OW1
 
     def _init_srgemm(self, model, device, group):
         B, geo = self.B, self.geo
@@ -466,6 +496,14 @@ class DetectorNet:
         op = self.convs[0][0]
         if isinstance(op, FusedConv1):
             op.plane = self.plane
+        elif isinstance(op, FusedC12):
+            # the plane pointer lives in the kernel's tensor map: one bound op per plane, same output tensor
+            if not hasattr(self, "_c12_ops"):
+                self._c12_ops = {0: op}
+            if slot not in self._c12_ops:
+                Hp, Wp, w1, sc1, sh1, w2, sc2, sh2, mean = self._c12_args
+                self._c12_ops[slot] = FusedC12(self.plane, Hp, Wp, w1, sc1, sh1, w2, sc2, sh2, mean, out=op.out)
+            self.convs[0] = (self._c12_ops[slot], 1)
 
     def build_plane(self, frames, M):
         """frames: uint8 [M,H,W,3] device tensor -> tiled pyramid plane (RGBA u8)."""
@@ -502,7 +540,7 @@ class DetectorNet:
         L = _lib.lib()
         st = _lib.stream_ptr()
         geo = self.geo
-        if self.conv1_mode == "fused":
+        if self.conv1_mode in ("fused", "c12"):
             pass   # conv1 reads the plane in place
         elif self.conv1_mode == "pixrows":
             # NB: the pixel buffer is [2, Bcap, Hq, W]; a partial batch writes the first M images of

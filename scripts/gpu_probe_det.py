@@ -32,7 +32,7 @@ def main():
     if args.once:
         torch.cuda.synchronize()
         return
-    names = ["conv%d" % (i + 1) for i in range(len(det.convs))]
+    names = list(det.layer_names)
     acc = {n: 0.0 for n in names}
     acc["pyramid"] = 0.0
     acc["forward_scores"] = 0.0
@@ -66,6 +66,8 @@ def main():
         from pyannote_video_b200 import _lib
         dbg = {}
         for (op, _), n in zip(det.convs[1:], names[1:]):
+            if not hasattr(op, "_create") or op._create != "pv_rsconv_create":
+                continue
             a = (C.c_longlong * 8)()
             _lib.check(_lib.lib().pv_rsconv_debug(op.h, a), "pv_rsconv_debug")
             rows = max(1, a[3])
@@ -83,6 +85,12 @@ def main():
         out["c1_debug_cycles_per_tile"] = dict(tiles=a[3], mma_wait_acc=round(a[0] / t), mma_wait_px=round(a[1] / t), mma_issue=round(a[2] / t),
                                                conv_wait_raw=round(a[4] / t), conv_wait_slot=round(a[5] / t), conv_work=round(a[6] / t),
                                                epi_wait=round(a[7] / t))
+    if os.environ.get("PV_C12_DEBUG") and det.conv1_mode == "c12":
+        op = det.convs[0][0]
+        d = op.debug()
+        q, r = max(1, d["c1_quads"]), max(1, d["c2_rows"])
+        out["c12_debug_cycles_per_quad"] = {k: round(v / q) for k, v in d.items() if k not in ("c1_quads", "c2_rows")}
+        out["c12_debug_cycles_per_quad"].update(quads=d["c1_quads"], conv2_rows=d["c2_rows"], info=op.info())
     out["mode"] = det.conv1_mode
     out["frames"] = B
     out["unit"] = "us"

@@ -53,6 +53,7 @@ def test_embed_net_matches_oracle(cuda, impl, M, cap):
 
 
 @pytest.mark.parametrize("upsample,conv1_mode,conv_impl", [
+    (1, "c12", "rsconv"), (0, "c12", "rsconv"),
     (1, "fused", "rsconv"), (0, "fused", "rsconv"), (1, "gathered", "rsconv"),
     (1, "fused", "detconv"), (0, "fused", "detconv"),
     (0, "gathered", "srgemm"), (1, "gathered", "srgemm"), (1, "pixrows", "srgemm"), (0, "pixrows", "srgemm"),
