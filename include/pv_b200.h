@@ -230,6 +230,41 @@ int pv_c12_check(void* handle, void* stream);
 int pv_c12_debug(void* handle, long long* out16);
 
 /* ------------------------------------------------------------------------------------------
+ * HOG frontal face detector (csrc/hog.cu): dlib.get_frontal_face_detector()(rgb, 1), the detector the reference
+ * really calls (pyannote/video/face/face.py:54,66).  Input = the tiled pyramid plane of pv_resize_bilinear /
+ * pv_pyramid_tail; per usable level (both sides >= 80 px) a table entry.  pv_hog_features writes the 31-channel
+ * Felzenszwalb features (cell 8) of every interior cell as bf16 x 32 channels into a feature plane
+ * [B, FH, fpitch, 32] at (fy0 + y, fx0 + x) (tiles at least 10 zero cells apart; the plane is zeroed once by the
+ * caller).  The sliding-window scores are ONE pv_rsconv launch over that plane (instance c_in 32, n_out 16, 10x10,
+ * stride 1, fp32 out; filters = output channels).  pv_hog_decode thresholds, sorts (score desc, level, filter, row,
+ * col) and applies greedy NMS (dlib test_box_overlap); boxes through fhog_to_image, pyramid_down<6>::rect_up and,
+ * when `upsampled`, pyramid_down<2>::rect_down.  counts < 0 reports a candidate overflow.
+ * ------------------------------------------------------------------------------------------ */
+#define PV_HOG_MAX_LEVELS 24
+typedef struct PvHogLevel {
+  int32_t x0, y0, w, h;     /* level rectangle in the plane (pixels)                         */
+  int32_t cx, cy;           /* cells: (int)(w / 8.f + 0.5f), same for h                       */
+  int32_t fx0, fy0;         /* origin of the level's (cy-2) x (cx-2) feature tile             */
+  int32_t px_off, cell_off, feat_off;   /* prefix sums of w*h, cx*cy, (cx-2)*(cy-2)           */
+} PvHogLevel;
+typedef struct PvHogGeo {
+  int32_t n_levels, Hp, Wp;
+  int32_t total_px, total_cells, total_feat;
+  int32_t FH, FW, fpitch;
+  PvHogLevel lv[PV_HOG_MAX_LEVELS];
+} PvHogGeo;
+/* uv18: device float[18] = cos(o*pi/9) (o < 9) then sin(o*pi/9); ori/mag: plane-sized scratch (u8 / f32 per pixel);
+ * hist f32 [B, total_cells, 18]; nrm f32 [B, total_cells] */
+int pv_hog_features(const void* plane_rgba, int B, const PvHogGeo* geo, const float* uv18, void* ori_u8, void* mag_f32,
+                    float* hist, float* nrm, void* feat_bf16, void* stream);
+/* scores: fp32 [B, OHs, opitch, 16] (the rsconv output; OHs = FH + 1); thr_dev: device float[D]; D <= 8 filters;
+ * cand_*: [B, cap]; out_boxes int32 [B, max_det, 4] (l,t,r,b), out_scores f32, out_which int32 (filter index) */
+int pv_hog_decode(const float* scores, int B, int OHs, int opitch, const PvHogGeo* geo, const float* thr_dev, int D,
+                  int upsampled, double iou_thresh, double covered_thresh, int cap, int max_det, int* counts,
+                  float* cand_score, int* cand_code, int* out_boxes, float* out_scores, int* out_which, int* out_counts,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * first-layer packing and the small layers of the embedder (csrc/layers.cu)
  * ------------------------------------------------------------------------------------------ */
 /* RGBA u8 [B,H,W,4] (A==0: pyramid padding) -> "gathered" bf16 rows for a kw x kw stride-2 first conv:

@@ -275,7 +275,7 @@ extern "C" int pvc_extract_chips(const uint8_t* rgb, int H, int W, const int64_t
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 typedef std::complex<double> cd;
-constexpr int FS = 64, NCH = 31, NPIX = FS * FS;
+constexpr int FS = 64, NFH = 31, NCH = 32, NPIX = FS * FS;   // 31 FHOG planes + the intensity plane
 constexpr int NSC = 32, SW = 23, SCELLS = 6, SOUT = 4, SF = 31 * SOUT * SOUT;
 constexpr double kPi = 3.14159265358979323846;
 
@@ -362,7 +362,7 @@ static void fhog_cell1(const uint8_t* chip, float* out) {
     const int y0 = 1 + dy + y, x0 = 1 + dx + x;
     return ((P[y0 * pn + x0] + P[y0 * pn + x0 + 1]) + P[(y0 + 1) * pn + x0]) + P[(y0 + 1) * pn + x0 + 1];
   };
-  memset(out, 0, sizeof(float) * NCH * NPIX);
+  memset(out, 0, sizeof(float) * NFH * NPIX);
   const int dys[4] = {-1, -1, 0, 0}, dxs[4] = {-1, 0, -1, 0};
   for (int y = 1; y < n - 1; ++y)
     for (int x = 1; x < n - 1; ++x) {
@@ -472,7 +472,7 @@ static void fft2(cd* x, bool inverse) {
 
 struct Track {
   double pos[4];
-  std::vector<cd> A;      // [31][4096]
+  std::vector<cd> A;      // [32][4096]
   std::vector<double> B;  // [4096]
   std::vector<cd> As;     // [496][32]
   std::vector<double> Bs; // [32]
@@ -494,6 +494,11 @@ static void features(const uint8_t* rgb, int H, int W, const double* rect, std::
   chip_sample(rgb, H, W, rl, rt, sx, sy, FS, chip.data());
   std::vector<float> fh((size_t)NCH * NPIX);
   fhog_cell1(chip.data(), fh.data());
+  // 32nd plane: chip intensity (r + g + b) / 3 (unsigned integer division, dlib assign_pixel) / 255
+  for (int i = 0; i < NPIX; ++i) {
+    const unsigned g = ((unsigned)chip[3 * i] + chip[3 * i + 1] + chip[3 * i + 2]) / 3u;
+    fh[(size_t)NFH * NPIX + i] = (float)g / 255.0f;
+  }
   F.resize((size_t)NCH * NPIX);
   for (int ch = 0; ch < NCH; ++ch) {
     for (int y = 0; y < FS; ++y)
@@ -602,10 +607,16 @@ static double update_one(Bank& bk, Track& tk, const uint8_t* rgb, int H, int W) 
   double ppx = px, ppy = py;
   auto Rr = [&](int y, int x) { return R[y * FS + x].real(); };
   if (px > 0 && px < FS - 1 && py > 0 && py < FS - 1) {
-    const double dxx = Rr(py, px - 1) - 2 * Rr(py, px) + Rr(py, px + 1);
-    const double dyy = Rr(py - 1, px) - 2 * Rr(py, px) + Rr(py + 1, px);
-    if (dxx != 0) ppx += 0.5 * (Rr(py, px - 1) - Rr(py, px + 1)) / dxx;
-    if (dyy != 0) ppy += 0.5 * (Rr(py - 1, px) - Rr(py + 1, px)) / dyy;
+    // dlib max_point_interpolated: Newton step of the 3x3 finite-difference quadratic (cross term included), clamped to +-1
+    const double dx = 0.5 * (Rr(py, px + 1) - Rr(py, px - 1)), dy = 0.5 * (Rr(py + 1, px) - Rr(py - 1, px));
+    const double dxx = Rr(py, px + 1) - 2 * Rr(py, px) + Rr(py, px - 1);
+    const double dyy = Rr(py + 1, px) - 2 * Rr(py, px) + Rr(py - 1, px);
+    const double dxy = 0.25 * ((Rr(py + 1, px + 1) + Rr(py - 1, px - 1)) - (Rr(py + 1, px - 1) + Rr(py - 1, px + 1)));
+    const double det = dxx * dyy - dxy * dxy;
+    if (det != 0) {
+      ppx += std::min(1.0, std::max(-1.0, -(dyy * dx - dxy * dy) / det));
+      ppy += std::min(1.0, std::max(-1.0, -(dxx * dy - dxy * dx) / det));
+    }
   }
   double sum = 0, n = 0;
   for (int y = 0; y < FS; ++y)

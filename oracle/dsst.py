@@ -5,10 +5,14 @@ it: `start_track(frame, drectangle)`, `update(frame) -> PSR`, `get_position()`
 (pyannote/video/tracking.py:203,231,250-251), following dlib 19.12's correlation_tracker.h as
 recalled in SURVEY.md App. A.5 (dlib absent: parity unpinned).
 
-Restated: translation filter over the 31-channel FHOG (cell size 1) of a 64x64 chip cut from the
-position rectangle grown by 1.4, cosine window, per-channel numerators A_i = conj(G) F_i and shared
-denominator B = sum |F_i|^2, response = ifft2(sum F_i conj(A_i) / (B + 0.001)), sub-pixel peak, PSR
-over everything outside the 8x8 peak window, running update with nu = 0.025.
+Restated: translation filter over 32 feature planes of a 64x64 chip cut from the position rectangle grown by
+1.4 — the 31-channel FHOG (cell size 1) plus, as the 32nd plane, the chip's intensity / 255 (dlib's make_chip:
+"the HOG features ignore the overall brightness ... so we add it as the 32nd feature") — cosine window,
+per-plane numerators A_i = conj(G) F_i and shared denominator B = sum |F_i|^2, response =
+ifft2(sum F_i conj(A_i) / (B + 0.001)), sub-pixel peak as in dlib's max_point_interpolated (Newton step of the
+3x3 finite-difference quadratic INCLUDING the cross term, clamped to +-1 pixel), PSR over everything outside the
+8x8 peak window, running update with nu = 0.025.  Still not restated: extract_image_chip's pyramid_down
+pre-shrink of chips whose source region is more than twice the chip (DESIGN.md audit list).
 Also restated: the 1-D scale filter of `update` — 32 scales alpha^(k-16) (alpha = 1.020) of the
 position rectangle, each resampled to 23x23, FHOG with cell size 4 (4x4 cells x 31 = 496 features),
 Hann window over scales, per-feature numerators As_j = conj(Gs) Fs_j and denominator Bs = sum |Fs_j|^2
@@ -20,6 +24,7 @@ import numpy as np
 f32 = np.float32
 
 FS = 64
+NCH = 32          # 31 FHOG planes + the intensity plane
 PADDING = 1.4
 LAMBDA = 0.001
 NU = 0.025
@@ -111,6 +116,30 @@ def fhog_cell1(chip):
     for k in range(4):
         out[27 + k] = np.where(valid, f32(0.2357) * h[k], 0)
     return out
+
+
+def gray_plane(chip):
+    """dlib assign_pixel rgb -> grayscale: (r + g + b) / 3 in unsigned integers, then / 255 (float32)"""
+    g = (chip.astype(np.uint32).sum(axis=2) // 3).astype(f32)
+    return (g / f32(255)).astype(f32)
+
+
+def interpolated_peak(R):
+    """dlib max_point_interpolated: argmax (first in raster order); inside the border a Newton step of the quadratic
+    through the 3x3 neighbourhood (central differences, cross term included), each component clamped to [-1, 1]"""
+    py, px = np.unravel_index(int(np.argmax(R)), R.shape)
+    ppx, ppy = float(px), float(py)
+    if 0 < px < R.shape[1] - 1 and 0 < py < R.shape[0] - 1:
+        dx = 0.5 * (R[py, px + 1] - R[py, px - 1])
+        dy = 0.5 * (R[py + 1, px] - R[py - 1, px])
+        dxx = R[py, px + 1] - 2 * R[py, px] + R[py, px - 1]
+        dyy = R[py + 1, px] - 2 * R[py, px] + R[py - 1, px]
+        dxy = 0.25 * ((R[py + 1, px + 1] + R[py - 1, px - 1]) - (R[py + 1, px - 1] + R[py - 1, px + 1]))
+        det = dxx * dyy - dxy * dxy
+        if det != 0:
+            ppx += float(np.clip(-(dyy * dx - dxy * dy) / det, -1.0, 1.0))
+            ppy += float(np.clip(-(dxx * dy - dxy * dx) / det, -1.0, 1.0))
+    return int(py), int(px), ppx, ppy
 
 
 def hann2d(n=FS):
@@ -258,7 +287,8 @@ class CorrelationTracker(object):
 
     def _features(self, rgb, rect):
         chip, tf = extract_chip(rgb, rect)
-        F = fhog_cell1(chip) * hann2d()[None]
+        planes = np.concatenate([fhog_cell1(chip), gray_plane(chip)[None]], axis=0)
+        F = (planes * hann2d()[None]).astype(f32)
         return np.fft.fft2(F.astype(np.float64)), tf
 
     def start_track(self, rgb, rect):
@@ -299,15 +329,7 @@ class CorrelationTracker(object):
         guess = self.position
         F, (rl, rt, sx, sy) = self._features(rgb, guess)
         R = np.real(np.fft.ifft2((F * np.conj(self.A)).sum(0) / (self.B + LAMBDA)))
-        py, px = np.unravel_index(int(np.argmax(R)), R.shape)
-        ppx, ppy = float(px), float(py)
-        if 0 < px < FS - 1 and 0 < py < FS - 1:
-            dxx = R[py, px - 1] - 2 * R[py, px] + R[py, px + 1]
-            dyy = R[py - 1, px] - 2 * R[py, px] + R[py + 1, px]
-            if dxx != 0:
-                ppx += 0.5 * (R[py, px - 1] - R[py, px + 1]) / dxx
-            if dyy != 0:
-                ppy += 0.5 * (R[py - 1, px] - R[py + 1, px]) / dyy
+        py, px, ppx, ppy = interpolated_peak(R)
         mask = np.ones_like(R, bool)
         mask[max(py - 4, 0):py + 4, max(px - 4, 0):px + 4] = False
         side = R[mask]

@@ -111,6 +111,18 @@ class PvC12Desc(C.Structure):
     ]
 
 
+PV_HOG_MAX_LEVELS = 24
+
+
+class PvHogLevel(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("x0", "y0", "w", "h", "cx", "cy", "fx0", "fy0", "px_off", "cell_off", "feat_off")]
+
+
+class PvHogGeo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_levels", "Hp", "Wp", "total_px", "total_cells", "total_feat", "FH", "FW", "fpitch")] \
+        + [("lv", PvHogLevel * PV_HOG_MAX_LEVELS)]
+
+
 _lib = None
 
 

@@ -113,22 +113,23 @@ struct RsGeo {
   static constexpr int kPadY = S == 1 ? KH / 2 : 0, kPadX = S == 1 ? KW / 2 : 0;
   static constexpr int kNQ0 = (KH + S - 1) / S;            // filter rows of parity class 0 (kh = 0, S, 2S, ...)
   static constexpr int kNQ1 = S == 2 ? KH / 2 : 0;          // parity class 1 (kh = 1, 3, ...)
-  // layers with <= 32 output channels run two CTAs per SM (each half of TMEM and of shared memory): their rows
-  // carry few MMAs, so a second issuing thread hides the per-row hand-offs of the first
-  static constexpr int kCtas = NC <= 32 ? 2 : 1;
-  static constexpr int kTmemBudget = 512 / kCtas;
-  static constexpr int kSlots = (kTmemBudget / NC) < kMaxSlots ? (kTmemBudget / NC) : kMaxSlots;
-  static constexpr uint32_t kTmemCols = kSlots * NC > 256 ? 512u : (kSlots * NC > 128 ? 256u : 128u);
   static constexpr int kTile0Bytes = kNQ0 * NC * 32;        // one (kw, chunk) weight tile of class 0
   static constexpr int kTile1Bytes = kNQ1 * NC * 32;
   static constexpr int kQ1Base = KW * kKch * kTile0Bytes;
   static constexpr int kWBytes = KW * kKch * (kTile0Bytes + kTile1Bytes);
+  // layers with <= 32 output channels run two CTAs per SM (each half of TMEM and of shared memory): their rows
+  // carry few MMAs, so a second issuing thread hides the per-row hand-offs of the first — unless the resident weights
+  // (the HOG detector's 10 x 10 x 32 filters: 100 KB) leave no room for two input rings
+  static constexpr int kCtas = (NC <= 32 && kWBytes <= 64 * 1024) ? 2 : 1;
+  static constexpr int kTmemBudget = 512 / kCtas;
+  static constexpr int kSlots = (kTmemBudget / NC) < kMaxSlots ? (kTmemBudget / NC) : kMaxSlots;
+  static constexpr uint32_t kTmemCols = kSlots * NC > 256 ? 512u : (kSlots * NC > 128 ? 256u : 128u);
 };
 
 // C: channels per input pixel in memory (16/32/48), NC: padded output channels, KH x KW filter, S stride
 // (1: pad = K/2 on both axes, 2: pad 0), F32: fp32 output rows (last layer)
 template <int C, int NC, int KH, int KW, int S, bool F32>
-__global__ void __launch_bounds__(kThreads, (NC <= 32 ? 2 : 1)) rsconv_kernel(const __grid_constant__ RsParams p) {
+__global__ void __launch_bounds__(kThreads, (RsGeo<C, NC, KH, KW, S>::kCtas)) rsconv_kernel(const __grid_constant__ RsParams p) {
   using G = RsGeo<C, NC, KH, KW, S>;
   constexpr int NSLOT = G::kSlots;
   static_assert(NC % 16 == 0 && NC >= 16 && NC <= 64, "NC");
@@ -473,6 +474,7 @@ constexpr RsInstance kRsInstances[] = {
     {32, 32, 3, 3, 1, 0},   // embedder level 4 (35 x 35, faces side by side)
     {32, 64, 3, 3, 2, 0},   // embedder level 3 entry (stride 2)
     {64, 64, 3, 3, 1, 0},   // embedder level 3 (17 x 17)
+    {32, 16, 10, 10, 1, 1}, // HOG detector: up to 16 linear filters of 10 x 10 cells x 31(+1) features, fp32 scores
 };
 constexpr int kNumRsInstances = sizeof(kRsInstances) / sizeof(kRsInstances[0]);
 
@@ -530,7 +532,8 @@ extern "C" int pv_rsconv_create(const PvDetconvDesc* d, void** out_handle) {
     case 4: rs_geometry<48, 16, 9, 1, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
     case 5: rs_geometry<32, 32, 3, 3, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
     case 6: rs_geometry<32, 64, 3, 3, 2>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
-    default: rs_geometry<64, 64, 3, 3, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
+    case 7: rs_geometry<64, 64, 3, 3, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
+    default: rs_geometry<32, 16, 10, 10, 1>(&aw, &rowel0, &rowel1, &stage_bytes, &w_bytes, &ctas); break;
   }
   PV_REQUIRE(d->w_bytes == (int64_t)w_bytes, "pv_rsconv_create: weight image is %lld bytes, expected %d", (long long)d->w_bytes, w_bytes);
   const size_t fixed = (2 * kMaxStages + 2 * kMaxSlots + 1) * sizeof(uint64_t) + 2 * in.N * sizeof(float) + 64;
@@ -656,7 +659,8 @@ extern "C" int pv_rsconv_run(void* handle, int B, void* stream) {
     case 4: e = rs_launch<48, 16, 9, 1, 1, true>(plan, p, grid, st); break;
     case 5: e = rs_launch<32, 32, 3, 3, 1, false>(plan, p, grid, st); break;
     case 6: e = rs_launch<32, 64, 3, 3, 2, false>(plan, p, grid, st); break;
-    default: e = rs_launch<64, 64, 3, 3, 1, false>(plan, p, grid, st); break;
+    case 7: e = rs_launch<64, 64, 3, 3, 1, false>(plan, p, grid, st); break;
+    default: e = rs_launch<32, 16, 10, 10, 1, true>(plan, p, grid, st); break;
   }
   g_pv_launches.fetch_add(1);
   PV_CUDA_CHECK(e);

@@ -18,7 +18,7 @@ namespace {
 
 constexpr int FS = 64;
 constexpr int NPIX = FS * FS;
-constexpr int NCH = 31;
+constexpr int NCH = 32;            // 31 FHOG planes + the chip intensity / 255 (dlib make_chip's 32nd feature)
 constexpr int kThreads = 512;
 
 struct TrackerTables {
@@ -123,6 +123,7 @@ struct Smem {
   float* red;      // [64]
   int* redi;       // [32]
   uint8_t* ori;    // [4096]      snapped orientation 0..17
+  uint8_t* gray;   // [4096]      chip intensity (r + g + b) / 3
   uint8_t* chip;   // [4096 * 3]  aliases `plane`
 };
 
@@ -136,10 +137,11 @@ __device__ Smem carve(uint8_t* base) {
   s.red = s.bsum + NPIX;
   s.redi = reinterpret_cast<int*>(s.red + 64);
   s.ori = reinterpret_cast<uint8_t*>(s.redi + 32);
+  s.gray = s.ori + NPIX;
   s.chip = reinterpret_cast<uint8_t*>(s.plane);
   return s;
 }
-constexpr size_t kSmemBytes = (size_t)FS * PS * 8 + 3 * NPIX * 4 + (NI * NI + 3) * 4 + 64 * 4 + 32 * 4 + NPIX;
+constexpr size_t kSmemBytes = (size_t)FS * PS * 8 + 3 * NPIX * 4 + (NI * NI + 3) * 4 + 64 * 4 + 32 * 4 + 2 * NPIX;
 static_assert((size_t)NPIX * 3 <= (size_t)FS * PS * 8, "chip must fit into the work plane");
 static_assert(2 * (kSmemBytes + 2048) <= 227 * 1024, "two CTAs per SM");
 
@@ -201,6 +203,7 @@ __device__ void features_prepare(const BankParams& p, const TrackerTables& tb, c
     }
     s.mag[i] = m;
     s.ori[i] = (uint8_t)bo;
+    s.gray[i] = (uint8_t)(((uint32_t)s.chip[3 * i] + s.chip[3 * i + 1] + s.chip[3 * i + 2]) / 3u);   // dlib assign_pixel rgb -> gray
   }
   __syncthreads();
   // inverse norm of every 2x2 block of squared magnitudes, once per update (it was recomputed — 4 loads, a square root
@@ -241,10 +244,12 @@ __device__ __forceinline__ float feature_value(const Smem& s, const TrackerTable
   float v;
   if (ch < 18) v = (o == ch) ? s.osum[i] : 0.f;
   else if (ch < 27) v = ((o >= 9 ? o - 9 : o) == ch - 18) ? s.osum[i] : 0.f;
-  else {
+  else if (ch < 31) {
     const int k = ch - 27;
     const float nk = inv_block(s, y - 1 + (k >> 1), x - 1 + (k & 1));
     v = __fmul_rn(0.2357f, fminf(__fmul_rn(s.mag[i], nk), 0.2f));
+  } else {
+    v = __fdiv_rn(u8f(s.gray[i]), 255.0f);          // the 32nd feature: overall brightness
   }
   return __fmul_rn(v, __fmul_rn(tb.hann[y], tb.hann[x]));
 }
@@ -486,10 +491,16 @@ __global__ void __launch_bounds__(kThreads, 2) tracker_kernel(BankParams p, cons
     double ppx = px, ppy = py;
     if (px > 0 && px < FS - 1 && py > 0 && py < FS - 1) {
       const float2* e = s.plane + py * PS + px;
+      // dlib max_point_interpolated: Newton step of the 3x3 finite-difference quadratic (cross term included), clamped to +-1
       const double c = e->x, xl = e[-1].x, xr = e[1].x, yu = e[-PS].x, yd = e[PS].x;
-      const double dxx = xl - 2 * c + xr, dyy = yu - 2 * c + yd;
-      if (dxx != 0) ppx += 0.5 * (xl - xr) / dxx;
-      if (dyy != 0) ppy += 0.5 * (yu - yd) / dyy;
+      const double dx = 0.5 * (xr - xl), dy = 0.5 * (yd - yu);
+      const double dxx = xr - 2 * c + xl, dyy = yd - 2 * c + yu;
+      const double dxy = 0.25 * (((double)e[PS + 1].x + (double)e[-PS - 1].x) - ((double)e[PS - 1].x + (double)e[-PS + 1].x));
+      const double det = dxx * dyy - dxy * dxy;
+      if (det != 0) {
+        ppx += fmin(1.0, fmax(-1.0, -(dyy * dx - dxy * dy) / det));
+        ppy += fmin(1.0, fmax(-1.0, -(dxx * dy - dxy * dx) / det));
+      }
     }
     const double ix = (double)tf[0] + ppx * (double)tf[2], iy = (double)tf[1] + ppy * (double)tf[3];
     const double cx = 0.5 * ((double)rect[0] + (double)rect[2]), cy = 0.5 * ((double)rect[1] + (double)rect[3]);

@@ -15,7 +15,8 @@ from . import _lib
 INSTANCES = {  # (c_in, n_out, kh, kw, stride, out_f32)
     (16, 32, 5, 5, 2, 0), (32, 32, 5, 5, 2, 0), (32, 48, 5, 5, 1, 0), (48, 48, 5, 5, 1, 0), (48, 16, 9, 1, 1, 1)}
 # rsconv additionally serves the embedder's 3x3 layers of levels 4 and 3 (faces packed side by side in an image row)
-INSTANCES_RS = INSTANCES | {(32, 32, 3, 3, 1, 0), (32, 64, 3, 3, 2, 0), (64, 64, 3, 3, 1, 0)}
+# ... and the HOG detector's sliding-window filters (10 x 10 cells x 32 features, filters as output channels)
+INSTANCES_RS = INSTANCES | {(32, 32, 3, 3, 1, 0), (32, 64, 3, 3, 2, 0), (64, 64, 3, 3, 1, 0), (32, 16, 10, 10, 1, 1)}
 
 
 def even(n):

@@ -49,10 +49,12 @@ class Face(object):
     embedding : str or dict, optional
         Path to (or in-memory) face embedding model (`.npz` container or dlib `.dat`).
     detector : str or dict
-        CNN (MMOD) detector model (`.npz`, dlib `mmod_human_face_detector.dat`, or an in-memory dict).
-        dlib compiles its HOG detector's weights into the library (`face/face.py:54`); nothing equivalent
-        ships here, so a detector model must be named.  `"synthetic"` selects the seeded random-weight
-        detector used by the tests and the benchmark (it does not find faces).
+        CNN (MMOD) detector model (`.npz`, dlib `mmod_human_face_detector.dat`, or an in-memory dict), or a HOG
+        detector model (dict / `.npz` of kind "hog_detector": filters [D,31,10,10] + thresholds — the detector
+        family the reference itself uses, `face/face.py:54`).  dlib compiles its HOG detector's trained weights
+        into the library; nothing equivalent ships here, so a detector model must be named.  `"synthetic"` /
+        `"synthetic-hog"` select the seeded random-weight CNN / HOG detectors used by the tests and the benchmark
+        (they do not find faces).
     upsample : int
         Number of 2x upsamplings before detection (0 or 1); the reference calls `face_detector_(rgb, 1)`.
     """
@@ -77,7 +79,14 @@ class Face(object):
             detector = os.environ.get("PYANNOTE_FACE_DETECTOR") or None
         if isinstance(detector, str) and detector == "synthetic":
             detector = W.make_detector()
-        self._detector_model = _load(detector, "mmod_detector")
+        if isinstance(detector, str) and detector == "synthetic-hog":
+            detector = W.make_hog_detector()
+        if isinstance(detector, str) and detector.endswith(".npz"):
+            detector = W.load_model(detector)               # either detector family
+        if isinstance(detector, dict) and detector.get("kind") == "hog_detector":
+            self._detector_model = detector
+        else:
+            self._detector_model = _load(detector, "mmod_detector")
         self._detectors = {}
 
         with torch.cuda.device(self.device):
@@ -102,7 +111,11 @@ class Face(object):
                 "PYANNOTE_FACE_DETECTOR), or detector='synthetic' for the seeded random-weight detector of the tests.")
         if key not in self._detectors:
             with torch.cuda.device(self.device):
-                self._detectors[key] = DetectorNet(self._detector_model, H, Wd, self.upsample, self.max_frames, self.device)
+                if self._detector_model.get("kind") == "hog_detector":
+                    from .hog import HogDetectorNet
+                    self._detectors[key] = HogDetectorNet(self._detector_model, H, Wd, self.upsample, self.max_frames, self.device)
+                else:
+                    self._detectors[key] = DetectorNet(self._detector_model, H, Wd, self.upsample, self.max_frames, self.device)
         return self._detectors[key]
 
     def _to_device_frames(self, frames):

@@ -458,8 +458,9 @@ class DetectorNet:
             if not last:
                 lcur, cur = lo, o
 
-    def _init_tail(self, model, device):
-        B, geo = self.B, self.geo
+    def _init_pyramid(self):
+        """tables of build_plane (shared with hog.HogDetectorNet, which scans the same tiled pyramid plane)"""
+        geo = self.geo
         # pyramid: big levels one launch each, the small tail (<= TAIL_PIXELS per level) in one launch
         f32 = np.float32
         tail_from = next((i for i, (w, h) in enumerate(geo.sizes) if i >= 1 and w * h <= self.TAIL_PIXELS), geo.n_levels)
@@ -472,6 +473,10 @@ class DetectorNet:
                 (pw, ph), (w, h) = geo.sizes[lv - 1], geo.sizes[lv]
                 sc.append((f32(pw - 1) / f32(max(w - 1, 1)), f32(ph - 1) / f32(max(h - 1, 1))))
             self._tail_scales = np.asarray(sc, np.float32).reshape(-1, 2).copy()
+
+    def _init_tail(self, model, device):
+        B, geo = self.B, self.geo
+        self._init_pyramid()
         rects, fxy = geo.level_table()
         self.level_rects = _t(rects).to(device)
         self.level_fxy = _t(fxy).to(device)

@@ -211,3 +211,25 @@ def load_model(path, kind=None):
     if kind is not None and model.get("kind") != kind:
         raise RuntimeError("model file %s holds a '%s', expected '%s'" % (path, model.get("kind"), kind))
     return model
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# HOG frontal detector (dlib.get_frontal_face_detector, pyannote/video/face/face.py:54).  dlib compiles its five
+# trained filters into the library as a base64 blob — not obtainable here — so the tests use seeded random filters.
+# ---------------------------------------------------------------------------------------------------------------
+HOG_CELL = 8
+HOG_FILTER = 10          # cells: 80 x 80 detection window, padding 1  [MEMORY]
+HOG_NMS_IOU = 0.5        # [MEMORY] test_box_overlap of the serialised detector
+HOG_NMS_COVERED = 1.0
+
+
+def make_hog_detector(seed=5, n_filters=5, threshold=None):
+    """seeded random HOG detector: {"kind": "hog_detector", "filters": f32 [D,31,10,10], "thresholds": f32 [D]}.
+    The default thresholds are set so that a few windows per 1080p frame fire on the synthetic test frames."""
+    rng = np.random.default_rng(seed)
+    filt = (rng.standard_normal((n_filters, 31, HOG_FILTER, HOG_FILTER)) * 0.05).astype(np.float32)
+    # round the filters to bf16: the CUDA path multiplies bf16 operands (fp32 accumulate), the oracle then sees the same weights
+    import torch
+    filt = torch.from_numpy(filt).to(torch.bfloat16).float().numpy()
+    thr = np.full(n_filters, 2.3 if threshold is None else float(threshold), np.float32)
+    return {"kind": "hog_detector", "filters": filt, "thresholds": thr, "iou_thresh": HOG_NMS_IOU, "covered_thresh": HOG_NMS_COVERED}

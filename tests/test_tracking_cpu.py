@@ -43,6 +43,25 @@ def test_hungarian_matches_scipy():
             assert pairs == list(zip(r.tolist(), cc.tolist()))
 
 
+def test_hungarian_with_ties_is_optimal_and_deterministic():
+    """cost matrices with ties (equal overlaps, the zero padding of `_associate`).  The real `munkres`
+    package is absent, so its tie ORDER cannot be pinned; what can be: the assignment is a permutation, its total cost is
+    the optimum (scipy), it is the same on every call, and the pairs `_associate` keeps (overlap > 0 inside the real
+    block, tracking.py:176-178) have the same total overlap whichever optimal assignment is taken."""
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(1)
+    for n in (2, 3, 5, 8):
+        for _ in range(25):
+            c = rng.integers(0, 3, size=(n, n)).astype(float)       # many ties
+            k = int(rng.integers(0, n))
+            c[k:, :] = c.max()                                       # zero-overlap padding rows (cost = max - 0)
+            pairs = hungarian(c.tolist())
+            assert pairs == hungarian(c.tolist())
+            assert sorted(r for r, _ in pairs) == list(range(n)) and sorted(q for _, q in pairs) == list(range(n))
+            r, cc = linear_sum_assignment(c)
+            assert sum(c[i, j] for i, j in pairs) == c[r, cc].sum()
+
+
 def test_segment_generator_protocol():
     g = get_segment_generator([sc.Seg(0, 1.0), sc.Seg(1.0, 2.0)])
     g.send(None)
