@@ -7,6 +7,7 @@
 // All float arithmetic uses explicitly rounded, unfused operations in the same order as
 // oracle/pyramid.py so results are bit-identical.
 #include <atomic>
+#include <cstdlib>
 #include "../../include/pv_b200.h"
 #include "pv_common.cuh"
 
@@ -168,6 +169,142 @@ __global__ void __launch_bounds__(256) resize_cols_kernel(const uint8_t* __restr
       // q[ch] = 0x4B0000vv: byte0 = q0, byte1 = q1, byte2 = q2, byte3 = 255
       const uint32_t t01 = __byte_perm(q[0], q[1], 0x0040u);            // [q0.b0, q1.b0, -, -]
       const uint32_t t2a = __byte_perm(q[2], 0xFF000000u, 0x0070u);     // [q2.b0, 0xFF, -, -]
+      if (on[j]) d[256 * j] = __byte_perm(t01, t2a, 0x5410u);
+    }
+    d += dst_pitch_px;
+  }
+}
+
+// ---- the same kernel on sm_100a's packed fp32 pipe (FADD2 / FFMA2): the two columns of a thread travel as f32x2 -----------
+// Bit-identical arithmetic: a product is fma(a, b, nz) with nz = -0 passed at run time (exactly the rounded product; ptxas
+// 12.9 contracts a mul.rn.f32x2 / add.rn.f32x2 pair — and an fma with a literal -0 — into ONE FFMA2 with a single
+// rounding, even with -fmad=false), sums are add.rn.f32x2, floor(t) is add.rm.f32x2 with 2^23.  Half the FP instructions per pixel pair.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// nz = (-0, -0) arrives as a KERNEL ARGUMENT: x * y + (-0) is exactly the rounded product (sign of zero included), and
+// because ptxas cannot see the addend's value it cannot turn the fma back into a mul and contract it with the next add
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b, f2_t nz) {
+  f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+  return r;
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+  f2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2_t f2_add_rd(f2_t a, f2_t b) {
+  f2_t r;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+template <int SEL>
+__device__ __forceinline__ uint32_t pv_u8_sel_bits(uint32_t v, uint32_t magic) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(magic), "n"(0x7540 | SEL));
+  return r;
+}
+
+// horizontally interpolated source row of BOTH columns: h[ch] = omlr * S[il][ch] + lr * S[ir][ch], packed (col 0, col 1)
+template <int SRC_CH>
+__device__ __forceinline__ void hrow2(const uint8_t* __restrict__ s, const uint32_t (&il)[2], const uint32_t (&ir)[2], uint32_t off,
+                                      f2_t lr2, f2_t omlr2, uint32_t magic, f2_t nz, f2_t (&h)[3]) {
+  const f2_t m23 = f2_pack(-8388608.0f, -8388608.0f);
+  uint32_t a[2][3], b[2][3];
+  if (SRC_CH == 4) {
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(s);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t va = __ldg(s4 + il[j] + off), vb = __ldg(s4 + ir[j] + off);
+      a[j][0] = pv_u8_sel_bits<0>(va, magic); a[j][1] = pv_u8_sel_bits<1>(va, magic); a[j][2] = pv_u8_sel_bits<2>(va, magic);
+      b[j][0] = pv_u8_sel_bits<0>(vb, magic); b[j][1] = pv_u8_sel_bits<1>(vb, magic); b[j][2] = pv_u8_sel_bits<2>(vb, magic);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint8_t* pl = s + (il[j] + off) * 3u;
+      const uint8_t* pr = s + (ir[j] + off) * 3u;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        a[j][ch] = 0x4B000000u | (uint32_t)__ldg(pl + ch);
+        b[j][ch] = 0x4B000000u | (uint32_t)__ldg(pr + ch);
+      }
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const f2_t L = f2_add(f2_pack(__uint_as_float(a[0][ch]), __uint_as_float(a[1][ch])), m23);   // exact: (2^23 + v) - 2^23
+    const f2_t R = f2_add(f2_pack(__uint_as_float(b[0][ch]), __uint_as_float(b[1][ch])), m23);
+    h[ch] = f2_add(f2_mul(omlr2, L, nz), f2_mul(lr2, R, nz));
+  }
+}
+
+template <int SRC_CH>
+__global__ void __launch_bounds__(256) resize_cols2_kernel(const uint8_t* __restrict__ src, long long src_img_stride,
+                                                           int src_pitch_px, int sx0, int sy0, int sw, int sh,
+                                                           uchar4* __restrict__ dst, long long dst_img_stride, int dst_pitch_px,
+                                                           int dx0, int dy0, int dw, int dh, float xs, float ys, uint32_t magic, f2_t nz) {
+  const int c0 = blockIdx.x * (256 * kResizeCols) + threadIdx.x;
+  if (c0 >= dw) return;
+  const int r0 = blockIdx.y * kResizeRows;
+  const int r1 = min(r0 + kResizeRows, dh);
+  const uint8_t* s = src + (long long)blockIdx.z * src_img_stride;
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst) + (long long)blockIdx.z * dst_img_stride + (long long)(dy0 + r0) * dst_pitch_px + dx0 + c0;
+  uint32_t il[2], ir[2];
+  float lr[2], omlr[2];
+  bool on[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = c0 + 256 * j;
+    on[j] = c < dw;
+    const float x = __fmul_rn((float)min(c, dw - 1), xs);
+    const int left = min((int)(pv_floor_bits(x) & 0x7FFFFFu), sw - 1);
+    const int right = min(left + 1, sw - 1);
+    lr[j] = __fsub_rn(x, (float)left);
+    omlr[j] = __fsub_rn(1.0f, lr[j]);
+    il[j] = (uint32_t)(sy0 * src_pitch_px + sx0 + left);
+    ir[j] = (uint32_t)(sy0 * src_pitch_px + sx0 + right);
+  }
+  const f2_t lr2 = f2_pack(lr[0], lr[1]), omlr2 = f2_pack(omlr[0], omlr[1]);
+  const f2_t half2 = f2_pack(0.5f, 0.5f), big2 = f2_pack(8388608.0f, 8388608.0f);
+  int cur = -2;
+  f2_t hc[3], hn[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) hc[ch] = hn[ch] = 0ull;
+  for (int r = r0; r < r1; ++r) {
+    const float y = __fmul_rn((float)r, ys);
+    const int top = min((int)(pv_floor_bits(y) & 0x7FFFFFu), sh - 1);
+    const int bot = min(top + 1, sh - 1);
+    const float tb = __fsub_rn(y, (float)top), omtb = __fsub_rn(1.0f, tb);
+    if (top != cur) {                            // warp-uniform: rows depend on r only
+      if (top == cur + 1) { hc[0] = hn[0]; hc[1] = hn[1]; hc[2] = hn[2]; }
+      else hrow2<SRC_CH>(s, il, ir, (uint32_t)(top * src_pitch_px), lr2, omlr2, magic, nz, hc);
+      if (bot == top) { hn[0] = hc[0]; hn[1] = hc[1]; hn[2] = hc[2]; }
+      else hrow2<SRC_CH>(s, il, ir, (uint32_t)(bot * src_pitch_px), lr2, omlr2, magic, nz, hn);
+      cur = top;
+    }
+    const f2_t tb2 = f2_pack(tb, tb), omtb2 = f2_pack(omtb, omtb);
+    uint32_t q[2][3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const f2_t v = f2_add(f2_mul(omtb2, hc[ch], nz), f2_mul(tb2, hn[ch], nz));
+      float v0, v1;
+      f2_unpack(f2_add(v, half2), v0, v1);
+      // floor(v + 0.5) clamped to [0, 255]: v >= 0, so only the upper clamp can bind
+      float f0, f1;
+      f2_unpack(f2_add_rd(f2_pack(fminf(v0, 255.5f), fminf(v1, 255.5f)), big2), f0, f1);
+      q[0][ch] = __float_as_uint(f0);
+      q[1][ch] = __float_as_uint(f1);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t t01 = __byte_perm(q[j][0], q[j][1], 0x0040u);
+      const uint32_t t2a = __byte_perm(q[j][2], 0xFF000000u, 0x0070u);
       if (on[j]) d[256 * j] = __byte_perm(t01, t2a, 0x5410u);
     }
     d += dst_pitch_px;
@@ -428,10 +565,24 @@ extern "C" int pv_resize_bilinear(const void* src, int src_channels, int64_t src
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!copy_only) {
     const dim3 cb((unsigned)((dw + 256 * kResizeCols - 1) / (256 * kResizeCols)), (unsigned)((dh + kResizeRows - 1) / kResizeRows), (unsigned)B);
-    if (src_channels == 3)
+    // PV_RESIZE_PACKED=0 selects the scalar-fp32 kernel (same results bit for bit; the packed one halves the FP instructions)
+    static int packed = -1;
+    if (packed < 0) {
+      const char* e = getenv("PV_RESIZE_PACKED");
+      packed = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (src_channels == 3 && packed)
+      resize_cols2_kernel<3><<<cb, 256, 0, s>>>(static_cast<const uint8_t*>(src), src_img_stride, src_pitch_px, sx0, sy0, sw,
+                                                sh, static_cast<uchar4*>(dst_rgba), dst_img_stride_px, dst_pitch_px, dx0, dy0,
+                                                dw, dh, xs, ys, 0x4B000000u, 0x8000000080000000ull);
+    else if (src_channels == 3)
       resize_cols_kernel<3><<<cb, 256, 0, s>>>(static_cast<const uint8_t*>(src), src_img_stride, src_pitch_px, sx0, sy0, sw,
                                                sh, static_cast<uchar4*>(dst_rgba), dst_img_stride_px, dst_pitch_px, dx0, dy0,
                                                dw, dh, xs, ys, 0x4B000000u);
+    else if (packed)
+      resize_cols2_kernel<4><<<cb, 256, 0, s>>>(static_cast<const uint8_t*>(src), src_img_stride, src_pitch_px, sx0, sy0, sw,
+                                                sh, static_cast<uchar4*>(dst_rgba), dst_img_stride_px, dst_pitch_px, dx0, dy0,
+                                                dw, dh, xs, ys, 0x4B000000u, 0x8000000080000000ull);
     else
       resize_cols_kernel<4><<<cb, 256, 0, s>>>(static_cast<const uint8_t*>(src), src_img_stride, src_pitch_px, sx0, sy0, sw,
                                                sh, static_cast<uchar4*>(dst_rgba), dst_img_stride_px, dst_pitch_px, dx0, dy0,

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Summarise an `ncu --set full` report into a small CSV (the committed evidence under profiles/).
-usage: python scripts/ncu_summary.py gpurun_out/x.ncu-rep profiles/x_summary.csv"""
+"""Summarise an `ncu --set full` capture into a small CSV (the committed evidence under profiles/).
+usage: python scripts/ncu_summary.py <x.ncu-rep | x_raw.csv (ncu -i x.ncu-rep --page raw --csv)> profiles/x_summary.csv"""
 import csv
 import subprocess
 import sys
@@ -11,14 +11,19 @@ KEYS = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+        "sm__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max"]
 
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
