@@ -62,8 +62,8 @@ def main():
     counts_all = rng.integers(2, 7, size=a.frames)
     counts = counts_all[lo:hi]
     n_faces = int(counts.sum())
-    emb_all = torch.empty(n_faces, 128, dtype=torch.float32, device=dev)
-    trk_all = torch.empty(n_faces, dtype=torch.int64, device=dev)
+    emb_all = torch.zeros(n_faces, 128, dtype=torch.float32, device=dev)
+    trk_all = torch.zeros(n_faces, dtype=torch.int64, device=dev)   # (uninitialised ids overflowed rank * stride in the warm-up gather at N = 8)
     # boxes of every batch, prepared before the timed region (in `extract` they come from the track file)
     batches = []
     off = 0
