@@ -403,6 +403,12 @@ def main():
     ms_max = float(t.item())
     det0.check()
     face.face_recognition_.check()
+    if os.environ.get("PV_BENCH_DEBUG") and use_tracker:
+        st_ = bank.read_state(trk_ids).float().cpu()
+        wd_ = st_[:, 2] - st_[:, 0]
+        sys.stderr.write("[bench debug] tracker state after the resident leg: |coord| max %.4g, width %.4g..%.4g, psr %.4g..%.4g, finite %s\n"
+                         % (float(st_[:, :4].abs().max()), float(wd_.min()), float(wd_.max()), float(st_[:, 4].min()),
+                            float(st_[:, 4].max()), bool(torch.isfinite(st_).all())))
 
     # ---------------- end-to-end timing (host buffers, H2D + D2H inside) ----------------
     run_e2e(min(max(args.warmup, 1), 2))
@@ -571,5 +577,30 @@ def main():
         dist.destroy_process_group()
 
 
+def main_guarded():
+    """Single-GPU runs execute the measurement in a child process and repeat it (at most twice) if the child dies:
+    one of seven otherwise identical runs of this round aborted with a CUDA illegal-address error in the e2e leg
+    (profiles/README.md, gpurun #84; not reproduced since, root cause open — the chip / tracker samplers were hardened
+    against non-finite coordinates afterwards).  A repeat is reported in the JSON line as "retries".  Multi-rank
+    (torchrun) runs, --impl reference and PV_BENCH_NO_RETRY=1 run in-process."""
+    if (int(os.environ.get("WORLD_SIZE", "1")) > 1 or "--impl" in sys.argv or os.environ.get("PV_BENCH_NO_RETRY")
+            or os.environ.get("PV_BENCH_CHILD")):
+        return main()
+    env = dict(os.environ, PV_BENCH_CHILD="1")
+    for attempt in range(3):
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, stdout=subprocess.PIPE, text=True)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode == 0 and lines:
+            line = json.loads(lines[-1])
+            line["retries"] = attempt
+            print(json.dumps(line), flush=True)
+            return
+        if r.returncode >= 0 and r.returncode != 134:
+            sys.stdout.write(r.stdout)                     # an ordinary failure (no device, bad arguments): not repeated
+            raise SystemExit(r.returncode)
+        sys.stderr.write("bench.py: attempt %d died (exit code %d); repeating\n" % (attempt + 1, r.returncode))
+    raise SystemExit("bench.py: the measurement died three times")
+
+
 if __name__ == "__main__":
-    main()
+    main_guarded()

@@ -668,7 +668,7 @@ static double update_one(Bank& bk, Track& tk, const uint8_t* rgb, int H, int W) 
     double p = pk;
     if (pk > 0 && pk < NSC - 1) {
       const double d = r[pk - 1] - 2 * r[pk] + r[pk + 1];
-      if (d != 0) p += 0.5 * (r[pk - 1] - r[pk + 1]) / d;
+      if (d != 0) p += std::min(1.0, std::max(-1.0, 0.5 * (r[pk - 1] - r[pk + 1]) / d));   // stays inside [pk - 1, pk + 1] (dlib lagrange_poly_min_extrap)
     }
     const double f = std::pow(1.020, p - NSC / 2);
     const double ccx = 0.5 * (tk.pos[0] + tk.pos[2]), ccy = 0.5 * (tk.pos[1] + tk.pos[3]);

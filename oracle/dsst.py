@@ -312,7 +312,8 @@ class CorrelationTracker(object):
         if 0 < pk < N_SCALES - 1:
             d = r[pk - 1] - 2 * r[pk] + r[pk + 1]
             if d != 0:
-                p += 0.5 * (r[pk - 1] - r[pk + 1]) / d
+                # dlib's 1-D max_point_interpolated (lagrange_poly_min_extrap) stays inside [pk - 1, pk + 1]
+                p += float(np.clip(0.5 * (r[pk - 1] - r[pk + 1]) / d, -1.0, 1.0))
         self.position = scale_rect(self.position, SCALE_ALPHA ** (p - N_SCALES // 2))
         Gs = np.conj(np.fft.fft(scale_target(p).astype(np.float64)))
         self.As = (1 - SCALE_NU) * self.As + SCALE_NU * (Gs[None] * Fs)

@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(256) chip_kernel(const uint8_t* __restrict__ f
     const float y = __fadd_rn(__fadd_rn(__fmul_rn(sm.m10, fc), __fmul_rn(sm.m11, fr)), sm.ty);
     const int left = (int)floorf(x), top = (int)floorf(y);
     uchar4 o = make_uchar4(0, 0, 0, 255);
-    if (left >= 0 && top >= 0 && left + 1 < W && top + 1 < H) {
+    // left >= 0 && left + 1 < W on the floats: a degenerate similarity fit (inf / NaN / beyond int range) must read nothing
+    if (x >= 0.f && y >= 0.f && x < (float)(W - 1) && y < (float)(H - 1)) {
       const float lr = __fsub_rn(x, (float)left), tb = __fsub_rn(y, (float)top);
       const float omlr = __fsub_rn(1.0f, lr), omtb = __fsub_rn(1.0f, tb);
       const uint8_t* ptl = img + ((long long)top * W + left) * 3;

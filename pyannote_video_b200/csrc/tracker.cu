@@ -160,7 +160,8 @@ __device__ void features_prepare(const BankParams& p, const TrackerTables& tb, c
     const float fx = __fadd_rn(rl, __fmul_rn((float)x, sx)), fy = __fadd_rn(rt, __fmul_rn((float)y, sy));
     const int left = (int)floorf(fx), top = (int)floorf(fy);
     uint8_t o[3] = {0, 0, 0};
-    if (left >= 0 && left + 1 < p.W && top >= 0 && top + 1 < p.H) {
+    // left >= 0 && left + 1 < W, tested on the floats: a runaway box (inf / NaN / beyond int range) must read nothing
+    if (fx >= 0.f && fx < (float)(p.W - 1) && fy >= 0.f && fy < (float)(p.H - 1)) {
       const float lr = __fsub_rn(fx, (float)left), tbv = __fsub_rn(fy, (float)top);
       const float omlr = __fsub_rn(1.0f, lr), omtb = __fsub_rn(1.0f, tbv);
       const uint8_t* ptl = p.frame + ((long long)top * p.W + left) * 3;
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(kThreads, 2) tracker_scale_kernel(ScaleParams 
       const float fx = __fadd_rn(lk, __fmul_rn((float)x, sx)), fy = __fadd_rn(tk, __fmul_rn((float)y, sy));
       const int left = (int)floorf(fx), top = (int)floorf(fy);
       uint8_t o[3] = {0, 0, 0};
-      if (left >= 0 && left + 1 < p.W && top >= 0 && top + 1 < p.H) {
+      if (fx >= 0.f && fx < (float)(p.W - 1) && fy >= 0.f && fy < (float)(p.H - 1)) {   // overflow-safe form of left >= 0 && left + 1 < W
         const float lr = __fsub_rn(fx, (float)left), tbv = __fsub_rn(fy, (float)top);
         const float omlr = __fsub_rn(1.0f, lr), omtb = __fsub_rn(1.0f, tbv);
         const uint8_t* ptl = p.frame + ((long long)top * p.W + left) * 3;
@@ -825,7 +826,8 @@ __global__ void __launch_bounds__(kThreads, 2) tracker_scale_kernel(ScaleParams 
       if (pk > 0 && pk < NS - 1) {
         const double c = s_resp[pk], a = s_resp[pk - 1], d2 = s_resp[pk + 1];
         const double den = a - 2 * c + d2;
-        if (den != 0) pp += 0.5 * (a - d2) / den;
+        // dlib's 1-D max_point_interpolated (lagrange_poly_min_extrap) stays inside [pk - 1, pk + 1]
+        if (den != 0) pp += fmin(1.0, fmax(-1.0, 0.5 * (a - d2) / den));
       }
       const double f = pow(tb.alpha, pp - NS / 2);
       const double dl = l, dt = t, dr = r, db = b;
