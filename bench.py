@@ -587,6 +587,11 @@ def main_guarded():
             or os.environ.get("PV_BENCH_CHILD")):
         return main()
     env = dict(os.environ, PV_BENCH_CHILD="1")
+    try:                                     # build once here (the child finds the library up to date) and map it in this process too
+        import __graft_entry__ as ge
+        ge.build()
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write("bench.py: build failed in the parent process: %r\n" % (e, ))
     for attempt in range(3):
         r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, stdout=subprocess.PIPE, text=True)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
