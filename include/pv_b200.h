@@ -230,6 +230,26 @@ int pv_c12_check(void* handle, void* stream);
 int pv_c12_debug(void* handle, long long* out16);
 
 /* ------------------------------------------------------------------------------------------
+ * host-side tracking control in C++ (csrc/control.cu, no device code): the per-frame
+ * association and the per-shot link graph of TrackingByDetection — pyannote/video/tracking.py:129-182 (_match,
+ * _associate: overlap matrix with the min-overlap rule, Munkres on max - overlap, pairs with overlap > 0),
+ * :209-244,340-347 (link graph, connected components in node insertion order), :261-296 (_fix) and :298-329
+ * (_fill_gaps).  Rectangles are drectangles (l,t,r,b doubles, area (r-l)(b-t)); status codes 0 forward, 1 detection,
+ * 2 backward.
+ * ------------------------------------------------------------------------------------------ */
+/* match[d] = index of the tracker associated with detection d, or -1 */
+int pv_ctl_associate(const double* positions, int n_trackers, const double* detections, int n_detections,
+                     double min_overlap_ratio, int* match);
+int pv_ctl_shot_create(void** out_handle);
+int pv_ctl_shot_destroy(void* handle);
+int pv_ctl_shot_add(void* handle, double t, const double* box, int status);
+int pv_ctl_shot_link(void* handle, double ta, const double* box_a, int sa, double tb, const double* box_b, int sb);
+/* components -> _fix -> _fill_gaps -> sorted by (first, last time): sizes first, then the rows */
+int pv_ctl_shot_finish(void* handle, double min_overlap_ratio, double max_gap, int* n_tracks, int* n_rows);
+/* track_len [n_tracks]; per row: time, integer box (l,t,r,b), counts {forward, detection, backward, error flag} */
+int pv_ctl_shot_tracks(void* handle, int* track_len, double* row_t, long long* row_box, int* row_counts);
+
+/* ------------------------------------------------------------------------------------------
  * HOG frontal face detector (csrc/hog.cu): dlib.get_frontal_face_detector()(rgb, 1), the detector the reference
  * really calls (pyannote/video/face/face.py:54,66).  Input = the tiled pyramid plane of pv_resize_bilinear /
  * pv_pyramid_tail; per usable level (both sides >= 80 px) a table entry.  pv_hog_features writes the 31-channel

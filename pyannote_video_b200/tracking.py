@@ -118,6 +118,66 @@ class _LinkGraph(object):
         return [groups[r] for r in sorted(groups)]   # root = smallest index = first inserted node
 
 
+_STATUS_CODE = {FORWARD: 0, DETECTION: 1, BACKWARD: 2}
+
+
+class _NativeGraph(object):
+    """the shot's link graph in C++ (csrc/control.cu): same add / link protocol as _LinkGraph; `tracks()` runs the
+    connected components, _fix, _fill_gaps and the final sort natively"""
+
+    def __init__(self):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self.h = C.c_void_p()
+        _lib.check(_lib.lib().pv_ctl_shot_create(C.byref(self.h)), "pv_ctl_shot_create")
+
+    def _box(self, box):
+        return (self._C.c_double * 4)(*[float(v) for v in box])
+
+    def add(self, node):
+        t, box, status = node
+        self._lib.check(self._lib.lib().pv_ctl_shot_add(self.h, self._C.c_double(t), self._box(box), _STATUS_CODE[status]),
+                        "pv_ctl_shot_add")
+
+    def link(self, a, b):
+        C = self._C
+        self._lib.check(self._lib.lib().pv_ctl_shot_link(self.h, C.c_double(a[0]), self._box(a[1]), _STATUS_CODE[a[2]],
+                                                         C.c_double(b[0]), self._box(b[1]), _STATUS_CODE[b[2]]),
+                        "pv_ctl_shot_link")
+
+    def tracks(self, min_overlap_ratio, max_gap):
+        C, L = self._C, self._lib.lib()
+        nt, nr = C.c_int(), C.c_int()
+        self._lib.check(L.pv_ctl_shot_finish(self.h, C.c_double(min_overlap_ratio), C.c_double(max_gap), C.byref(nt), C.byref(nr)),
+                        "pv_ctl_shot_finish")
+        lens = (C.c_int * max(nt.value, 1))()
+        ts = (C.c_double * max(nr.value, 1))()
+        boxes = (C.c_longlong * (4 * max(nr.value, 1)))()
+        counts = (C.c_int * (4 * max(nr.value, 1)))()
+        self._lib.check(L.pv_ctl_shot_tracks(self.h, lens, ts, boxes, counts), "pv_ctl_shot_tracks")
+        out, r = [], 0
+        for k in range(nt.value):
+            track = []
+            for _ in range(lens[k]):
+                nf, nd, nb, err = counts[4 * r:4 * r + 4]
+                status = "+".join([FORWARD] * nf + [DETECTION] * nd + [BACKWARD] * nb)
+                if err:
+                    status = "error({0})".format(status)
+                track.append((ts[r], (boxes[4 * r], boxes[4 * r + 1], boxes[4 * r + 2], boxes[4 * r + 3]), status))
+                r += 1
+            out.append(track)
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self._lib.lib().pv_ctl_shot_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class TrackingByDetection(object):
     """(Forward/backward) tracking by detection
 
@@ -141,11 +201,16 @@ class TrackingByDetection(object):
     tracker_bank : object, optional
         Correlation-tracker bank (start/update/position/release/reset).  Defaults to the CUDA
         `TrackerBank` of this package.
+    control : "python" | "native", optional
+        Where the per-frame association (overlap matrix + Munkres) and the per-shot link graph (components, `_fix`,
+        `_fill_gaps`) run: in this file, or in C++ (`csrc/control.cu`, `pv_ctl_*`).  Both give identical tracks
+        (tests/test_tracking_cpu.py: the reference's golden scenarios and random ones); default: `PV_TRACK_CONTROL`
+        or "python".
     """
 
     def __init__(self, detect_func, detect_smallest=1, detect_min_size=0., detect_every=0.,
                  track_min_confidence=10., track_min_overlap_ratio=0.3, track_max_gap=0.,
-                 tracker_bank=None, prepare_frame=None):
+                 tracker_bank=None, prepare_frame=None, control=None):
         super(TrackingByDetection, self).__init__()
         self.detect_func = detect_func
         self.detect_smallest = detect_smallest
@@ -157,6 +222,10 @@ class TrackingByDetection(object):
         self._hungarian = Munkres()
         self._bank = tracker_bank
         self._prepare_frame = prepare_frame
+        import os
+        self.control = control or os.environ.get("PV_TRACK_CONTROL", "python")
+        if self.control not in ("python", "native"):
+            raise ValueError("control must be 'python' or 'native'")
 
     # ------------------------------------------------------------------ helpers
     def _get_bank(self):
@@ -178,6 +247,16 @@ class TrackingByDetection(object):
         n_trackers, n_detections = len(positions), len(detections)
         if n_trackers < 1 or n_detections < 1:
             return dict()
+        if self.control == "native":
+            import ctypes as C
+            from . import _lib
+            pos = (C.c_double * (4 * n_trackers))(*[v for p in positions for v in (p.left(), p.top(), p.right(), p.bottom())])
+            det = (C.c_double * (4 * n_detections))(*[float(v) for d in detections for v in d])
+            out = (C.c_int * n_detections)()
+            _lib.check(_lib.lib().pv_ctl_associate(pos, n_trackers, det, n_detections, C.c_double(self.track_min_overlap_ratio), out),
+                       "pv_ctl_associate")
+            # same insertion order as the Python path (pairs sorted by tracker index)
+            return {d: t for t, d in sorted((out[d], d) for d in range(n_detections) if out[d] >= 0)}
         n = max(n_trackers, n_detections)
         overlap_area = np.zeros((n, n))
         for t, position in enumerate(positions):
@@ -288,6 +367,10 @@ class TrackingByDetection(object):
     def _forward_backward(self):
         self._track(direction=FORWARD)
         self._track(direction=BACKWARD)
+        if self.control == "native":
+            for track in self._graph.tracks(self.track_min_overlap_ratio, self.track_max_gap):
+                yield track
+            return
         tracks = [self._fix(track) for track in self._graph.components()]
         tracks = self._fill_gaps(tracks)
         for track in sorted(tracks, key=get_min_max_t):
@@ -295,7 +378,7 @@ class TrackingByDetection(object):
 
     def _reset(self):
         self._frame_cache = []
-        self._graph = _LinkGraph()
+        self._graph = _NativeGraph() if self.control == "native" else _LinkGraph()
         self._detections = {}
 
     def _normalize_track(self, track, frame_width, frame_height):
