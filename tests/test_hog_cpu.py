@@ -72,3 +72,21 @@ def test_feature_plane_layout():
         assert b0 - a1 >= GAP                       # tiles at least one filter apart
     assert rows[-1][1] + GAP <= g.FH
     assert g.total_feat == sum((g.lv[k].cx - 2) * (g.lv[k].cy - 2) for k in range(g.n_levels))
+
+
+def test_oracle_matches_committed_golden():
+    """regression pin of the restatement (tests/golden/make_hog_golden.py)"""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_hog_golden as mk
+    g = np.load(os.path.join(here, "golden", "hog_golden.npz"))
+    img, filt = mk.inputs()
+    feat = hog.fhog_features(hog.fhog_hist(img))
+    assert np.array_equal(feat, g["feat"])
+    sc = hog.score_maps(feat, filt)
+    assert np.allclose(sc, g["scores"], rtol=0, atol=1e-5)
+    boxes, scores, which = hog.detect_levels([img], filt, [float(g["thr"])] * filt.shape[0], upsampled=True)
+    assert np.array_equal(np.asarray(boxes, np.int32), g["boxes"]) and list(which) == g["which"].tolist()
+    assert np.allclose(scores, g["det_scores"], atol=1e-5)
