@@ -131,7 +131,8 @@ def face_generator(tracking, frame_width, frame_height, reference_quirks=False):
 
 
 def track(video, shot, output, detect_min_size=0.0, detect_every=0.0, track_min_overlap_ratio=MIN_OVERLAP_RATIO,
-          track_min_confidence=MIN_CONFIDENCE, track_max_gap=MAX_GAP, face=None, tracker_bank=None, detector=None):
+          track_min_confidence=MIN_CONFIDENCE, track_max_gap=MAX_GAP, face=None, tracker_bank=None, detector=None,
+          control=None):
     """Tracking by detection"""
     from .tracking import FaceTracking
     if face is None:
@@ -140,7 +141,7 @@ def track(video, shot, output, detect_min_size=0.0, detect_every=0.0, track_min_
     tracking = FaceTracking(detect_min_size=detect_min_size, detect_every=detect_every,
                             track_min_overlap_ratio=track_min_overlap_ratio,
                             track_min_confidence=track_min_confidence, track_max_gap=track_max_gap, face=face,
-                            tracker_bank=tracker_bank)
+                            tracker_bank=tracker_bank, control=control)
     shots = load_shots(shot) if isinstance(shot, str) else shot
     with open(output, 'w') as foutput:
         for identifier, trk in enumerate(tracking(video, shots)):
@@ -210,9 +211,13 @@ def main(argv=None):
                                  formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--frame-rate", type=float, default=25.0)
+    ap.add_argument("--control", default=None, choices=["python", "native"],
+                    help="tracking control loop (association, link graph, _fix, _fill_gaps): this package's Python or the C++ "
+                         "of csrc/control.cu — identical tracks (default: $PV_TRACK_CONTROL or python)")
     ap.add_argument("--detector", default=None,
-                    help="CNN (MMOD) detector model: mmod_human_face_detector.dat, an .npz container, or 'synthetic' "
-                         "(default: $PYANNOTE_FACE_DETECTOR)")
+                    help="detector model: CNN (MMOD) — mmod_human_face_detector.dat or an .npz container — or a HOG model "
+                         "(.npz of kind 'hog_detector', the reference's detector family); 'synthetic' / 'synthetic-hog' "
+                         "select the seeded random-weight detectors of the tests (default: $PYANNOTE_FACE_DETECTOR)")
     sub = ap.add_subparsers(dest="verb", required=True)
     p = sub.add_parser("track")
     p.add_argument("video")
@@ -244,7 +249,7 @@ def main(argv=None):
     if a.verb == "track":
         track(open_video(a.video, a.frame_rate), a.shot, a.tracking, detect_min_size=a.min_size, detect_every=a.every,
               track_min_overlap_ratio=a.min_overlap, track_min_confidence=a.min_confidence, track_max_gap=a.max_gap,
-              detector=a.detector)
+              detector=a.detector, control=a.control)
     elif a.verb in ("extract", "embed"):
         extract(open_video(a.video, a.frame_rate), a.landmark_model, a.embedding_model, a.tracking, a.landmarks,
                 a.embeddings, reference_quirks=a.reference_quirks)

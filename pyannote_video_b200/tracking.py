@@ -447,10 +447,11 @@ class FaceTracking(TrackingByDetection):
     """Face tracking (same parameters as pyannote/video/face/tracking.py:45-78)"""
 
     def __init__(self, detect_min_size=0., detect_every=0., track_min_confidence=10., track_min_overlap_ratio=0.3,
-                 track_max_gap=0., face=None, tracker_bank=None):
+                 track_max_gap=0., face=None, tracker_bank=None, control=None):
         from .face import Face, DLIB_SMALLEST_FACE
         face = face if face is not None else Face()
         super(FaceTracking, self).__init__(
             detect_func=get_face_detect(face), detect_smallest=DLIB_SMALLEST_FACE, detect_min_size=detect_min_size,
             detect_every=detect_every, track_min_confidence=track_min_confidence,
-            track_min_overlap_ratio=track_min_overlap_ratio, track_max_gap=track_max_gap, tracker_bank=tracker_bank)
+            track_min_overlap_ratio=track_min_overlap_ratio, track_max_gap=track_max_gap, tracker_bank=tracker_bank,
+            control=control)
