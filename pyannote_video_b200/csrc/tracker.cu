@@ -2,7 +2,7 @@
 // ONE launch.  Replaces dlib.correlation_tracker.start_track / update / get_position called per
 // tracker per frame from Python (pyannote/video/tracking.py:203,231,250-251).
 //
-// Per track state in HBM (float32): A[31][33x64] complex numerators (half plane: the spectra of real features are
+// Per track state in HBM (float32): A[32][33x64] complex numerators (31 FHOG planes + the brightness plane) (half plane: the spectra of real features are
 // Hermitian), B[33x64] denominator, position (l,t,r,b).  update = chip (bilinear, rect*1.4 -> 64x64) -> FHOG-31 (cell 1)
 // x cosine window -> 16 packed 2-D FFTs (shared memory, radix-8) -> response = ifft2(sum F_i conj(A_i)/(B+lambda))
 // -> argmax / sub-pixel / PSR (warp-shuffle + shared reductions) -> position -> filter update from the spectra that
@@ -303,7 +303,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // pass 2 (the filter update, which needs the peak found by pass 1) streams them back instead of redoing 16 transforms.
 // Every thread owns the same bins (h = tid + 512 k, k < 4, plus h = 2048 + tid for tid < 64) for the whole kernel: the
 // response accumulator and conj(G^) live in registers, the spilled spectra are re-read by the thread that wrote them (no
-// synchronisation), the CTA needs 95 KB of shared memory and two CTAs (two tracks) share an SM.
+// synchronisation), the CTA needs 106 KB of shared memory and two CTAs (two tracks) share an SM.
 constexpr int NHB = 33 * FS;          // stored half-plane bins per channel
 constexpr int NB = 5;                 // bins per thread (the fifth only for tid < 64)
 
