@@ -40,6 +40,11 @@ def gather_embeddings(emb, track_ids, group=None):
     dist.all_gather(counts, n, group=group)
     sizes = [int(c[0].item()) for c in counts]
     stride = max(int(c[1].item()) for c in counts)
+    if track_ids.numel() and int(track_ids.min().item()) < 0:
+        raise ValueError("gather_embeddings: negative track id")
+    if stride * world >= 2 ** 62:
+        raise ValueError("gather_embeddings: track ids up to %d cannot be made unique over %d ranks in int64 "
+                         "(uninitialised ids?)" % (stride - 1, world))
     nmax = max(sizes)
     pad_e = torch.zeros(nmax, emb.shape[1], dtype=emb.dtype, device=dev)
     pad_t = torch.zeros(nmax, dtype=torch.int64, device=dev)
